@@ -1,0 +1,108 @@
+"""ctypes binding of libmalstroem_b200.so (include/malstroem_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is present when a
+function is called, the call raises.
+"""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmalstroem_b200.so")
+
+MS_F32, MS_F64, MS_U8, MS_I32, MS_I64 = 0, 1, 2, 3, 4
+DTYPE_CODE = {np.dtype(np.float32): MS_F32, np.dtype(np.float64): MS_F64, np.dtype(np.uint8): MS_U8,
+              np.dtype(np.bool_): MS_U8, np.dtype(np.int32): MS_I32, np.dtype(np.int64): MS_I64}
+
+ERR_CUDA, ERR_ARG, ERR_SHAPE, ERR_LABEL, ERR_NOCONV = -1, -2, -3, -4, -5
+
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_dbl = ctypes.c_double
+c_p = ctypes.c_void_p
+
+# every exported symbol of include/malstroem_b200.h: (restype, argtypes)
+SIGNATURES = {
+    "ms_version": (c_int, []),
+    "ms_init": (c_int, [c_int]),
+    "ms_shutdown": (c_int, []),
+    "ms_last_error": (ctypes.c_char_p, []),
+    "ms_device_count": (c_int, []),
+    "ms_kernel_launches": (c_i64, [c_int]),
+    "ms_host_alloc": (c_p, [c_i64]),
+    "ms_host_free": (c_int, [c_p]),
+    "ms_fill_terrain": (c_int, [c_p, c_p, c_p, c_i64, c_i64]),
+    "ms_fill_terrain_dev": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_p]),
+    "ms_minmax_f32": (c_int, [c_p, c_i64, c_p, c_p]),
+    "ms_minmax_f32_dev": (c_int, [c_p, c_i64, c_p, c_p]),
+    "ms_fill_terrain_no_flats": (c_int, [c_p, c_dbl, c_dbl, c_p, c_i64, c_i64]),
+    "ms_fill_terrain_no_flats_dev": (c_int, [c_p, c_p, c_dbl, c_dbl, c_p, c_i64, c_i64, c_p, c_p]),
+    "ms_flowdir": (c_int, [c_p, c_p, c_i64, c_i64, c_int]),
+    "ms_flowdir_dev": (c_int, [c_p, c_p, c_i64, c_i64, c_int, c_p]),
+    "ms_accumulated_flow": (c_int, [c_p, c_p, c_i64, c_i64]),
+    "ms_accumulated_flow_dev": (c_int, [c_p, c_p, c_i64, c_i64, c_p]),
+    "ms_watersheds_from_labels": (c_int, [c_p, c_p, c_int, c_i64, c_i64, c_i64]),
+    "ms_watersheds_from_labels_dev": (c_int, [c_p, c_p, c_int, c_i64, c_i64, c_i64, c_p]),
+    "ms_connected_components": (c_int, [c_p, c_int, c_p, c_i64, c_i64, c_p]),
+    "ms_connected_components_dev": (c_int, [c_p, c_int, c_p, c_i64, c_i64, c_p, c_p]),
+    "ms_label_range": (c_int, [c_p, c_i64, c_p, c_p]),
+    "ms_label_range_dev": (c_int, [c_p, c_i64, c_p, c_p]),
+    "ms_label_stats": (c_int, [c_p, c_int, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p]),
+    "ms_label_stats_dev": (c_int, [c_p, c_int, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p]),
+    "ms_label_extreme_index": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_int, c_p, c_p, c_p]),
+    "ms_label_extreme_index_dev": (c_int, [c_p, c_p, c_i64, c_i64, c_i64, c_int, c_p, c_p, c_p, c_p]),
+    "ms_label_count": (c_int, [c_p, c_i64, c_i64, c_p]),
+    "ms_label_count_dev": (c_int, [c_p, c_i64, c_i64, c_p, c_p]),
+    "ms_keep_labels": (c_int, [c_p, c_i64, c_p, c_i64, c_p]),
+    "ms_keep_labels_dev": (c_int, [c_p, c_i64, c_p, c_i64, c_p, c_p]),
+    "ms_pipeline_dev": (c_int, [c_p, c_p]),
+    "ms_synth_fractal_dev": (c_int, [c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_p]),
+}
+
+
+class MsRasters(ctypes.Structure):
+    """struct ms_rasters of include/malstroem_b200.h"""
+    _fields_ = [("rows", c_i64), ("cols", c_i64),
+                ("dem", c_p), ("filled", c_p), ("depths", c_p), ("fnf", c_p), ("flowdir", c_p), ("accum", c_p),
+                ("labels", c_p), ("wsheds", c_p),
+                ("table_capacity", c_i64),
+                ("st_min", c_p), ("st_max", c_p), ("st_sum", c_p), ("st_count", c_p), ("ws_count", c_p),
+                ("ppmin_value", c_p), ("ppmin_row", c_p), ("ppmin_col", c_p),
+                ("ppmax_value", c_p), ("ppmax_row", c_p), ("ppmax_col", c_p),
+                ("nlabels", c_i64), ("short_eps", c_dbl), ("diag_eps", c_dbl), ("stats", c_i64 * 8)]
+
+
+_lib = None
+lock = threading.RLock()      # ctypes drops the GIL; the library keeps per-process state
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("malstroem_b200: %s is missing — build it with `python malstroem_b200/build.py` "
+                              "(there is no CPU fallback)" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc == 0:
+        return
+    msg = lib().ms_last_error().decode("utf-8", "replace")
+    if rc in (ERR_ARG, ERR_SHAPE):
+        raise ValueError("%s: %s" % (what, msg))
+    if rc == ERR_LABEL:
+        raise IndexError("%s: %s" % (what, msg))
+    raise RuntimeError("%s: %s (code %d)" % (what, msg, rc))
+
+
+def ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)

@@ -1,0 +1,128 @@
+// common.cuh — shared helpers of the sm_100a raster kernels (error handling, stream-ordered scratch
+// memory, order-preserving float keys, D8 neighbour tables).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/malstroem_b200.h"
+
+namespace ms {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern int64_t g_launches;
+
+#define MS_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            ms::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return MS_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define MS_TRY(call)                \
+    do {                            \
+        int r__ = (call);           \
+        if (r__ != MS_OK) return r__; \
+    } while (0)
+
+// kernel launch + error check + launch counter
+#define MS_LAUNCH(kernel, grid, block, smem, stream, ...)                                    \
+    do {                                                                                     \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
+        ms::g_launches++;                                                                    \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess) {                                                            \
+            ms::set_error("%s:%d: launch %s -> %s", __FILE__, __LINE__, #kernel,             \
+                          cudaGetErrorString(e__));                                          \
+            return MS_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+int ensure_init();
+
+// ---- stream-ordered scratch buffer (cudaMallocAsync pool; freed in stream order) -----------------
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    cudaStream_t s = nullptr;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    int alloc(size_t n, cudaStream_t stream) {
+        release();
+        s = stream;
+        if (n == 0) n = 1;
+        cudaError_t e = cudaMallocAsync((void **)&p, n * sizeof(T), stream);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMallocAsync(%zu bytes) -> %s", n * sizeof(T), cudaGetErrorString(e));
+            return MS_ERR_CUDA;
+        }
+        return MS_OK;
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+    }
+    ~DevBuf() { release(); }
+    operator T *() const { return p; }
+};
+
+// pinned host scalar(s) for flags / counters that come back every round
+struct HostFlags {
+    int64_t *h = nullptr;
+    int init();
+};
+HostFlags &host_flags();
+
+static inline unsigned int cdiv(int64_t a, int64_t b) { return (unsigned int)((a + b - 1) / b); }
+
+// ---- order-preserving keys ----------------------------------------------------------------------
+// okey(a) < okey(b)  <=>  a < b  for non-NaN floats, with -0.0 canonicalised to +0.0
+__host__ __device__ inline uint32_t okey32(float f) {
+    f = f + 0.0f;
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } v; v.f = f; uint32_t b = v.u;
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ inline float okey32_inv(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    union { float f; uint32_t u; } v; v.u = b; return v.f;
+#endif
+}
+__device__ inline unsigned long long okey64(double d) {
+    d = d + 0.0;
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ inline double okey64_inv(unsigned long long k) {
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// ---- D8 neighbour order of the reference (flow.py:30-38, _flow.pyx:36-46):
+//      0 Up, 1 UpRight, 2 Right, 3 DownRight, 4 Down, 5 DownLeft, 6 Left, 7 UpLeft, 8 none
+__device__ __constant__ const int kDR[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+__device__ __constant__ const int kDC[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+
+// ---- shared device primitives (scan.cu, forest.cu) ----------------------------------------------
+// exclusive scan of int32 flags; out may alias flags; *total_dev receives the sum (int64 on device)
+int exclusive_scan_i32(const int *flags, int *out, int64_t n, int64_t *total_dev, cudaStream_t s);
+// pointer jumping on a forest given as parent indices (roots point to themselves); in place.
+// rounds_out (host, optional) receives the number of rounds.  MS_ERR_NOCONV after 64 rounds (cycles).
+int forest_resolve(int *ptr, int64_t n, int64_t *rounds_out, cudaStream_t s);
+
+// internal device-pointer stage entry points used by the pipeline (pipeline.cu)
+int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_t rows, int64_t cols,
+                          int64_t *stats, cudaStream_t s);
+
+}  // namespace ms

@@ -1,0 +1,281 @@
+// flow.cu — K3 D8 flow direction, K4 flow accumulation, K7 local watersheds.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ms {
+
+// ------------------------------------------------------------------------------------------------
+// K3.  flow.terrain_flowdirection (flow.py:142-167): interior stencil speedups/_flow.pyx:98-176 —
+// dz = z - nbr (edge) or (z - nbr) * INV_SQRT2 (diagonal), float64, strict `>` against a running maximum
+// that starts at 0, neighbours visited Up, UpRight, Right, DownRight, Down, DownLeft, Left, UpLeft, so
+// the first maximum wins; 8 when no neighbour is lower.  Border rule flow.py:118-139 applied in the
+// reference's assignment order (rows, then columns, then corners).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_flowdir(const double *__restrict__ t, uint8_t *__restrict__ out, int rows,
+                                                 int cols, int edges, double inv_sqrt2) {
+    int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (r >= rows || c >= cols) return;
+    size_t i = (size_t)r * cols + c;
+    int code = 8;
+    if (r >= 1 && r <= rows - 2 && c >= 1 && c <= cols - 2) {
+        const double *p = t + i;
+        double z = *p, dzmax = 0.0, dz;
+        dz = __dsub_rn(z, __ldg(p - cols));                              if (dz > dzmax) { dzmax = dz; code = 0; }
+        dz = __dmul_rn(__dsub_rn(z, __ldg(p - cols + 1)), inv_sqrt2);    if (dz > dzmax) { dzmax = dz; code = 1; }
+        dz = __dsub_rn(z, __ldg(p + 1));                                 if (dz > dzmax) { dzmax = dz; code = 2; }
+        dz = __dmul_rn(__dsub_rn(z, __ldg(p + cols + 1)), inv_sqrt2);    if (dz > dzmax) { dzmax = dz; code = 3; }
+        dz = __dsub_rn(z, __ldg(p + cols));                              if (dz > dzmax) { dzmax = dz; code = 4; }
+        dz = __dmul_rn(__dsub_rn(z, __ldg(p + cols - 1)), inv_sqrt2);    if (dz > dzmax) { dzmax = dz; code = 5; }
+        dz = __dsub_rn(z, __ldg(p - 1));                                 if (dz > dzmax) { dzmax = dz; code = 6; }
+        dz = __dmul_rn(__dsub_rn(z, __ldg(p - cols - 1)), inv_sqrt2);    if (dz > dzmax) { dzmax = dz; code = 7; }
+    }
+    if (edges) {
+        int mr = rows - 1, mc = cols - 1;
+        if (r == 0) code = 0;
+        if (r == mr) code = 4;
+        if (c == 0) code = 6;
+        if (c == mc) code = 2;
+        if (r == 0 && c == 0) code = 7;
+        if (r == 0 && c == mc) code = 1;
+        if (r == mr && c == 0) code = 5;
+        if (r == mr && c == mc) code = 3;
+    }
+    out[i] = (uint8_t)code;
+}
+
+int flowdir_dev_impl(const double *t, uint8_t *out, int64_t rows, int64_t cols, int edges, cudaStream_t s) {
+    if (!t || !out) { set_error("terrain_flowdirection: null pointer"); return MS_ERR_ARG; }
+    if (rows < 1 || cols < 1 || rows * cols > (1ll << 30)) {
+        set_error("terrain_flowdirection: unsupported shape %lld x %lld", (long long)rows, (long long)cols);
+        return MS_ERR_SHAPE;
+    }
+    const double inv_sqrt2 = 1.0 / pow(2.0, 0.5);     // _flow.pyx:93-94: SQRT2 = 2**0.5; INV_SQRT2 = 1 / SQRT2
+    dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
+    MS_LAUNCH(k_flowdir, g2, 256, 0, s, t, out, (int)rows, (int)cols, edges, inv_sqrt2);
+    return MS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4.  flow.accumulated_flow (flow.py:344-364; speedups/_flow.pyx:225-273): accum(c) = 1 + sum of accum
+// over the cells that flow into c, i.e. the size of c's upstream tree, as exact float64 integers.
+// Here: in-degree count, then every leaf walks downstream carrying its finished value: add it to the
+// next cell, decrement that cell's in-degree, and carry on only if that was the last missing input
+// (the reference's tracer rule "stop at a cell with an unresolved upstream cell", run from all leaves
+// at once).  Codes > 7 and steps off the raster end a walk.
+// ------------------------------------------------------------------------------------------------
+__device__ inline bool d8_next(int r, int c, int d, int rows, int cols, int *nr, int *nc) {
+    if (d > 7) return false;
+    *nr = r + kDR[d];
+    *nc = c + kDC[d];
+    return *nr >= 0 && *nr < rows && *nc >= 0 && *nc < cols;
+}
+
+__global__ void __launch_bounds__(256) k_acc_indeg(const uint8_t *__restrict__ fd, int *__restrict__ indeg,
+                                                   double *__restrict__ acc, int rows, int cols) {
+    int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (r >= rows || c >= cols) return;
+    size_t i = (size_t)r * cols + c;
+    int n = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int nr = r + kDR[k], nc = c + kDC[k];
+        if (nr < 0 || nr >= rows || nc < 0 || nc >= cols) continue;
+        n += (__ldg(fd + (size_t)nr * cols + nc) == ((k + 4) & 7));
+    }
+    indeg[i] = n ? n : -1;      // -1 marks a leaf: only leaves start a walk (0 = resolved by a walker)
+    acc[i] = 1.0;
+}
+
+__global__ void __launch_bounds__(256) k_acc_trace(const uint8_t *__restrict__ fd, int *indeg, double *acc,
+                                                   int rows, int cols) {
+    int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (r >= rows || c >= cols) return;
+    size_t i = (size_t)r * cols + c;
+    if (__ldcg(indeg + i) != -1) return;
+    double carried = 1.0;
+    for (;;) {
+        int nr, nc;
+        if (!d8_next(r, c, fd[i], rows, cols, &nr, &nc)) return;
+        size_t j = (size_t)nr * cols + nc;
+        atomicAdd(acc + j, carried);
+        __threadfence();
+        if (atomicSub(indeg + j, 1) != 1) return;
+        __threadfence();
+        carried = __ldcg(acc + j);
+        r = nr; c = nc; i = j;
+    }
+}
+
+int accum_dev_impl(const uint8_t *fd, double *acc, int64_t rows, int64_t cols, cudaStream_t s) {
+    if (!fd || !acc) { set_error("accumulated_flow: null pointer"); return MS_ERR_ARG; }
+    if (rows < 1 || cols < 1 || rows * cols > (1ll << 30)) {
+        set_error("accumulated_flow: unsupported shape %lld x %lld", (long long)rows, (long long)cols);
+        return MS_ERR_SHAPE;
+    }
+    DevBuf<int> indeg;
+    MS_TRY(indeg.alloc((size_t)(rows * cols), s));
+    dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
+    MS_LAUNCH(k_acc_indeg, g2, 256, 0, s, fd, indeg.p, acc, (int)rows, (int)cols);
+    MS_LAUNCH(k_acc_trace, g2, 256, 0, s, fd, indeg.p, acc, (int)rows, (int)cols);
+    return MS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7.  flow.watersheds_from_labels (flow.py:398-412; speedups/_flow.pyx:276-403).  The reference walks
+// upstream from every border cell handing down the label of the last labelled cell.  Net effect: an
+// `unassigned` cell takes the label of the first labelled cell on its downstream path, provided the
+// path ends on the raster border (cells whose path dies at an interior no-direction cell are never
+// visited and stay untouched).  Here: ptr = self for labelled / terminal cells, else the downstream
+// cell; pointer jumping; gather.  The "path ends on the border" test needs a second forest (pointers
+// that do not stop at labels) and is only run when an interior cell with code > 7 exists.
+// ------------------------------------------------------------------------------------------------
+template <typename L>
+__global__ void __launch_bounds__(256) k_ws_ptr(const uint8_t *__restrict__ fd, const L *__restrict__ lab, int *ptr,
+                                                int *ptr_full, int *interior_nodir, L unassigned, int rows,
+                                                int cols) {
+    int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (r >= rows || c >= cols) return;
+    int i = r * cols + c;
+    int d = fd[i], nr, nc;
+    bool moves = d8_next(r, c, d, rows, cols, &nr, &nc);
+    int nxt = moves ? nr * cols + nc : i;
+    if (ptr) ptr[i] = (lab[i] != unassigned) ? i : nxt;
+    if (ptr_full) ptr_full[i] = nxt;
+    if (interior_nodir && d > 7 && r > 0 && c > 0 && r < rows - 1 && c < cols - 1) *interior_nodir = 1;
+}
+
+template <typename L>
+__global__ void __launch_bounds__(256) k_ws_assign(L *lab, const int *__restrict__ ptr,
+                                                   const int *__restrict__ ptr_full, int64_t n, int rows, int cols) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int root = ptr[i];
+    if (root == (int)i) return;
+    if (ptr_full) {
+        int t = ptr_full[i];
+        int tr = t / cols, tc = t - tr * cols;
+        if (!(tr == 0 || tc == 0 || tr == rows - 1 || tc == cols - 1)) return;
+    }
+    lab[i] = lab[root];     // roots never change, non-roots are never read: in place is safe
+}
+
+template <typename L>
+int watersheds_dev_t(const uint8_t *fd, L *lab, int64_t rows, int64_t cols, L unassigned, int64_t *stats,
+                     cudaStream_t s) {
+    int64_t n = rows * cols;
+    DevBuf<int> ptr, ptr_full, flag;
+    MS_TRY(ptr.alloc((size_t)n, s));
+    MS_TRY(flag.alloc(1, s));
+    MS_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
+    dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
+    MS_LAUNCH(k_ws_ptr<L>, g2, 256, 0, s, fd, lab, ptr.p, (int *)nullptr, flag.p, unassigned, (int)rows, (int)cols);
+    int64_t *h = host_flags().h;
+    MS_CUDA(cudaMemcpyAsync(h + 8, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    int64_t rounds = 0;
+    MS_TRY(forest_resolve(ptr.p, n, &rounds, s));     // synchronises: h[8] is valid afterwards
+    bool general = *(int *)(h + 8) != 0;
+    if (general) {
+        MS_TRY(ptr_full.alloc((size_t)n, s));
+        MS_LAUNCH(k_ws_ptr<L>, g2, 256, 0, s, fd, lab, (int *)nullptr, ptr_full.p, (int *)nullptr, unassigned,
+                  (int)rows, (int)cols);
+        MS_TRY(forest_resolve(ptr_full.p, n, nullptr, s));
+    }
+    MS_LAUNCH(k_ws_assign<L>, cdiv(n, 256), 256, 0, s, lab, ptr.p, general ? ptr_full.p : (int *)nullptr, n,
+              (int)rows, (int)cols);
+    if (stats) stats[6] = rounds;
+    return MS_OK;
+}
+
+int watersheds_dev_impl(const uint8_t *fd, void *lab, int label_bytes, int64_t rows, int64_t cols,
+                        int64_t unassigned, int64_t *stats, cudaStream_t s) {
+    if (!fd || !lab) { set_error("watersheds_from_labels: null pointer"); return MS_ERR_ARG; }
+    if (rows < 1 || cols < 1 || rows * cols > (1ll << 30)) {
+        set_error("watersheds_from_labels: unsupported shape %lld x %lld", (long long)rows, (long long)cols);
+        return MS_ERR_SHAPE;
+    }
+    if (label_bytes == 4) return watersheds_dev_t<int32_t>(fd, (int32_t *)lab, rows, cols, (int32_t)unassigned, stats, s);
+    if (label_bytes == 8) return watersheds_dev_t<int64_t>(fd, (int64_t *)lab, rows, cols, unassigned, stats, s);
+    set_error("watersheds_from_labels: label_bytes must be 4 or 8");
+    return MS_ERR_ARG;
+}
+
+}  // namespace ms
+
+extern "C" {
+
+int ms_flowdir_dev(const double *terrain, uint8_t *flowdir, int64_t rows, int64_t cols, int edges_flow_outward,
+                   void *stream) {
+    MS_TRY(ms::ensure_init());
+    return ms::flowdir_dev_impl(terrain, flowdir, rows, cols, edges_flow_outward, (cudaStream_t)stream);
+}
+
+int ms_flowdir(const double *terrain, uint8_t *flowdir, int64_t rows, int64_t cols, int edges_flow_outward) {
+    MS_TRY(ms::ensure_init());
+    if (!terrain || !flowdir || rows < 1 || cols < 1) { ms::set_error("terrain_flowdirection: bad argument"); return MS_ERR_ARG; }
+    cudaStream_t s = nullptr;
+    size_t n = (size_t)(rows * cols);
+    ms::DevBuf<double> t;
+    ms::DevBuf<uint8_t> o;
+    MS_TRY(t.alloc(n, s));
+    MS_TRY(o.alloc(n, s));
+    MS_CUDA(cudaMemcpyAsync(t.p, terrain, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    MS_TRY(ms::flowdir_dev_impl(t.p, o.p, rows, cols, edges_flow_outward, s));
+    MS_CUDA(cudaMemcpyAsync(flowdir, o.p, n, cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaStreamSynchronize(s));
+    return MS_OK;
+}
+
+int ms_accumulated_flow_dev(const uint8_t *flowdir, double *accum, int64_t rows, int64_t cols, void *stream) {
+    MS_TRY(ms::ensure_init());
+    return ms::accum_dev_impl(flowdir, accum, rows, cols, (cudaStream_t)stream);
+}
+
+int ms_accumulated_flow(const uint8_t *flowdir, double *accum, int64_t rows, int64_t cols) {
+    MS_TRY(ms::ensure_init());
+    if (!flowdir || !accum || rows < 1 || cols < 1) { ms::set_error("accumulated_flow: bad argument"); return MS_ERR_ARG; }
+    cudaStream_t s = nullptr;
+    size_t n = (size_t)(rows * cols);
+    ms::DevBuf<uint8_t> f;
+    ms::DevBuf<double> a;
+    MS_TRY(f.alloc(n, s));
+    MS_TRY(a.alloc(n, s));
+    MS_CUDA(cudaMemcpyAsync(f.p, flowdir, n, cudaMemcpyHostToDevice, s));
+    MS_TRY(ms::accum_dev_impl(f.p, a.p, rows, cols, s));
+    MS_CUDA(cudaMemcpyAsync(accum, a.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaStreamSynchronize(s));
+    return MS_OK;
+}
+
+int ms_watersheds_from_labels_dev(const uint8_t *flowdir, void *labelled, int label_bytes, int64_t rows,
+                                  int64_t cols, int64_t unassigned, void *stream) {
+    MS_TRY(ms::ensure_init());
+    return ms::watersheds_dev_impl(flowdir, labelled, label_bytes, rows, cols, unassigned, nullptr,
+                                   (cudaStream_t)stream);
+}
+
+int ms_watersheds_from_labels(const uint8_t *flowdir, void *labelled, int label_bytes, int64_t rows, int64_t cols,
+                              int64_t unassigned) {
+    MS_TRY(ms::ensure_init());
+    if (!flowdir || !labelled || rows < 1 || cols < 1 || (label_bytes != 4 && label_bytes != 8)) {
+        ms::set_error("watersheds_from_labels: bad argument");
+        return MS_ERR_ARG;
+    }
+    cudaStream_t s = nullptr;
+    size_t n = (size_t)(rows * cols);
+    ms::DevBuf<uint8_t> f, l;
+    MS_TRY(f.alloc(n, s));
+    MS_TRY(l.alloc(n * label_bytes, s));
+    MS_CUDA(cudaMemcpyAsync(f.p, flowdir, n, cudaMemcpyHostToDevice, s));
+    MS_CUDA(cudaMemcpyAsync(l.p, labelled, n * label_bytes, cudaMemcpyHostToDevice, s));
+    MS_TRY(ms::watersheds_dev_impl(f.p, l.p, label_bytes, rows, cols, unassigned, nullptr, s));
+    MS_CUDA(cudaMemcpyAsync(labelled, l.p, n * label_bytes, cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaStreamSynchronize(s));
+    return MS_OK;
+}
+
+}  // extern "C"

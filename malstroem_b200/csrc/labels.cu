@@ -1,0 +1,697 @@
+// labels.cu — K5/K6 connected components in scipy's numbering, K8 per-label statistics, K8'/K8'' per-label
+// arg-min / arg-max with raster-order tie-break, K9 keep-LUT gather, K10 label histogram.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ms {
+
+// ------------------------------------------------------------------------------------------------
+// K5/K6.  label.connected_components (label.py:19-40 -> scipy.ndimage.label, full 3x3 structure):
+// foreground = value != 0 (NaN and denormals are foreground, -0.0 is not), 8-connectivity, int32 labels
+// numbered 1..n by each component's first cell in row-major order.  Union-find over cell indices where a
+// union always hangs the larger root under the smaller, so every component's root is its minimum index;
+// an exclusive scan of the root flags in raster order then gives scipy's numbering.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ inline bool is_fg(T v) { return v != (T)0; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_cc_init(const T *__restrict__ data, int *__restrict__ parent, int rows,
+                                                 int cols) {
+    int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (r >= rows || c >= cols) return;
+    int i = r * cols + c;
+    if (!is_fg(data[i])) { parent[i] = -1; return; }
+    parent[i] = (c > 0 && is_fg(data[i - 1])) ? i - 1 : i;     // runs along a row are pre-linked
+}
+
+__device__ inline int cc_find(const int *parent, int x) {
+    int p = __ldcg(parent + x);
+    while (p != x) { x = p; p = __ldcg(parent + x); }
+    return x;
+}
+
+__device__ inline void cc_union(int *parent, int a, int b) {
+    for (;;) {
+        a = cc_find(parent, a);
+        b = cc_find(parent, b);
+        if (a == b) return;
+        if (a > b) { int t = a; a = b; b = t; }
+        int old = atomicMin(parent + b, a);      // b was a root: hang it under the smaller root a
+        if (old == b) return;
+        b = old;                                  // somebody re-parented b meanwhile: retry from there
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cc_merge(int *parent, int rows, int cols) {
+    int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (r >= rows || c >= cols || r == 0) return;
+    int i = r * cols + c;
+    if (parent[i] < 0) return;
+    int up = i - cols;
+    if (parent[up] >= 0) {
+        // N is foreground: NW and NE (if foreground) are row-linked to N already
+        // only the first cell of a run, or a cell whose NW is background, adds information
+        if (c == 0 || parent[i - 1] < 0 || parent[up - 1] < 0) cc_union(parent, i, up);
+    } else {
+        if (c > 0 && parent[up - 1] >= 0) cc_union(parent, i, up - 1);
+        if (c < cols - 1 && parent[up + 1] >= 0) cc_union(parent, i, up + 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cc_flatten(int *parent, int *flag, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = parent[i];
+    int f = 0;
+    if (p >= 0) {
+        int root = cc_find(parent, (int)i);
+        if (root != p) parent[i] = root;
+        f = (root == (int)i);
+    }
+    flag[i] = f;
+}
+
+__global__ void __launch_bounds__(256) k_cc_number(const int *__restrict__ parent, const int *__restrict__ rank,
+                                                   int32_t *__restrict__ labels, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = parent[i];
+    labels[i] = p < 0 ? 0 : rank[p] + 1;
+}
+
+template <typename T>
+int cc_dev_t(const T *data, int32_t *labels, int64_t rows, int64_t cols, int64_t *nlabels_dev, cudaStream_t s) {
+    int64_t n = rows * cols;
+    DevBuf<int> parent, flag;
+    MS_TRY(parent.alloc((size_t)n, s));
+    MS_TRY(flag.alloc((size_t)n, s));
+    dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
+    unsigned g1 = cdiv(n, 256);
+    MS_LAUNCH(k_cc_init<T>, g2, 256, 0, s, data, parent.p, (int)rows, (int)cols);
+    MS_LAUNCH(k_cc_merge, g2, 256, 0, s, parent.p, (int)rows, (int)cols);
+    MS_LAUNCH(k_cc_flatten, g1, 256, 0, s, parent.p, flag.p, n);
+    MS_TRY(exclusive_scan_i32(flag.p, flag.p, n, nlabels_dev, s));
+    MS_LAUNCH(k_cc_number, g1, 256, 0, s, parent.p, flag.p, labels, n);
+    return MS_OK;
+}
+
+int cc_dev_impl(const void *data, int dtype, int32_t *labels, int64_t rows, int64_t cols, int64_t *nlabels_dev,
+                cudaStream_t s) {
+    if (!data || !labels) { set_error("connected_components: null pointer"); return MS_ERR_ARG; }
+    if (rows < 1 || cols < 1 || rows * cols > (1ll << 30)) {
+        set_error("connected_components: unsupported shape %lld x %lld", (long long)rows, (long long)cols);
+        return MS_ERR_SHAPE;
+    }
+    switch (dtype) {
+        case MS_F32: return cc_dev_t<float>((const float *)data, labels, rows, cols, nlabels_dev, s);
+        case MS_F64: return cc_dev_t<double>((const double *)data, labels, rows, cols, nlabels_dev, s);
+        case MS_U8: return cc_dev_t<uint8_t>((const uint8_t *)data, labels, rows, cols, nlabels_dev, s);
+        case MS_I32: return cc_dev_t<int32_t>((const int32_t *)data, labels, rows, cols, nlabels_dev, s);
+        case MS_I64: return cc_dev_t<int64_t>((const int64_t *)data, labels, rows, cols, nlabels_dev, s);
+    }
+    set_error("connected_components: unsupported dtype code %d", dtype);
+    return MS_ERR_ARG;
+}
+
+// ------------------------------------------------------------------------------------------------
+// label range (the `nlabels = np.max(labelled)` default, label.py:57,116,150)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_label_range(const int32_t *__restrict__ lab, int64_t n, int32_t *out) {
+    int lo = INT32_MAX, hi = INT32_MIN;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int v = lab[i];
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out, lo);
+        atomicMax(out + 1, hi);
+    }
+}
+
+int label_range_dev_impl(const int32_t *lab, int64_t n, int32_t *out2, cudaStream_t s) {
+    static const int32_t init[2] = {INT32_MAX, INT32_MIN};
+    MS_CUDA(cudaMemcpyAsync(out2, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    int64_t want = (n + 1023) / 1024;
+    int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+    MS_LAUNCH(k_label_range, blocks, 256, 0, s, lab, n, out2);
+    return MS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8.  label.label_stats (label.py:43-75; speedups/_label.pyx:31-97): per label min, max, sum (float64),
+// count.  Labels are spatially coherent, so lanes of a warp that hold the same label are combined first
+// (match.any + redux for the ordered min/max keys, a lane-ordered shuffle sum) and one lane issues the
+// atomics; label 0 (the background, most of the raster) is kept in registers and reduced per CTA.
+// min / max / count are exact; sum is float64 in a different association than the reference's raster
+// order (within 1e-6 relative, north_star).
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct KeyOf;
+template <> struct KeyOf<float> {
+    typedef uint32_t K;
+    static __device__ K key(float v) { return okey32(v); }
+    static __device__ double inv(K k) { return (double)okey32_inv(k); }
+    static constexpr K kMax = 0xffffffffu;
+};
+template <> struct KeyOf<double> {
+    typedef unsigned long long K;
+    static __device__ K key(double v) { return okey64(v); }
+    static __device__ double inv(K k) { return okey64_inv(k); }
+    static constexpr K kMax = ~0ull;
+};
+
+__device__ inline uint32_t grp_min(unsigned m, uint32_t v) { return __reduce_min_sync(m, v); }
+__device__ inline uint32_t grp_max(unsigned m, uint32_t v) { return __reduce_max_sync(m, v); }
+__device__ inline unsigned long long grp_min(unsigned m, unsigned long long v) {
+    // 64-bit: high word first, then the low word among the lanes that hold the winning high word
+    uint32_t hi = (uint32_t)(v >> 32);
+    uint32_t bh = __reduce_min_sync(m, hi);
+    uint32_t lo = (hi == bh) ? (uint32_t)v : 0xffffffffu;
+    return ((unsigned long long)bh << 32) | __reduce_min_sync(m, lo);
+}
+__device__ inline unsigned long long grp_max(unsigned m, unsigned long long v) {
+    uint32_t hi = (uint32_t)(v >> 32);
+    uint32_t bh = __reduce_max_sync(m, hi);
+    uint32_t lo = (hi == bh) ? (uint32_t)v : 0u;
+    return ((unsigned long long)bh << 32) | __reduce_max_sync(m, lo);
+}
+
+__device__ inline double grp_sum(unsigned m, double v) {
+    double s = 0.0;
+    unsigned rest = m;
+    while (rest) {                       // lane order = raster order inside the group
+        int src = __ffs(rest) - 1;
+        rest &= rest - 1;
+        s += __shfl_sync(m, v, src);
+    }
+    return s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_label_stats(const T *__restrict__ data, const int32_t *__restrict__ lab,
+                                                     int64_t n, int64_t nlabels, typename KeyOf<T>::K *tmin,
+                                                     typename KeyOf<T>::K *tmax, double *tsum,
+                                                     unsigned long long *tcnt, int *err) {
+    typedef typename KeyOf<T>::K K;
+    K bmin = KeyOf<T>::kMax, bmax = 0;
+    double bsum = 0.0;
+    unsigned long long bcnt = 0;
+    bool nan_in_bg = false;
+    int64_t span = (int64_t)gridDim.x * blockDim.x;
+    int64_t nround = (n + span - 1) / span;
+    for (int64_t it = 0; it < nround; it++) {
+        int64_t i = it * span + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        int lbl = -1;
+        T v = 0;
+        if (i < n) {
+            lbl = lab[i];
+            v = data[i];
+            if (lbl < 0 || lbl > nlabels) { *err = 1; lbl = -1; }
+        }
+        if (lbl == 0) {
+            K k = KeyOf<T>::key(v);
+            if (v == v) { bmin = k < bmin ? k : bmin; bmax = k > bmax ? k : bmax; } else nan_in_bg = true;
+            bsum += (double)v;
+            bcnt++;
+        }
+        unsigned act = __ballot_sync(0xffffffffu, lbl > 0);
+        if (lbl > 0) {
+            unsigned g = __match_any_sync(act, lbl);
+            bool ok = (v == v);                  // NaN never wins a strict comparison (label.py:70-73)
+            K k = KeyOf<T>::key(ok ? v : (T)0);
+            K kmn = grp_min(g, ok ? k : KeyOf<T>::kMax);
+            K kmx = grp_max(g, ok ? k : (K)0);
+            double sm = grp_sum(g, (double)v);
+            if ((int)(__ffs(g) - 1) == (int)(threadIdx.x & 31)) {
+                if (kmn < tmin[lbl]) atomicMin(tmin + lbl, kmn);
+                if (kmx > tmax[lbl]) atomicMax(tmax + lbl, kmx);
+                atomicAdd(tsum + lbl, sm);
+                atomicAdd(tcnt + lbl, (unsigned long long)__popc(g));
+            }
+        }
+    }
+    (void)nan_in_bg;
+    // CTA reduction of the background accumulators
+    unsigned full = 0xffffffffu;
+    K wmin = grp_min(full, bmin), wmax = grp_max(full, bmax);
+    double wsum = bsum;
+    unsigned long long wcnt = bcnt;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        wsum += __shfl_xor_sync(full, wsum, o);
+        wcnt += __shfl_xor_sync(full, wcnt, o);
+    }
+    __shared__ K smin[8], smax[8];
+    __shared__ double ssum[8];
+    __shared__ unsigned long long scnt[8];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { smin[w] = wmin; smax[w] = wmax; ssum[w] = wsum; scnt[w] = wcnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; k++) {
+            wmin = smin[k] < wmin ? smin[k] : wmin;
+            wmax = smax[k] > wmax ? smax[k] : wmax;
+            wsum += ssum[k];
+            wcnt += scnt[k];
+        }
+        if (wcnt) {
+            atomicMin(tmin, wmin);
+            atomicMax(tmax, wmax);
+            atomicAdd(tsum, wsum);
+            atomicAdd(tcnt, wcnt);
+        }
+    }
+}
+
+template <typename K>
+__global__ void __launch_bounds__(256) k_stats_init(K *tmin, K *tmax, double *tsum, unsigned long long *tcnt,
+                                                    int64_t m, K kmax) {
+    int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < m) { tmin[l] = kmax; tmax[l] = 0; tsum[l] = 0.0; tcnt[l] = 0; }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_stats_finish(const typename KeyOf<T>::K *tmin,
+                                                      const typename KeyOf<T>::K *tmax, const unsigned long long *tcnt,
+                                                      double *omin, double *omax, int64_t *ocnt, int64_t m) {
+    int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= m) return;
+    typedef typename KeyOf<T>::K K;
+    K a = tmin[l], b = tmax[l];
+    omin[l] = (a == KeyOf<T>::kMax) ? (double)INFINITY : KeyOf<T>::inv(a);     // label.py:61-62 defaults
+    omax[l] = (b == (K)0) ? (double)-INFINITY : KeyOf<T>::inv(b);
+    ocnt[l] = (int64_t)tcnt[l];
+}
+
+template <typename T>
+int label_stats_dev_t(const T *data, const int32_t *lab, int64_t n, int64_t nlabels, double *omin, double *omax,
+                      double *osum, int64_t *ocnt, int *err_dev, cudaStream_t s) {
+    typedef typename KeyOf<T>::K K;
+    int64_t m = nlabels + 1;
+    DevBuf<K> tmin, tmax;
+    DevBuf<unsigned long long> tcnt;
+    MS_TRY(tmin.alloc((size_t)m, s));
+    MS_TRY(tmax.alloc((size_t)m, s));
+    MS_TRY(tcnt.alloc((size_t)m, s));
+    unsigned gm = cdiv(m, 256);
+    MS_LAUNCH(k_stats_init<K>, gm, 256, 0, s, tmin.p, tmax.p, osum, tcnt.p, m, KeyOf<T>::kMax);
+    int64_t want = (n + 255) / 256;
+    int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
+    MS_LAUNCH(k_label_stats<T>, blocks, 256, 0, s, data, lab, n, nlabels, tmin.p, tmax.p, osum, tcnt.p, err_dev);
+    MS_LAUNCH(k_stats_finish<T>, gm, 256, 0, s, tmin.p, tmax.p, tcnt.p, omin, omax, ocnt, m);
+    return MS_OK;
+}
+
+int label_stats_dev_impl(const void *data, int dtype, const int32_t *lab, int64_t n, int64_t nlabels, double *omin,
+                         double *omax, double *osum, int64_t *ocnt, int *err_dev, cudaStream_t s) {
+    if (!data || !lab || !omin || !omax || !osum || !ocnt || n < 1 || nlabels < 0) {
+        set_error("label_stats: bad argument");
+        return MS_ERR_ARG;
+    }
+    if (dtype == MS_F32) return label_stats_dev_t<float>((const float *)data, lab, n, nlabels, omin, omax, osum, ocnt, err_dev, s);
+    if (dtype == MS_F64) return label_stats_dev_t<double>((const double *)data, lab, n, nlabels, omin, omax, osum, ocnt, err_dev, s);
+    set_error("label_stats: data dtype must be MS_F32 or MS_F64");
+    return MS_ERR_ARG;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8' / K8''.  label.label_min_index / label_max_index (label.py:101-166; speedups/_label.pyx:99-128):
+// strict comparison while scanning in raster order, so among equal extreme values the smallest flat
+// index wins; NaN never wins; labels never seen keep (+-inf, -1, -1).  Two passes: the extreme ordered
+// key per label, then the smallest index among the cells that hold it.  (-0.0 and +0.0 share a key, as
+// they compare equal; the reported value is read back from the winning cell.)
+// ------------------------------------------------------------------------------------------------
+template <bool MAX>
+__global__ void __launch_bounds__(256) k_extreme_key(const double *__restrict__ data, const int32_t *__restrict__ lab,
+                                                     int64_t n, int64_t nlabels, unsigned long long *tkey, int *err) {
+    unsigned long long bg = MAX ? 0ull : ~0ull;
+    int64_t span = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += span) {
+        int lbl = lab[i];
+        double v = data[i];
+        if (lbl < 0 || lbl > nlabels) { *err = 1; continue; }
+        if (v != v) continue;
+        unsigned long long k = okey64(v);
+        if (lbl == 0) {
+            bg = MAX ? (k > bg ? k : bg) : (k < bg ? k : bg);
+        } else if (MAX) {
+            if (k > tkey[lbl]) atomicMax(tkey + lbl, k);
+        } else {
+            if (k < tkey[lbl]) atomicMin(tkey + lbl, k);
+        }
+    }
+    bg = MAX ? grp_max(0xffffffffu, bg) : grp_min(0xffffffffu, bg);
+    if ((threadIdx.x & 31) == 0) {
+        if (MAX) { if (bg > tkey[0]) atomicMax(tkey, bg); }
+        else     { if (bg < tkey[0]) atomicMin(tkey, bg); }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_extreme_index(const double *__restrict__ data, const int32_t *__restrict__ lab,
+                                                       int64_t n, int64_t nlabels,
+                                                       const unsigned long long *__restrict__ tkey, int *tidx) {
+    int64_t span = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += span) {
+        int lbl = lab[i];
+        if (lbl < 0 || lbl > nlabels) continue;
+        double v = data[i];
+        if (v != v) continue;
+        if (okey64(v) != tkey[lbl]) continue;
+        if ((int)i < tidx[lbl]) atomicMin(tidx + lbl, (int)i);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_extreme_finish(const double *__restrict__ data, const int *__restrict__ tidx,
+                                                        int64_t m, int cols, int want_max, double *oval, int64_t *orow,
+                                                        int64_t *ocol) {
+    int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= m) return;
+    int i = tidx[l];
+    if (i == INT32_MAX) {
+        oval[l] = want_max ? (double)-INFINITY : (double)INFINITY;
+        orow[l] = -1;
+        ocol[l] = -1;
+    } else {
+        oval[l] = data[i];
+        orow[l] = i / cols;
+        ocol[l] = i % cols;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fill_u64(unsigned long long *p, unsigned long long v, int *q, int w, int64_t m) {
+    int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < m) { p[l] = v; q[l] = w; }
+}
+
+int label_extreme_dev_impl(const double *data, const int32_t *lab, int64_t rows, int64_t cols, int64_t nlabels,
+                           int want_max, double *oval, int64_t *orow, int64_t *ocol, int *err_dev, cudaStream_t s) {
+    if (!data || !lab || !oval || !orow || !ocol || rows < 1 || cols < 1 || nlabels < 0 || rows * cols > (1ll << 30)) {
+        set_error("label_min/max_index: bad argument");
+        return MS_ERR_ARG;
+    }
+    int64_t n = rows * cols, m = nlabels + 1;
+    DevBuf<unsigned long long> tkey;
+    DevBuf<int> tidx;
+    MS_TRY(tkey.alloc((size_t)m, s));
+    MS_TRY(tidx.alloc((size_t)m, s));
+    unsigned gm = cdiv(m, 256);
+    MS_LAUNCH(k_fill_u64, gm, 256, 0, s, tkey.p, want_max ? 0ull : ~0ull, tidx.p, INT32_MAX, m);
+    int64_t want = (n + 255) / 256;
+    int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
+    if (want_max) MS_LAUNCH(k_extreme_key<true>, blocks, 256, 0, s, data, lab, n, nlabels, tkey.p, err_dev);
+    else MS_LAUNCH(k_extreme_key<false>, blocks, 256, 0, s, data, lab, n, nlabels, tkey.p, err_dev);
+    MS_LAUNCH(k_extreme_index, blocks, 256, 0, s, data, lab, n, nlabels, tkey.p, tidx.p);
+    MS_LAUNCH(k_extreme_finish, gm, 256, 0, s, data, tidx.p, m, (int)cols, want_max, oval, orow, ocol);
+    return MS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10.  label.label_count (label.py:169-180, np.bincount) and K9 label.keep_labels (label.py:78-98)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_label_count(const int32_t *__restrict__ lab, int64_t n, int64_t nbins,
+                                                     unsigned long long *cnt, int *err) {
+    unsigned long long bg = 0;
+    int64_t span = (int64_t)gridDim.x * blockDim.x;
+    int64_t nround = (n + span - 1) / span;
+    for (int64_t it = 0; it < nround; it++) {
+        int64_t i = it * span + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        int lbl = -1;
+        if (i < n) {
+            lbl = lab[i];
+            if (lbl < 0 || lbl >= nbins) { *err = 1; lbl = -1; }
+        }
+        if (lbl == 0) bg++;
+        unsigned act = __ballot_sync(0xffffffffu, lbl > 0);
+        if (lbl > 0) {
+            unsigned g = __match_any_sync(act, lbl);
+            if ((int)(__ffs(g) - 1) == (int)(threadIdx.x & 31)) atomicAdd(cnt + lbl, (unsigned long long)__popc(g));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) bg += __shfl_xor_sync(0xffffffffu, bg, o);
+    __shared__ unsigned long long sb[8];
+    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = bg;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; k++) bg += sb[k];
+        if (bg) atomicAdd(cnt, bg);
+    }
+}
+
+int label_count_dev_impl(const int32_t *lab, int64_t n, int64_t nbins, int64_t *cnt, int *err_dev, cudaStream_t s) {
+    if (!lab || !cnt || n < 1 || nbins < 1) { set_error("label_count: bad argument"); return MS_ERR_ARG; }
+    MS_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nbins * sizeof(int64_t), s));
+    int64_t want = (n + 255) / 256;
+    int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
+    MS_LAUNCH(k_label_count, blocks, 256, 0, s, lab, n, nbins, (unsigned long long *)cnt, err_dev);
+    return MS_OK;
+}
+
+__global__ void __launch_bounds__(256) k_keep_labels(const int32_t *__restrict__ lab, int64_t n,
+                                                     const uint8_t *__restrict__ keep, int64_t nkeep,
+                                                     uint8_t *__restrict__ out, int *err) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int l = lab[i];
+    if (l < 0 || l >= nkeep) { *err = 1; out[i] = 0; return; }
+    out[i] = __ldg(keep + l) ? 1 : 0;
+}
+
+int keep_labels_dev_impl(const int32_t *lab, int64_t n, const uint8_t *keep, int64_t nkeep, uint8_t *out,
+                         int *err_dev, cudaStream_t s) {
+    if (!lab || !keep || !out || n < 1 || nkeep < 1) { set_error("keep_labels: bad argument"); return MS_ERR_ARG; }
+    MS_LAUNCH(k_keep_labels, cdiv(n, 256), 256, 0, s, lab, n, keep, nkeep, out, err_dev);
+    return MS_OK;
+}
+
+}  // namespace ms
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct ErrFlag {
+    ms::DevBuf<int> d;
+    cudaStream_t s;
+    int init(cudaStream_t stream) {
+        s = stream;
+        MS_TRY(d.alloc(1, s));
+        MS_CUDA(cudaMemsetAsync(d.p, 0, sizeof(int), s));
+        return MS_OK;
+    }
+    // synchronises the stream
+    int check(const char *what) {
+        int64_t *h = ms::host_flags().h;
+        MS_CUDA(cudaMemcpyAsync(h + 16, d.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MS_CUDA(cudaStreamSynchronize(s));
+        if (*(int *)(h + 16)) {
+            ms::set_error("%s: a label lies outside the table", what);
+            return MS_ERR_LABEL;
+        }
+        return MS_OK;
+    }
+};
+
+size_t dtype_size(int dtype) {
+    switch (dtype) {
+        case MS_F32: case MS_I32: return 4;
+        case MS_F64: case MS_I64: return 8;
+        case MS_U8: return 1;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ms_connected_components_dev(const void *data, int dtype, int32_t *labels, int64_t rows, int64_t cols,
+                                int64_t *nlabels, void *stream) {
+    MS_TRY(ms::ensure_init());
+    cudaStream_t s = (cudaStream_t)stream;
+    ms::DevBuf<int64_t> tot;
+    MS_TRY(tot.alloc(1, s));
+    MS_TRY(ms::cc_dev_impl(data, dtype, labels, rows, cols, tot.p, s));
+    int64_t *h = ms::host_flags().h;
+    MS_CUDA(cudaMemcpyAsync(h, tot.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaStreamSynchronize(s));
+    if (nlabels) *nlabels = h[0];
+    return MS_OK;
+}
+
+int ms_connected_components(const void *data, int dtype, int32_t *labels, int64_t rows, int64_t cols,
+                            int64_t *nlabels) {
+    MS_TRY(ms::ensure_init());
+    size_t es = dtype_size(dtype);
+    if (!data || !labels || !es || rows < 1 || cols < 1) { ms::set_error("connected_components: bad argument"); return MS_ERR_ARG; }
+    cudaStream_t s = nullptr;
+    size_t n = (size_t)(rows * cols);
+    ms::DevBuf<uint8_t> d;
+    ms::DevBuf<int32_t> l;
+    MS_TRY(d.alloc(n * es, s));
+    MS_TRY(l.alloc(n, s));
+    MS_CUDA(cudaMemcpyAsync(d.p, data, n * es, cudaMemcpyHostToDevice, s));
+    MS_TRY(ms_connected_components_dev(d.p, dtype, l.p, rows, cols, nlabels, s));
+    MS_CUDA(cudaMemcpyAsync(labels, l.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaStreamSynchronize(s));
+    return MS_OK;
+}
+
+int ms_label_range_dev(const int32_t *labels, int64_t n, int32_t *out_minmax_dev2, void *stream) {
+    MS_TRY(ms::ensure_init());
+    if (!labels || !out_minmax_dev2 || n < 1) { ms::set_error("label_range: bad argument"); return MS_ERR_ARG; }
+    return ms::label_range_dev_impl(labels, n, out_minmax_dev2, (cudaStream_t)stream);
+}
+
+int ms_label_range(const int32_t *labels, int64_t n, int32_t *out_min, int32_t *out_max) {
+    MS_TRY(ms::ensure_init());
+    if (!labels || n < 1) { ms::set_error("label_range: bad argument"); return MS_ERR_ARG; }
+    cudaStream_t s = nullptr;
+    ms::DevBuf<int32_t> l, o;
+    MS_TRY(l.alloc((size_t)n, s));
+    MS_TRY(o.alloc(2, s));
+    MS_CUDA(cudaMemcpyAsync(l.p, labels, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    MS_TRY(ms::label_range_dev_impl(l.p, n, o.p, s));
+    int32_t r[2];
+    MS_CUDA(cudaMemcpyAsync(r, o.p, sizeof(r), cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaStreamSynchronize(s));
+    if (out_min) *out_min = r[0];
+    if (out_max) *out_max = r[1];
+    return MS_OK;
+}
+
+int ms_label_stats_dev(const void *data, int dtype, const int32_t *labels, int64_t n, int64_t nlabels,
+                       double *out_min, double *out_max, double *out_sum, int64_t *out_count, void *stream) {
+    MS_TRY(ms::ensure_init());
+    ErrFlag ef;
+    MS_TRY(ef.init((cudaStream_t)stream));
+    return ms::label_stats_dev_impl(data, dtype, labels, n, nlabels, out_min, out_max, out_sum, out_count, ef.d.p,
+                                    (cudaStream_t)stream);
+}
+
+int ms_label_stats(const void *data, int dtype, const int32_t *labels, int64_t n, int64_t nlabels, double *out_min,
+                   double *out_max, double *out_sum, int64_t *out_count) {
+    MS_TRY(ms::ensure_init());
+    size_t es = dtype_size(dtype);
+    if (!data || !labels || (dtype != MS_F32 && dtype != MS_F64) || n < 1 || nlabels < 0) {
+        ms::set_error("label_stats: bad argument");
+        return MS_ERR_ARG;
+    }
+    cudaStream_t s = nullptr;
+    size_t m = (size_t)nlabels + 1;
+    ms::DevBuf<uint8_t> d;
+    ms::DevBuf<int32_t> l;
+    ms::DevBuf<double> a, b, c;
+    ms::DevBuf<int64_t> k;
+    MS_TRY(d.alloc((size_t)n * es, s));
+    MS_TRY(l.alloc((size_t)n, s));
+    MS_TRY(a.alloc(m, s)); MS_TRY(b.alloc(m, s)); MS_TRY(c.alloc(m, s)); MS_TRY(k.alloc(m, s));
+    MS_CUDA(cudaMemcpyAsync(d.p, data, (size_t)n * es, cudaMemcpyHostToDevice, s));
+    MS_CUDA(cudaMemcpyAsync(l.p, labels, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    ErrFlag ef;
+    MS_TRY(ef.init(s));
+    MS_TRY(ms::label_stats_dev_impl(d.p, dtype, l.p, n, nlabels, a.p, b.p, c.p, k.p, ef.d.p, s));
+    MS_TRY(ef.check("label_stats"));
+    MS_CUDA(cudaMemcpyAsync(out_min, a.p, m * 8, cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaMemcpyAsync(out_max, b.p, m * 8, cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaMemcpyAsync(out_sum, c.p, m * 8, cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaMemcpyAsync(out_count, k.p, m * 8, cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaStreamSynchronize(s));
+    return MS_OK;
+}
+
+int ms_label_extreme_index_dev(const double *data, const int32_t *labels, int64_t rows, int64_t cols,
+                               int64_t nlabels, int want_max, double *out_value, int64_t *out_row, int64_t *out_col,
+                               void *stream) {
+    MS_TRY(ms::ensure_init());
+    ErrFlag ef;
+    MS_TRY(ef.init((cudaStream_t)stream));
+    return ms::label_extreme_dev_impl(data, labels, rows, cols, nlabels, want_max, out_value, out_row, out_col,
+                                      ef.d.p, (cudaStream_t)stream);
+}
+
+int ms_label_extreme_index(const double *data, const int32_t *labels, int64_t rows, int64_t cols, int64_t nlabels,
+                           int want_max, double *out_value, int64_t *out_row, int64_t *out_col) {
+    MS_TRY(ms::ensure_init());
+    if (!data || !labels || rows < 1 || cols < 1 || nlabels < 0) { ms::set_error("label_min/max_index: bad argument"); return MS_ERR_ARG; }
+    cudaStream_t s = nullptr;
+    size_t n = (size_t)(rows * cols), m = (size_t)nlabels + 1;
+    ms::DevBuf<double> d, v;
+    ms::DevBuf<int32_t> l;
+    ms::DevBuf<int64_t> r, c;
+    MS_TRY(d.alloc(n, s)); MS_TRY(l.alloc(n, s));
+    MS_TRY(v.alloc(m, s)); MS_TRY(r.alloc(m, s)); MS_TRY(c.alloc(m, s));
+    MS_CUDA(cudaMemcpyAsync(d.p, data, n * 8, cudaMemcpyHostToDevice, s));
+    MS_CUDA(cudaMemcpyAsync(l.p, labels, n * 4, cudaMemcpyHostToDevice, s));
+    ErrFlag ef;
+    MS_TRY(ef.init(s));
+    MS_TRY(ms::label_extreme_dev_impl(d.p, l.p, rows, cols, nlabels, want_max, v.p, r.p, c.p, ef.d.p, s));
+    MS_TRY(ef.check("label_min/max_index"));
+    MS_CUDA(cudaMemcpyAsync(out_value, v.p, m * 8, cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaMemcpyAsync(out_row, r.p, m * 8, cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaMemcpyAsync(out_col, c.p, m * 8, cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaStreamSynchronize(s));
+    return MS_OK;
+}
+
+int ms_label_count_dev(const int32_t *labels, int64_t n, int64_t nbins, int64_t *out_count, void *stream) {
+    MS_TRY(ms::ensure_init());
+    ErrFlag ef;
+    MS_TRY(ef.init((cudaStream_t)stream));
+    return ms::label_count_dev_impl(labels, n, nbins, out_count, ef.d.p, (cudaStream_t)stream);
+}
+
+int ms_label_count(const int32_t *labels, int64_t n, int64_t nbins, int64_t *out_count) {
+    MS_TRY(ms::ensure_init());
+    if (!labels || !out_count || n < 1 || nbins < 1) { ms::set_error("label_count: bad argument"); return MS_ERR_ARG; }
+    cudaStream_t s = nullptr;
+    ms::DevBuf<int32_t> l;
+    ms::DevBuf<int64_t> c;
+    MS_TRY(l.alloc((size_t)n, s));
+    MS_TRY(c.alloc((size_t)nbins, s));
+    MS_CUDA(cudaMemcpyAsync(l.p, labels, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    ErrFlag ef;
+    MS_TRY(ef.init(s));
+    MS_TRY(ms::label_count_dev_impl(l.p, n, nbins, c.p, ef.d.p, s));
+    MS_TRY(ef.check("label_count"));
+    MS_CUDA(cudaMemcpyAsync(out_count, c.p, (size_t)nbins * 8, cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaStreamSynchronize(s));
+    return MS_OK;
+}
+
+int ms_keep_labels_dev(const int32_t *labels, int64_t n, const uint8_t *keep, int64_t nkeep, uint8_t *out,
+                       void *stream) {
+    MS_TRY(ms::ensure_init());
+    ErrFlag ef;
+    MS_TRY(ef.init((cudaStream_t)stream));
+    return ms::keep_labels_dev_impl(labels, n, keep, nkeep, out, ef.d.p, (cudaStream_t)stream);
+}
+
+int ms_keep_labels(const int32_t *labels, int64_t n, const uint8_t *keep, int64_t nkeep, uint8_t *out) {
+    MS_TRY(ms::ensure_init());
+    if (!labels || !keep || !out || n < 1 || nkeep < 1) { ms::set_error("keep_labels: bad argument"); return MS_ERR_ARG; }
+    cudaStream_t s = nullptr;
+    ms::DevBuf<int32_t> l;
+    ms::DevBuf<uint8_t> k, o;
+    MS_TRY(l.alloc((size_t)n, s));
+    MS_TRY(k.alloc((size_t)nkeep, s));
+    MS_TRY(o.alloc((size_t)n, s));
+    MS_CUDA(cudaMemcpyAsync(l.p, labels, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    MS_CUDA(cudaMemcpyAsync(k.p, keep, (size_t)nkeep, cudaMemcpyHostToDevice, s));
+    ErrFlag ef;
+    MS_TRY(ef.init(s));
+    MS_TRY(ms::keep_labels_dev_impl(l.p, n, k.p, nkeep, o.p, ef.d.p, s));
+    MS_TRY(ef.check("keep_labels"));
+    MS_CUDA(cudaMemcpyAsync(out, o.p, (size_t)n, cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaStreamSynchronize(s));
+    return MS_OK;
+}
+
+}  // extern "C"

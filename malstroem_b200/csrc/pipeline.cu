@@ -1,0 +1,88 @@
+// pipeline.cu — the whole raster hot path on device-resident data (what bench.py times):
+// DEM -> fill (+depths) -> short/diag -> no-flats fill -> D8 -> accumulation -> bluespot labels ->
+// label stats -> watersheds (+counts) -> pour points.  Order and operands follow DemTool.process
+// (malstroem/dem.py:53-93) and BluespotTool.process (malstroem/bluespots.py:138-216) without the
+// bluespot filter (bench: no filter; the tool layer applies its filter on the host between the stages).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace ms {
+int minmax_dev(const float *z, int64_t n, float *out2, cudaStream_t s);
+int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, double dg, double *out, int64_t rows,
+                           int64_t cols, int64_t *stats, cudaStream_t s);
+int flowdir_dev_impl(const double *t, uint8_t *out, int64_t rows, int64_t cols, int edges, cudaStream_t s);
+int accum_dev_impl(const uint8_t *fd, double *acc, int64_t rows, int64_t cols, cudaStream_t s);
+int watersheds_dev_impl(const uint8_t *fd, void *lab, int label_bytes, int64_t rows, int64_t cols, int64_t unassigned,
+                        int64_t *stats, cudaStream_t s);
+int cc_dev_impl(const void *data, int dtype, int32_t *labels, int64_t rows, int64_t cols, int64_t *nlabels_dev,
+                cudaStream_t s);
+int label_stats_dev_impl(const void *data, int dtype, const int32_t *lab, int64_t n, int64_t nlabels, double *omin,
+                         double *omax, double *osum, int64_t *ocnt, int *err_dev, cudaStream_t s);
+int label_extreme_dev_impl(const double *data, const int32_t *lab, int64_t rows, int64_t cols, int64_t nlabels,
+                           int want_max, double *oval, int64_t *orow, int64_t *ocol, int *err_dev, cudaStream_t s);
+int label_count_dev_impl(const int32_t *lab, int64_t n, int64_t nbins, int64_t *cnt, int *err_dev, cudaStream_t s);
+}  // namespace ms
+
+extern "C" int ms_pipeline_dev(ms_rasters *io, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!io || !io->dem || !io->filled || !io->depths || !io->fnf || !io->flowdir || !io->labels || !io->wsheds) {
+        set_error("pipeline: null raster pointer");
+        return MS_ERR_ARG;
+    }
+    int64_t rows = io->rows, cols = io->cols, n = rows * cols;
+    for (int k = 0; k < 8; k++) io->stats[k] = 0;
+    int64_t *h = host_flags().h;
+
+    // dem.py:67-72
+    MS_TRY(fill_terrain_dev_impl(io->dem, io->filled, io->depths, rows, cols, io->stats, s));
+    // dem.py:79 (fill.py:235-250)
+    DevBuf<float> mm;
+    MS_TRY(mm.alloc(2, s));
+    MS_TRY(minmax_dev(io->dem, n, mm.p, s));
+    MS_CUDA(cudaMemcpyAsync(h + 24, mm.p, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaStreamSynchronize(s));
+    float lo = ((float *)(h + 24))[0], hi = ((float *)(h + 24))[1];
+    double maxval = (double)fmaxf(fabsf(hi), fabsf(lo));
+    io->short_eps = (nextafter(maxval, (double)INFINITY) - maxval) * 1024.0;
+    io->diag_eps = io->short_eps * pow(2.0, 0.5);
+    // dem.py:80-83
+    int64_t nfstats[3] = {0, 0, 0};
+    MS_TRY(fill_no_flats_dev_impl(io->dem, io->filled, io->short_eps, io->diag_eps, io->fnf, rows, cols, nfstats, s));
+    io->stats[2] = nfstats[0]; io->stats[3] = nfstats[1]; io->stats[4] = nfstats[2];
+    MS_TRY(flowdir_dev_impl(io->fnf, io->flowdir, rows, cols, 1, s));
+    // dem.py:87-91
+    if (io->accum) MS_TRY(accum_dev_impl(io->flowdir, io->accum, rows, cols, s));
+    // bluespots.py:158-160
+    DevBuf<int64_t> tot;
+    DevBuf<int> err;
+    MS_TRY(tot.alloc(1, s));
+    MS_TRY(err.alloc(1, s));
+    MS_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), s));
+    MS_TRY(cc_dev_impl(io->depths, MS_F32, io->labels, rows, cols, tot.p, s));
+    MS_CUDA(cudaMemcpyAsync(h, tot.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaStreamSynchronize(s));
+    io->nlabels = h[0];
+    if (io->nlabels + 1 > io->table_capacity) {
+        set_error("pipeline: %lld labels do not fit table_capacity %lld", (long long)io->nlabels,
+                  (long long)io->table_capacity);
+        return MS_ERR_ARG;
+    }
+    if (io->st_min)
+        MS_TRY(label_stats_dev_impl(io->depths, MS_F32, io->labels, n, io->nlabels, io->st_min, io->st_max, io->st_sum,
+                                    io->st_count, err.p, s));
+    // bluespots.py:183-186
+    MS_CUDA(cudaMemcpyAsync(io->wsheds, io->labels, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    MS_TRY(watersheds_dev_impl(io->flowdir, io->wsheds, 4, rows, cols, 0, io->stats, s));
+    if (io->ws_count) MS_TRY(label_count_dev_impl(io->wsheds, n, io->nlabels + 1, io->ws_count, err.p, s));
+    // bluespots.py:195-206 (both pour-point variants)
+    if (io->ppmin_value)
+        MS_TRY(label_extreme_dev_impl(io->fnf, io->labels, rows, cols, io->nlabels, 0, io->ppmin_value, io->ppmin_row,
+                                      io->ppmin_col, err.p, s));
+    if (io->ppmax_value && io->accum)
+        MS_TRY(label_extreme_dev_impl(io->accum, io->labels, rows, cols, io->nlabels, 1, io->ppmax_value, io->ppmax_row,
+                                      io->ppmax_col, err.p, s));
+    return MS_OK;
+}

@@ -1,0 +1,127 @@
+"""Device-resident whole path: DEM in HBM -> every raster and per-label table of the hot path in HBM
+(`ms_pipeline_dev`), plus a host-buffer front end that adds the H2D / D2H copies.
+
+torch is used for what it is good at here — owning device / pinned memory and the CUDA stream; every
+kernel that runs is from libmalstroem_b200.so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+RASTERS = (("filled", torch.float32), ("depths", torch.float32), ("fnf", torch.float64), ("flowdir", torch.uint8),
+           ("accum", torch.float64), ("labels", torch.int32), ("wsheds", torch.int32))
+TABLES = (("st_min", torch.float64), ("st_max", torch.float64), ("st_sum", torch.float64), ("st_count", torch.int64),
+          ("ws_count", torch.int64), ("ppmin_value", torch.float64), ("ppmin_row", torch.int64),
+          ("ppmin_col", torch.int64), ("ppmax_value", torch.float64), ("ppmax_row", torch.int64),
+          ("ppmax_col", torch.int64))
+STAT_NAMES = ("boruvka_rounds", "catchments", "noflat_rounds", "noflat_tile_visits", "noflat_reverify",
+              "fill_jump_rounds", "wshed_jump_rounds", "reserved")
+
+
+class RasterPipeline(object):
+    """Buffers for one `rows x cols` raster on one GPU and the call that fills them."""
+
+    def __init__(self, rows, cols, device=0, with_accum=True, table_capacity=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("malstroem_b200.pipeline needs a CUDA device (there is no CPU fallback)")
+        self.rows, self.cols = int(rows), int(cols)
+        self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        self.with_accum = with_accum
+        n = self.rows * self.cols
+        # 8-connected components of a raster: at most ceil(rows/2)*ceil(cols/2)
+        cap = ((self.rows + 1) // 2) * ((self.cols + 1) // 2) + 1
+        self.table_capacity = int(table_capacity) if table_capacity else cap
+        with _lib.lock:
+            _lib.check(_lib.lib().ms_init(self.device.index or 0), "ms_init")
+        self.dem = torch.empty((self.rows, self.cols), dtype=torch.float32, device=self.device)
+        self.out = {}
+        for name, dt in RASTERS:
+            if name == "accum" and not with_accum:
+                continue
+            self.out[name] = torch.empty((self.rows, self.cols), dtype=dt, device=self.device)
+        self.tables = {}
+        for name, dt in TABLES:
+            if name.startswith("ppmax") and not with_accum:
+                continue
+            self.tables[name] = torch.empty((self.table_capacity,), dtype=dt, device=self.device)
+        self.io = _lib.MsRasters()
+        self.io.rows, self.io.cols = self.rows, self.cols
+        self.io.dem = self.dem.data_ptr()
+        for name, t in self.out.items():
+            setattr(self.io, name, t.data_ptr())
+        for name, t in self.tables.items():
+            setattr(self.io, name, t.data_ptr())
+        self.io.table_capacity = self.table_capacity
+        self.nlabels = 0
+        self.stats = {}
+        self._host = None
+
+    # ---- device-resident run (bench `value`) ---------------------------------------------------------
+    def run(self, dem=None):
+        """dem: optional cuda float32 tensor of the pipeline's shape (else self.dem is used as is)."""
+        if dem is not None and dem.data_ptr() != self.dem.data_ptr():
+            self.dem.copy_(dem)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with _lib.lock:
+            _lib.check(_lib.lib().ms_pipeline_dev(ctypes.byref(self.io), ctypes.c_void_p(stream)), "ms_pipeline_dev")
+        self.nlabels = int(self.io.nlabels)
+        self.stats = dict(zip(STAT_NAMES, [int(v) for v in self.io.stats]))
+        self.short, self.diag = float(self.io.short_eps), float(self.io.diag_eps)
+        return self
+
+    def table(self, name):
+        return self.tables[name][: self.nlabels + 1]
+
+    # ---- host-buffer run (bench `e2e`): H2D of the DEM, the run, D2H of every raster + table ---------
+    def host_buffers(self):
+        if self._host is None:
+            h = {"dem": torch.empty((self.rows, self.cols), dtype=torch.float32).pin_memory()}
+            for name, t in self.out.items():
+                h[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            for name, t in self.tables.items():
+                h[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            self._host = h
+        return self._host
+
+    def run_host(self, dem_host=None):
+        """dem_host: pinned (or pageable) float32 CPU tensor / ndarray.  Returns the dict of pinned host
+        tensors holding every output raster and the first nlabels+1 entries of every table."""
+        h = self.host_buffers()
+        if dem_host is not None:
+            src = torch.from_numpy(dem_host) if isinstance(dem_host, np.ndarray) else dem_host
+            if src.data_ptr() != h["dem"].data_ptr():
+                h["dem"].copy_(src)
+        self.dem.copy_(h["dem"], non_blocking=True)
+        self.run()
+        for name, t in self.out.items():
+            h[name].copy_(t, non_blocking=True)
+        m = self.nlabels + 1
+        for name, t in self.tables.items():
+            h[name][:m].copy_(t[:m], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return h
+
+    def bytes_h2d(self):
+        return self.rows * self.cols * 4
+
+    def bytes_d2h(self):
+        n = self.rows * self.cols
+        per_cell = sum(t.element_size() for t in self.out.values())
+        per_label = sum(t.element_size() for t in self.tables.values())
+        return n * per_cell + (self.nlabels + 1) * per_label
+
+
+def synth_fractal(rows, cols, seed=1, row0=0, col0=0, device=0, out=None):
+    """The synthetic fractal DEM (malstroem_b200/synth.py, bit-identical) generated on the device."""
+    dev = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with _lib.lock:
+        _lib.check(_lib.lib().ms_init(dev.index or 0), "ms_init")
+        _lib.check(_lib.lib().ms_synth_fractal_dev(out.data_ptr(), rows, cols, row0, col0, seed,
+                                                   ctypes.c_void_p(stream)), "ms_synth_fractal_dev")
+    return out

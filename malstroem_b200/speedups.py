@@ -1,0 +1,58 @@
+"""The plug-in switch, with the contract of malstroem/algorithms/speedups/__init__.py:22-100:
+`available`, `enabled`, `enable()`, `disable()`.
+
+enable() rebinds the twelve whole-function names the tool layer resolves at call time
+(malstroem/dem.py:67-89, malstroem/bluespots.py:159-205, malstroem/scripts/dem.py, scripts/bluespot.py) on the
+reference's own `malstroem.algorithms.{fill,flow,label}` modules to the B200 implementations, and leaves
+`malstroem.algorithms.speedups.enabled` truthy so the tools do not warn (dem.py:62, bluespots.py:154).
+Nothing else of the reference is touched; disable() restores the saved originals.
+"""
+import os
+import warnings
+
+from . import _lib
+from .algorithms import fill as _fill, flow as _flow, label as _label
+
+available = os.path.exists(_lib.LIB_PATH)
+enabled = False
+_orig = {}
+
+REBOUND = {
+    "fill": ("fill_terrain", "fill_terrain_no_flats", "minimum_safe_short_and_diag"),
+    "flow": ("terrain_flowdirection", "accumulated_flow", "watersheds_from_labels"),
+    "label": ("connected_components", "label_stats", "keep_labels", "label_min_index", "label_max_index",
+              "label_count"),
+}
+_OURS = {"fill": _fill, "flow": _flow, "label": _label}
+
+
+def enable(target=None):
+    """Rebind the hot-path functions of `target` (default: the imported `malstroem.algorithms` package)."""
+    global enabled
+    if not available:
+        warnings.warn("malstroem_b200: libmalstroem_b200.so not built; nothing enabled", RuntimeWarning)
+        return
+    if _orig:
+        return
+    if target is None:
+        import malstroem.algorithms as target      # the reference package must be importable
+    for modname, names in REBOUND.items():
+        mod = getattr(target, modname)
+        for name in names:
+            _orig[(modname, name)] = (mod, getattr(mod, name))
+            setattr(mod, name, getattr(_OURS[modname], name))
+    ref_speedups = getattr(target, "speedups", None)
+    if ref_speedups is not None:
+        _orig[("speedups", "enabled")] = (ref_speedups, ref_speedups.enabled)
+        ref_speedups.enabled = True
+    enabled = True
+
+
+def disable():
+    global enabled
+    if not _orig:
+        return
+    for (modname, name), (mod, fn) in _orig.items():
+        setattr(mod, name, fn)
+    _orig.clear()
+    enabled = False
