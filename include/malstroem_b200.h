@@ -46,6 +46,14 @@ const char *ms_last_error(void);
 int ms_device_count(void);
 /* launches of this library's own kernels since the last reset (bench.py's `gpu_launches`) */
 int64_t ms_kernel_launches(int reset);
+/* per-kernel CUDA-event timing on the launching stream: ms_profile(n >= 1) starts recording one event pair per
+ * launch (n > 1 pre-creates n pairs first), ms_profile(0) stops; ms_profile_report() synchronises the device and writes one line per kernel
+ * ("<name> <launches> <total ms> <total units>") into buf, then clears the records */
+int ms_profile(int enable);
+/* host-side accounting since the last reset: out4 = {seconds waiting in stream syncs, number of syncs,
+ * seconds inside pool allocations, number of allocations} */
+int ms_host_counters(double *out4, int reset);
+int ms_profile_report(char *buf, int64_t cap);
 /* pinned host memory for the host-pointer entry points (optional; pageable memory also works) */
 void *ms_host_alloc(int64_t bytes);
 int ms_host_free(void *p);

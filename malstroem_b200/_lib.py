@@ -31,6 +31,9 @@ SIGNATURES = {
     "ms_last_error": (ctypes.c_char_p, []),
     "ms_device_count": (c_int, []),
     "ms_kernel_launches": (c_i64, [c_int]),
+    "ms_profile": (c_int, [c_int]),
+    "ms_host_counters": (c_int, [c_p, c_int]),
+    "ms_profile_report": (c_int, [ctypes.c_char_p, c_i64]),
     "ms_host_alloc": (c_p, [c_i64]),
     "ms_host_free": (c_int, [c_p]),
     "ms_fill_terrain": (c_int, [c_p, c_p, c_p, c_i64, c_i64]),

@@ -28,10 +28,19 @@ extern int64_t g_launches;
         if (r__ != MS_OK) return r__; \
     } while (0)
 
+// optional per-kernel CUDA-event timing (ms_profile): one event pair per launch on the launching stream
+extern int g_prof;
+extern int64_t g_prof_units;      // "units" (cells) the next launch processes; consumed by prof_begin
+void prof_begin(const char *name, cudaStream_t s);
+void prof_end(cudaStream_t s);
+static inline void prof_units(int64_t u) { g_prof_units = u; }
+
 // kernel launch + error check + launch counter
 #define MS_LAUNCH(kernel, grid, block, smem, stream, ...)                                    \
     do {                                                                                     \
+        if (ms::g_prof) ms::prof_begin(#kernel, (stream));                                   \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
+        if (ms::g_prof) ms::prof_end((stream));                                              \
         ms::g_launches++;                                                                    \
         cudaError_t e__ = cudaGetLastError();                                                \
         if (e__ != cudaSuccess) {                                                            \
@@ -43,7 +52,21 @@ extern int64_t g_launches;
 
 int ensure_init();
 
-// ---- stream-ordered scratch buffer (cudaMallocAsync pool; freed in stream order) -----------------
+// host-side accounting (ms_host_counters): wall time spent waiting in stream syncs and in pool allocations
+extern double g_host_t[4];      // [0] sync seconds, [1] sync count, [2] alloc seconds, [3] alloc count
+int stream_sync(cudaStream_t s);
+double now_s();
+
+// ---- scratch memory: one device arena, stack discipline ------------------------------------------
+// All scratch of a call is carved from one cudaMalloc'ed arena with bump allocation (frees pop the top; an
+// out-of-order free is deferred until the blocks above it are gone).  Work of one call is ordered on one
+// stream, so a block can be handed out again without waiting.  The arena grows (when empty) to the high-water
+// mark of the previous call; a request that does not fit meanwhile is served by cudaMallocAsync.  This
+// replaced per-buffer cudaMallocAsync, whose pool re-mapped physical memory for the changing 256 MB-class
+// requests and cost 7-46 ms per step at 8192^2 (profiles/r01_host_overhead.txt).
+void *arena_alloc(size_t bytes, cudaStream_t s);
+void arena_free(void *p, cudaStream_t s);
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -55,16 +78,18 @@ struct DevBuf {
         release();
         s = stream;
         if (n == 0) n = 1;
-        cudaError_t e = cudaMallocAsync((void **)&p, n * sizeof(T), stream);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            set_error("cudaMallocAsync(%zu bytes) -> %s", n * sizeof(T), cudaGetErrorString(e));
+        double t0 = now_s();
+        p = (T *)arena_alloc(n * sizeof(T), stream);
+        g_host_t[2] += now_s() - t0;
+        g_host_t[3] += 1;
+        if (!p) {
+            set_error("device scratch allocation of %zu bytes failed", n * sizeof(T));
             return MS_ERR_CUDA;
         }
         return MS_OK;
     }
     void release() {
-        if (p) cudaFreeAsync(p, s);
+        if (p) arena_free(p, s);
         p = nullptr;
     }
     ~DevBuf() { release(); }

@@ -246,7 +246,7 @@ int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_
     MS_TRY(exclusive_scan_i32(tmp.p, tmp.p, n, total.p, s));
     MS_LAUNCH(k_catchment_ids, g1, 256, 0, s, lab.p, tmp.p, n);
     MS_CUDA(cudaMemcpyAsync(h, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     int nC = (int)h[0];
     tmp.release();
 
@@ -270,7 +270,7 @@ int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_
         MS_CUDA(cudaMemsetAsync(remaining.p, 0, sizeof(int), s));
         MS_LAUNCH(k_boruvka_update, gc, 256, 0, s, comp.p, E.p, parent.p, wk.p, nC, best.p, remaining.p);
         MS_CUDA(cudaMemcpyAsync(h, remaining.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-        MS_CUDA(cudaStreamSynchronize(s));
+        MS_TRY(ms::stream_sync(s));
         int64_t now = *(int *)h;
         rounds++;
         if (now >= live || rounds > 64) {
@@ -306,7 +306,7 @@ int ms_minmax_f32(const float *dem, int64_t n, float *out_min, float *out_max) {
     MS_TRY(ms::minmax_dev(d.p, n, o.p, s));
     float r[2];
     MS_CUDA(cudaMemcpyAsync(r, o.p, sizeof(r), cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     *out_min = r[0];
     *out_max = r[1];
     return MS_OK;
@@ -335,7 +335,7 @@ int ms_fill_terrain(const float *dtm, float *filled, float *depths, int64_t rows
     MS_TRY(ms::fill_terrain_dev_impl(d.p, f.p, depths ? dp.p : nullptr, rows, cols, nullptr, s));
     MS_CUDA(cudaMemcpyAsync(filled, f.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
     if (depths) MS_CUDA(cudaMemcpyAsync(depths, dp.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     return MS_OK;
 }
 

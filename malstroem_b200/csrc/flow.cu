@@ -226,7 +226,7 @@ int ms_flowdir(const double *terrain, uint8_t *flowdir, int64_t rows, int64_t co
     MS_CUDA(cudaMemcpyAsync(t.p, terrain, n * sizeof(double), cudaMemcpyHostToDevice, s));
     MS_TRY(ms::flowdir_dev_impl(t.p, o.p, rows, cols, edges_flow_outward, s));
     MS_CUDA(cudaMemcpyAsync(flowdir, o.p, n, cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     return MS_OK;
 }
 
@@ -247,7 +247,7 @@ int ms_accumulated_flow(const uint8_t *flowdir, double *accum, int64_t rows, int
     MS_CUDA(cudaMemcpyAsync(f.p, flowdir, n, cudaMemcpyHostToDevice, s));
     MS_TRY(ms::accum_dev_impl(f.p, a.p, rows, cols, s));
     MS_CUDA(cudaMemcpyAsync(accum, a.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     return MS_OK;
 }
 
@@ -274,7 +274,7 @@ int ms_watersheds_from_labels(const uint8_t *flowdir, void *labelled, int label_
     MS_CUDA(cudaMemcpyAsync(l.p, labelled, n * label_bytes, cudaMemcpyHostToDevice, s));
     MS_TRY(ms::watersheds_dev_impl(f.p, l.p, label_bytes, rows, cols, unassigned, nullptr, s));
     MS_CUDA(cudaMemcpyAsync(labelled, l.p, n * label_bytes, cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     return MS_OK;
 }
 

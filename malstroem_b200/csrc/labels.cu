@@ -490,7 +490,7 @@ struct ErrFlag {
     int check(const char *what) {
         int64_t *h = ms::host_flags().h;
         MS_CUDA(cudaMemcpyAsync(h + 16, d.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-        MS_CUDA(cudaStreamSynchronize(s));
+        MS_TRY(ms::stream_sync(s));
         if (*(int *)(h + 16)) {
             ms::set_error("%s: a label lies outside the table", what);
             return MS_ERR_LABEL;
@@ -521,7 +521,7 @@ int ms_connected_components_dev(const void *data, int dtype, int32_t *labels, in
     MS_TRY(ms::cc_dev_impl(data, dtype, labels, rows, cols, tot.p, s));
     int64_t *h = ms::host_flags().h;
     MS_CUDA(cudaMemcpyAsync(h, tot.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     if (nlabels) *nlabels = h[0];
     return MS_OK;
 }
@@ -540,7 +540,7 @@ int ms_connected_components(const void *data, int dtype, int32_t *labels, int64_
     MS_CUDA(cudaMemcpyAsync(d.p, data, n * es, cudaMemcpyHostToDevice, s));
     MS_TRY(ms_connected_components_dev(d.p, dtype, l.p, rows, cols, nlabels, s));
     MS_CUDA(cudaMemcpyAsync(labels, l.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     return MS_OK;
 }
 
@@ -561,7 +561,7 @@ int ms_label_range(const int32_t *labels, int64_t n, int32_t *out_min, int32_t *
     MS_TRY(ms::label_range_dev_impl(l.p, n, o.p, s));
     int32_t r[2];
     MS_CUDA(cudaMemcpyAsync(r, o.p, sizeof(r), cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     if (out_min) *out_min = r[0];
     if (out_max) *out_max = r[1];
     return MS_OK;
@@ -603,7 +603,7 @@ int ms_label_stats(const void *data, int dtype, const int32_t *labels, int64_t n
     MS_CUDA(cudaMemcpyAsync(out_max, b.p, m * 8, cudaMemcpyDeviceToHost, s));
     MS_CUDA(cudaMemcpyAsync(out_sum, c.p, m * 8, cudaMemcpyDeviceToHost, s));
     MS_CUDA(cudaMemcpyAsync(out_count, k.p, m * 8, cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     return MS_OK;
 }
 
@@ -637,7 +637,7 @@ int ms_label_extreme_index(const double *data, const int32_t *labels, int64_t ro
     MS_CUDA(cudaMemcpyAsync(out_value, v.p, m * 8, cudaMemcpyDeviceToHost, s));
     MS_CUDA(cudaMemcpyAsync(out_row, r.p, m * 8, cudaMemcpyDeviceToHost, s));
     MS_CUDA(cudaMemcpyAsync(out_col, c.p, m * 8, cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     return MS_OK;
 }
 
@@ -662,7 +662,7 @@ int ms_label_count(const int32_t *labels, int64_t n, int64_t nbins, int64_t *out
     MS_TRY(ms::label_count_dev_impl(l.p, n, nbins, c.p, ef.d.p, s));
     MS_TRY(ef.check("label_count"));
     MS_CUDA(cudaMemcpyAsync(out_count, c.p, (size_t)nbins * 8, cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     return MS_OK;
 }
 
@@ -690,7 +690,7 @@ int ms_keep_labels(const int32_t *labels, int64_t n, const uint8_t *keep, int64_
     MS_TRY(ms::keep_labels_dev_impl(l.p, n, k.p, nkeep, o.p, ef.d.p, s));
     MS_TRY(ef.check("keep_labels"));
     MS_CUDA(cudaMemcpyAsync(out, o.p, (size_t)n, cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     return MS_OK;
 }
 

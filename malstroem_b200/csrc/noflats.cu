@@ -213,11 +213,12 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
             MS_CUDA(cudaMemsetAsync(count.p, 0, sizeof(int), s));
             MS_LAUNCH(k_nf_compact, cdiv(ntiles, 256), 256, 0, s, tileflag.p, list.p, count.p, ntiles);
             MS_CUDA(cudaMemcpyAsync(h, count.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-            MS_CUDA(cudaStreamSynchronize(s));
+            MS_TRY(ms::stream_sync(s));
             int na = *(int *)h;
             if (na == 0) break;
             rounds++;
             visits += na;
+            prof_units((int64_t)na * NF_T * NF_T);
             MS_LAUNCH(k_nf_relax, na, 256, NF_SMEM, s, dtm, out, list.p, tileflag.p, (int)rows, (int)cols, tiles_x,
                       tiles_y, sh, dg);
             if (rounds > 4ll * (tiles_x + tiles_y) * NF_T * NF_T) {
@@ -228,7 +229,7 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
         MS_CUDA(cudaMemsetAsync(count.p + 1, 0, sizeof(int), s));
         MS_LAUNCH(k_nf_verify, g2, 256, 0, s, dtm, out, banned.p, count.p + 1, (int)rows, (int)cols, sh, dg);
         MS_CUDA(cudaMemcpyAsync(h, count.p + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
-        MS_CUDA(cudaStreamSynchronize(s));
+        MS_TRY(ms::stream_sync(s));
         int nviol = *(int *)h;
         if (nviol == 0) break;
         if (!banned.p) {
@@ -275,7 +276,7 @@ int ms_fill_terrain_no_flats(const float *dtm, double short_eps, double diag_eps
     MS_CUDA(cudaMemcpyAsync(d.p, dtm, n * sizeof(float), cudaMemcpyHostToDevice, s));
     MS_TRY(ms::fill_no_flats_dev_impl(d.p, nullptr, short_eps, diag_eps, o.p, rows, cols, nullptr, s));
     MS_CUDA(cudaMemcpyAsync(out, o.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     return MS_OK;
 }
 

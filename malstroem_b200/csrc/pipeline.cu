@@ -43,7 +43,7 @@ extern "C" int ms_pipeline_dev(ms_rasters *io, void *stream) {
     MS_TRY(mm.alloc(2, s));
     MS_TRY(minmax_dev(io->dem, n, mm.p, s));
     MS_CUDA(cudaMemcpyAsync(h + 24, mm.p, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     float lo = ((float *)(h + 24))[0], hi = ((float *)(h + 24))[1];
     double maxval = (double)fmaxf(fabsf(hi), fabsf(lo));
     io->short_eps = (nextafter(maxval, (double)INFINITY) - maxval) * 1024.0;
@@ -63,7 +63,7 @@ extern "C" int ms_pipeline_dev(ms_rasters *io, void *stream) {
     MS_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), s));
     MS_TRY(cc_dev_impl(io->depths, MS_F32, io->labels, rows, cols, tot.p, s));
     MS_CUDA(cudaMemcpyAsync(h, tot.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaStreamSynchronize(s));
+    MS_TRY(ms::stream_sync(s));
     io->nlabels = h[0];
     if (io->nlabels + 1 > io->table_capacity) {
         set_error("pipeline: %lld labels do not fit table_capacity %lld", (long long)io->nlabels,

@@ -175,7 +175,7 @@ int forest_resolve(int *ptr, int64_t n, int64_t *rounds_out, cudaStream_t s) {
         MS_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
         MS_LAUNCH(k_forest_jump, cdiv(n, 256), 256, 0, s, ptr, n, flag.p);
         MS_CUDA(cudaMemcpyAsync(h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-        MS_CUDA(cudaStreamSynchronize(s));
+        MS_TRY(ms::stream_sync(s));
         rounds++;
         if (*(int *)h == 0) break;
         if (rounds >= 64) {
