@@ -58,12 +58,7 @@ int flowdir_dev_impl(const double *t, uint8_t *out, int64_t rows, int64_t cols, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4.  flow.accumulated_flow (flow.py:344-364; speedups/_flow.pyx:225-273): accum(c) = 1 + sum of accum
-// over the cells that flow into c, i.e. the size of c's upstream tree, as exact float64 integers.
-// Here: in-degree count, then every leaf walks downstream carrying its finished value: add it to the
-// next cell, decrement that cell's in-degree, and carry on only if that was the last missing input
-// (the reference's tracer rule "stop at a cell with an unresolved upstream cell", run from all leaves
-// at once).  Codes > 7 and steps off the raster end a walk.
+// K4 (flow.accumulated_flow) lives in accum.cu; d8_next below is shared with K7.
 // ------------------------------------------------------------------------------------------------
 __device__ inline bool d8_next(int r, int c, int d, int rows, int cols, int *nr, int *nc) {
     if (d > 7) return false;
@@ -72,57 +67,7 @@ __device__ inline bool d8_next(int r, int c, int d, int rows, int cols, int *nr,
     return *nr >= 0 && *nr < rows && *nc >= 0 && *nc < cols;
 }
 
-__global__ void __launch_bounds__(256) k_acc_indeg(const uint8_t *__restrict__ fd, int *__restrict__ indeg,
-                                                   double *__restrict__ acc, int rows, int cols) {
-    int c = blockIdx.x * 64 + (threadIdx.x & 63);
-    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (r >= rows || c >= cols) return;
-    size_t i = (size_t)r * cols + c;
-    int n = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        int nr = r + kDR[k], nc = c + kDC[k];
-        if (nr < 0 || nr >= rows || nc < 0 || nc >= cols) continue;
-        n += (__ldg(fd + (size_t)nr * cols + nc) == ((k + 4) & 7));
-    }
-    indeg[i] = n ? n : -1;      // -1 marks a leaf: only leaves start a walk (0 = resolved by a walker)
-    acc[i] = 1.0;
-}
-
-__global__ void __launch_bounds__(256) k_acc_trace(const uint8_t *__restrict__ fd, int *indeg, double *acc,
-                                                   int rows, int cols) {
-    int c = blockIdx.x * 64 + (threadIdx.x & 63);
-    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (r >= rows || c >= cols) return;
-    size_t i = (size_t)r * cols + c;
-    if (__ldcg(indeg + i) != -1) return;
-    double carried = 1.0;
-    for (;;) {
-        int nr, nc;
-        if (!d8_next(r, c, fd[i], rows, cols, &nr, &nc)) return;
-        size_t j = (size_t)nr * cols + nc;
-        atomicAdd(acc + j, carried);
-        __threadfence();
-        if (atomicSub(indeg + j, 1) != 1) return;
-        __threadfence();
-        carried = __ldcg(acc + j);
-        r = nr; c = nc; i = j;
-    }
-}
-
-int accum_dev_impl(const uint8_t *fd, double *acc, int64_t rows, int64_t cols, cudaStream_t s) {
-    if (!fd || !acc) { set_error("accumulated_flow: null pointer"); return MS_ERR_ARG; }
-    if (rows < 1 || cols < 1 || rows * cols > (1ll << 30)) {
-        set_error("accumulated_flow: unsupported shape %lld x %lld", (long long)rows, (long long)cols);
-        return MS_ERR_SHAPE;
-    }
-    DevBuf<int> indeg;
-    MS_TRY(indeg.alloc((size_t)(rows * cols), s));
-    dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
-    MS_LAUNCH(k_acc_indeg, g2, 256, 0, s, fd, indeg.p, acc, (int)rows, (int)cols);
-    MS_LAUNCH(k_acc_trace, g2, 256, 0, s, fd, indeg.p, acc, (int)rows, (int)cols);
-    return MS_OK;
-}
+int accum_dev_impl(const uint8_t *fd, double *acc, int64_t rows, int64_t cols, cudaStream_t s);   // accum.cu
 
 // ------------------------------------------------------------------------------------------------
 // K7.  flow.watersheds_from_labels (flow.py:398-412; speedups/_flow.pyx:276-403).  The reference walks
