@@ -11,14 +11,15 @@
 //   k_nf_init    a dry cell (plain fill F == z) that has a strictly lower filled neighbour is seeded with
 //                W = z; every other interior cell starts at +inf (these are the lake / flat cells, 20-35 %
 //                of a fractal DEM).  Tiles holding a non-seed cell become active.
-//   k_nf_solve   ONE cooperative launch, CTAs resident on every SM.  Rounds: the CTAs take the active 64x64
-//                tiles off a list (ticket counter); a tile + 1-cell apron is held in shared memory and relaxed
-//                block-wise: the tile is 8x8 blocks of 8x8 cells, a 64-bit mask says which blocks may still
-//                change, a warp takes a dirty block (2 cells per lane), iterates it until it is quiet and
-//                marks the neighbouring blocks whose edge it changed.  Work therefore follows the wave fronts
-//                instead of sweeping 4096 cells per pass.  A tile whose outer ring changed appends its
-//                neighbours to the next round's list (flag + atomic append); grid.sync() separates rounds;
-//                the kernel ends when a round's list is empty.  No host round trips.
+//   k_nf_solve   ONE cooperative launch, CTAs resident on every SM, fed by a device-side FIFO of active 64x64
+//                tiles (ticket ring buffer; a counter of queued + running tiles ends the kernel).  A tile +
+//                1-cell apron is held in shared memory and relaxed block-wise: the tile is 8x8 blocks of 8x8
+//                cells, a 64-bit mask says which blocks may still change, a warp takes a dirty block (2 cells
+//                per lane), iterates it until it is quiet and marks the neighbouring blocks whose edge it
+//                changed.  Work therefore follows the wave fronts instead of sweeping 4096 cells per pass.  A
+//                tile whose outer ring changed queues its neighbours (per-tile flag word = which of its sides
+//                must be looked at).  No rounds, no host round trips: a wave moves on as soon as the tile it
+//                leaves has been written back.
 //   k_nf_verify  one stencil pass checks the equation everywhere.  Relaxed cells satisfy it by
 //                construction; a seed can only fail by being too LOW (its lower neighbour is closer than
 //                the accumulated epsilons).  Failing seeds are banned and the solve restarts — the result
@@ -47,17 +48,18 @@ constexpr int NF_SMEM = (NF_T + 2) * NF_LD * 8 + NF_T * NF_T * 4;
 constexpr int NF_BLOCK_ITERS = 64;   // in-block iteration guard (a block that hits it stays dirty)
 
 #ifdef NF_STATS
-__device__ unsigned long long g_nf_dbg[4 + 8 * 4096];   // [0] tile iterations [1] block visits [2] block iterations [3] -, then per round (n, ns)
+__device__ unsigned long long g_nf_dbg[16];   // [0] tile iterations [1] block visits [2] block iterations [3] -, then per round (n, ns)
 __device__ inline unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #endif
 
 struct NfCtl {
-    int count[3];      // entries of tile list k (round r reads list r%3, appends to (r+1)%3, clears (r+2)%3)
-    int ticket[3];     // next entry of list k to hand out
-    int nonseed;       // cells k_nf_init left at +inf
-    int nviol;         // cells failing k_nf_verify
-    int rounds;
+    unsigned head, tail;   // FIFO tickets: next entry to take / next entry to fill
+    int pending;           // tiles queued or being processed
+    int done;              // 1: no work left; 2: a consumer gave up waiting (watchdog)
+    int nonseed;           // cells k_nf_init left at +inf
+    int nviol;             // cells failing k_nf_verify
     int visits;
+    int reserved;
 };
 
 __device__ inline double dmin2(double a, double b) { return a <= b ? a : b; }
@@ -65,7 +67,8 @@ __device__ inline double dmin4(double a, double b, double c, double d) { return 
 
 __global__ void __launch_bounds__(256) k_nf_init(const float *__restrict__ z, const float *__restrict__ F,
                                                  double *__restrict__ W, const uint8_t *__restrict__ banned,
-                                                 int *tileflag, NfCtl *ctl, int rows, int cols, int tiles_x) {
+                                                 int *tileflag, int *tilesides, NfCtl *ctl, int rows, int cols,
+                                                 int tiles_x) {
     int c = blockIdx.x * 64 + (threadIdx.x & 63);
     int r = blockIdx.y * 4 + (threadIdx.x >> 6);
     bool nonseed = false;
@@ -91,17 +94,28 @@ __global__ void __launch_bounds__(256) k_nf_init(const float *__restrict__ z, co
     }
     // the 4 rows x 64 columns of this CTA lie in one tile
     int cnt = __syncthreads_count(nonseed);
+    int tile = ((blockIdx.y * 4) / NF_T) * tiles_x + blockIdx.x;
     if (threadIdx.x == 0 && cnt) {
         atomicAdd(&ctl->nonseed, cnt);
-        tileflag[((blockIdx.y * 4) / NF_T) * tiles_x + blockIdx.x] = 16;
+        tileflag[tile] = 16;
+    }
+    // sides of the tile along which a lake / flat cell lies (only those can be affected from outside)
+    if (nonseed) {
+        int lr = r & (NF_T - 1), lc = c & (NF_T - 1);
+        int sides = (lr == 0 ? 1 : 0) | (lr == NF_T - 1 || r == rows - 2 ? 2 : 0) | (lc == 0 ? 4 : 0) |
+                    (lc == NF_T - 1 || c == cols - 2 ? 8 : 0);
+        if (sides) atomicOr(tilesides + tile, sides);
     }
 }
 
-// flagged tiles -> list 0 (flags stay set: the solver clears a tile's flag when it picks the tile up)
-__global__ void __launch_bounds__(256) k_nf_compact(const int *tileflag, int *list, NfCtl *ctl, int ntiles) {
+// flagged tiles -> the FIFO (flags stay set: the solver clears a tile's flag word when it takes the tile)
+__global__ void __launch_bounds__(256) k_nf_compact(const int *tileflag, int *ring, NfCtl *ctl, int ntiles) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
-    if (tileflag[t]) list[atomicAdd(&ctl->count[0], 1)] = t;
+    if (tileflag[t]) {
+        ring[atomicAdd(&ctl->tail, 1u)] = t;
+        atomicAdd(&ctl->pending, 1);
+    }
 }
 
 // ---- in-tile relaxation -------------------------------------------------------------------------------
@@ -224,7 +238,7 @@ struct NfTileShared {
     int ring;          // bit 0/1/2/3: the tile's top / bottom / left / right ring changed
     int k;             // ticket
     int flags;         // side bits this tile was queued with
-    int e;             // common binade exponent of the tile's lake cells (integer form)
+    int e, elo;        // largest / smallest binade exponent of the tile's lake cells (integer form needs e == elo)
     int bad;           // tile does not qualify for the integer form
     int dmax;          // largest finite distance loaded
 };
@@ -285,35 +299,52 @@ __device__ inline int nf_tile_iterate(const R &rx, NfTileShared &S) {
     return it;
 }
 
-// lake cell (w > f) -> integer distance; anything else -> wall.  Tracks the common binade.
-__device__ inline int nf_to_int(double w, float f, NfTileShared &S, int &e_seen, int &dmax) {
+// lake cell (w > f) -> integer distance; anything else -> wall.  Tracks the range of binades seen (elo..ehi).
+__device__ inline int nf_to_int(double w, float f, int &bad, int &elo, int &ehi, int &dmax) {
     double fd = (double)f;
     if (!(w > fd)) return D_WALL;
-    long long mag = __double_as_longlong(fd) & 0x7fffffffffffffffll;
-    if (fd < 0) mag -= 1;                       // values above a negative F have the smaller magnitude
-    int e = (int)(mag >> 52) - 1023;
-    if (fd == 0.0 || e < -900) { S.bad = 1; return D_WALL; }
-    if (e != e_seen) {
-        int old = atomicCAS(&S.e, INT_MIN, e);
-        if (old != INT_MIN && old != e) S.bad = 1;
-        e_seen = e;
-    }
+    int hi = __double2hiint(fd);
+    int e = ((hi >> 20) & 0x7ff) - 1023;
+    // values just above a negative power of two have the smaller magnitude: they live one binade lower
+    if (fd < 0 && (hi & 0xfffff) == 0 && __double2loint(fd) == 0) e -= 1;
+    if (fd == 0.0 || e < -900) { bad = 1; return D_WALL; }
+    elo = min(elo, e);
+    ehi = max(ehi, e);
     if (w == INFINITY) return D_INF;
-    int ew = (int)((__double_as_longlong(w) & 0x7fffffffffffffffll) >> 52) - 1023;
-    if (ew != e) { S.bad = 1; return D_WALL; }
-    double inv_ulp = __longlong_as_double((long long)(1023 - (e - 52)) << 52);
+    int ew = ((__double2hiint(w) >> 20) & 0x7ff) - 1023;
+    if (ew != e) { bad = 1; return D_WALL; }
+    double inv_ulp = __hiloint2double((1023 - (e - 52)) << 20, 0);
     double d = (w - fd) * inv_ulp;              // exact: same binade, both multiples of its ulp
-    if (!(d < (double)D_LIMIT)) { S.bad = 1; return D_WALL; }
+    if (!(d < (double)D_LIMIT)) { bad = 1; return D_WALL; }
     int di = (int)d;
     dmax = max(dmax, di);
     return di;
 }
 
+// tile flag word: bits 0-3 = sides of the tile whose apron changed, bit 4 = look at everything; NF_RUNNING while
+// a CTA holds the tile.  "Side bits set and not running" means the tile is in the FIFO (exactly once).
+constexpr int NF_SIDES = 31;
+constexpr int NF_RUNNING = 256;
+
+__device__ inline void nf_push(int *ring, int cap, NfCtl *ctl, int tile) {
+    atomicAdd(&ctl->pending, 1);
+    unsigned idx = atomicAdd(&ctl->tail, 1u);
+    volatile int *slot = ring + (idx % (unsigned)cap);
+    // the ring holds every tile at most once, so the slot is free; wait if it is not (yet)
+    for (unsigned spins = 0; *slot != -1 && spins < (1u << 23); spins++) __nanosleep(100);
+    *slot = tile;
+}
+
+// converts one loaded row pair of the integer form (cells 2*lane, 2*lane+1 and, for lanes 0/1, an apron column)
+struct NfRowRegs {
+    double w0, w1, wa;
+    float f0, f1, fa;
+};
+
 template <bool CAP>
-__global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc, double *W, int *lists, int *tileflag,
-                                                  NfCtl *ctl, int rows, int cols, int tiles_x, int tiles_y, int ntiles,
-                                                  double sh, double dg, int max_rounds, int use_int) {
-    cg::grid_group grid = cg::this_grid();
+__global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc, double *W, int *ring, int cap,
+                                                  int *tileflag, const int *__restrict__ tilesides, NfCtl *ctl, int rows, int cols, int tiles_x,
+                                                  int tiles_y, double sh, double dg, int use_int) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sw = reinterpret_cast<double *>(smem_raw);
     float *sz = reinterpret_cast<float *>(smem_raw + (NF_T + 2) * NF_LD * 8);
@@ -321,227 +352,234 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
     __shared__ NfTileShared S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double capB = CAP ? ((double)ctl->nonseed + 16.0) * dg * 1.001 : 0.0;
+    if (*(volatile unsigned *)&ctl->tail == 0) return;      // nothing was queued (tail only grows)
 
-    for (int round = 0; round < max_rounds; round++) {
-        const int cur = round % 3, nxt = (round + 1) % 3, clr = (round + 2) % 3;
-        const int n = *(volatile int *)&ctl->count[cur];
-        if (n == 0) break;
-        if (blockIdx.x == 0 && tid == 0) {
-            ctl->count[clr] = 0;
-            ctl->ticket[clr] = 0;
-            ctl->rounds = round + 1;
-            ctl->visits += n;
-        }
-        const int *list = lists + (size_t)cur * ntiles;
-        int *listn = lists + (size_t)nxt * ntiles;
-#ifdef NF_STATS
-        unsigned long long t_round = gtimer();
-#endif
-        for (;;) {
-            __syncthreads();
-            if (tid == 0) S.k = atomicAdd(&ctl->ticket[cur], 1);
-            __syncthreads();
-            const int k = S.k;
-            if (k >= n) break;
-            const int t = __ldcg(list + k);
-#ifdef NF_STATS
-            long long tc0 = clock64(), tc1 = 0, tc2 = 0; int nit = 0;
-#endif
-            const int ty = t / tiles_x, tx = t - ty * tiles_x;
-            const int r0 = ty * NF_T, c0 = tx * NF_T;
-            if (tid == 0) {
-                // picked up: later changes of a neighbour's ring must queue this tile again
-                S.flags = atomicExch(tileflag + t, 0);
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            // take the next FIFO entry; wait for it to be filled unless all work is done
+            unsigned my = atomicAdd(&ctl->head, 1u);
+            volatile int *slot = ring + (my % (unsigned)cap);
+            int t = -1;
+            for (unsigned spins = 0;; spins++) {
+                t = *slot;
+                if (t >= 0) break;
+                if (*(volatile int *)&ctl->done) break;
+                __nanosleep(200);
+                if (spins > (1u << 23)) { atomicExch(&ctl->done, 2); break; }      // watchdog (~2 s): never hang the GPU
+            }
+            if (t >= 0) {
+                *slot = -1;
+                __threadfence();
+                // taken: while the tile runs, neighbours only leave their side bits; they are looked at when it ends
+                S.flags = atomicExch(tileflag + t, NF_RUNNING) & NF_SIDES;
                 S.dirty[1] = 0;
                 S.dirty[2] = 0;
                 S.chgmask = 0;
                 S.ring = 0;
                 S.e = INT_MIN;
+                S.elo = INT_MAX;
                 S.bad = 0;
                 S.dmax = 0;
+                atomicAdd(&ctl->visits, 1);
             }
-            __threadfence();
-            __syncthreads();
-            bool solved = false;
-            if (CAP && use_int) {
-                // ---- integer form: load tile + apron, convert on the fly
-                int e_seen = INT_MIN, dmax = 0;
-                const bool vec = ((cols & 1) == 0) && (c0 + NF_T <= cols);
-                for (int lr = warp; lr < NF_T + 2; lr += 8) {
-                    int r = r0 + lr - 1;
-                    int *row = sdi + lr * NF_ILD;
-                    if (r < 0 || r >= rows) {
-                        row[1 + 2 * lane] = D_WALL;
-                        row[2 + 2 * lane] = D_WALL;
-                        if (lane < 2) row[lane ? NF_T + 1 : 0] = D_WALL;
-                        continue;
-                    }
-                    const double *wr = W + (size_t)r * cols;
-                    const float *fr = zsrc + (size_t)r * cols;
-                    int c = c0 + 2 * lane;
-                    double w0v, w1v;
-                    float f0v, f1v;
-                    if (vec) {
-                        double2 wv = __ldcg(reinterpret_cast<const double2 *>(wr + c));
-                        float2 fv = __ldg(reinterpret_cast<const float2 *>(fr + c));
-                        w0v = wv.x; w1v = wv.y; f0v = fv.x; f1v = fv.y;
-                    } else {
-                        w0v = c < cols ? __ldcg(wr + c) : 0.0;
-                        f0v = c < cols ? __ldg(fr + c) : 0.f;
-                        w1v = c + 1 < cols ? __ldcg(wr + c + 1) : 0.0;
-                        f1v = c + 1 < cols ? __ldg(fr + c + 1) : 0.f;
-                    }
-                    row[1 + 2 * lane] = nf_to_int(w0v, f0v, S, e_seen, dmax);
-                    row[2 + 2 * lane] = nf_to_int(w1v, f1v, S, e_seen, dmax);
-                    if (lane < 2) {
-                        int ca = lane ? c0 + NF_T : c0 - 1;
-                        int v = D_WALL;
-                        if (ca >= 0 && ca < cols) v = nf_to_int(__ldcg(wr + ca), __ldg(fr + ca), S, e_seen, dmax);
-                        row[lane ? NF_T + 1 : 0] = v;
-                    }
-                }
-                dmax = __reduce_max_sync(0xffffffffu, dmax);
-                if (lane == 0 && dmax) atomicMax(&S.dmax, dmax);
-                __syncthreads();
-                double ulp = 0, sqd = 0, dqd = 0;
-                bool ok = !S.bad;
-                if (ok && S.e != INT_MIN) {
-                    int e = S.e;
-                    ulp = __longlong_as_double((long long)(e - 52 + 1023) << 52);
-                    double inv_ulp = __longlong_as_double((long long)(1023 - (e - 52)) << 52);
-                    sqd = sh * inv_ulp;
-                    double dqx = dg * inv_ulp;
-                    dqd = rint(dqx);
-                    double fr2 = fabs(dqx - floor(dqx) - 0.5);
-                    // short must be a whole number of ulps, diag must not sit on a rounding tie, and the distances
-                    // this tile can reach must stay far from the integer range's end
-                    ok = sqd >= 1.0 && sqd == rint(sqd) && dqd >= 1.0 && fr2 > 1e-9 && dqd < (double)(1 << 27) &&
-                         sqd < (double)(1 << 27) && S.dmax < D_LIMIT;
-                }
-                if (ok && S.e == INT_MIN) {
-                    solved = true;                      // no lake cell in the tile or its apron: nothing to do
-                } else if (ok) {
-                    if (tid == 0) S.dirty[0] = nf_region(S.flags);
-                    __syncthreads();
-                    RelaxI32 rx{sdi, (int)sqd, (int)dqd, &S.bad};
+            S.k = t;
+        }
+        __syncthreads();
+        const int t = S.k;
+        if (t < 0) break;
 #ifdef NF_STATS
-                    tc1 = clock64();
+        long long tc0 = clock64(), tc1 = 0, tc2 = 0; int nit = 0;
 #endif
-                    int its = nf_tile_iterate(rx, S);
-#ifdef NF_STATS
-                    nit = its;
-#endif
-                    (void)its;
-                    solved = !S.bad;                    // a distance left the trusted range: redo the tile in float64
-                    // write back the blocks that changed: W = F + D * ulp (exact)
-                    unsigned long long mm = solved ? S.chgmask : 0ull;
-                    for (int idx = 0; mm; idx++) {
-                        int b = __ffsll((long long)mm) - 1;
-                        mm &= mm - 1;
-                        if ((idx & 7) != warp) continue;
-                        int lr = (b >> 3) * 8 + (lane >> 2), lc = (b & 7) * 8 + (lane & 3) * 2;
-                        int r = r0 + lr, c = c0 + lc;
-                        const int *p = sdi + (lr + 1) * NF_ILD + (lc + 1);
-                        if (r < rows) {
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        const int r0 = ty * NF_T, c0 = tx * NF_T;
+        bool solved = false;
+        if (CAP && use_int) {
+            // ---- integer form: load tile + apron (all loads of a batch in flight together), convert on the fly
+            int bad = 0, elo = INT_MAX, ehi = INT_MIN, dmax = 0;
+            const bool vec = ((cols & 1) == 0) && (c0 + NF_T <= cols);
 #pragma unroll
-                            for (int q = 0; q < 2; q++) {
-                                int d = p[q];
-                                if (c + q < cols && d < D_INF) {
-                                    size_t i = (size_t)r * cols + c + q;
-                                    W[i] = __dadd_rn((double)__ldg(zsrc + i), __dmul_rn((double)d, ulp));
-                                }
-                            }
+            for (int half = 0; half < 2; half++) {
+                NfRowRegs rg[5];
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    int lr = warp + 8 * (half * 5 + j);
+                    int r = r0 + lr - 1;
+                    rg[j].w0 = rg[j].w1 = rg[j].wa = 0.0;
+                    rg[j].f0 = rg[j].f1 = rg[j].fa = 0.f;          // w == f: a wall
+                    if (lr < NF_T + 2 && r >= 0 && r < rows) {
+                        const double *wr = W + (size_t)r * cols;
+                        const float *fr = zsrc + (size_t)r * cols;
+                        int c = c0 + 2 * lane;
+                        if (vec) {
+                            double2 wv = __ldcg(reinterpret_cast<const double2 *>(wr + c));
+                            float2 fv = __ldg(reinterpret_cast<const float2 *>(fr + c));
+                            rg[j].w0 = wv.x; rg[j].w1 = wv.y; rg[j].f0 = fv.x; rg[j].f1 = fv.y;
+                        } else {
+                            if (c < cols) { rg[j].w0 = __ldcg(wr + c); rg[j].f0 = __ldg(fr + c); }
+                            if (c + 1 < cols) { rg[j].w1 = __ldcg(wr + c + 1); rg[j].f1 = __ldg(fr + c + 1); }
+                        }
+                        if (lane < 2) {
+                            int ca = lane ? c0 + NF_T : c0 - 1;
+                            if (ca >= 0 && ca < cols) { rg[j].wa = __ldcg(wr + ca); rg[j].fa = __ldg(fr + ca); }
                         }
                     }
                 }
-                if (!solved) __syncthreads();          // everybody is done with the integer tile before it is overwritten
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    int lr = warp + 8 * (half * 5 + j);
+                    if (lr < NF_T + 2) {
+                        int *row = sdi + lr * NF_ILD;
+                        row[1 + 2 * lane] = nf_to_int(rg[j].w0, rg[j].f0, bad, elo, ehi, dmax);
+                        row[2 + 2 * lane] = nf_to_int(rg[j].w1, rg[j].f1, bad, elo, ehi, dmax);
+                        if (lane < 2) row[lane ? NF_T + 1 : 0] = nf_to_int(rg[j].wa, rg[j].fa, bad, elo, ehi, dmax);
+                    }
+                }
             }
-            if (!solved) {
-                // ---- float64 form
-                if (tid == 0) {
-                    S.dirty[0] = nf_region(S.flags);
-                    S.dirty[1] = 0;
-                    S.dirty[2] = 0;
-                    S.chgmask = 0;
-                    S.ring = 0;
-                }
-                for (int q = tid; q < (NF_T + 2) * (NF_T + 2); q += 256) {
-                    int lr = q / (NF_T + 2), lc = q - lr * (NF_T + 2);
-                    int r = r0 + lr - 1, c = c0 + lc - 1;
-                    double v = INFINITY;
-                    if (r >= 0 && r < rows && c >= 0 && c < cols) v = __ldcg(W + (size_t)r * cols + c);
-                    sw[lr * NF_LD + lc] = v;
-                }
-                for (int q = tid; q < NF_T * NF_T; q += 256) {
-                    int lr = q >> 6, lc = q & 63;
-                    int r = r0 + lr, c = c0 + lc;
-                    sz[q] = (r < rows && c < cols) ? __ldg(zsrc + (size_t)r * cols + c) : INFINITY;
-                }
+            dmax = __reduce_max_sync(0xffffffffu, dmax);
+            elo = __reduce_min_sync(0xffffffffu, elo);
+            ehi = __reduce_max_sync(0xffffffffu, ehi);
+            bad = __any_sync(0xffffffffu, bad);
+            if (lane == 0) {
+                if (dmax) atomicMax(&S.dmax, dmax);
+                if (ehi != INT_MIN) { atomicMin(&S.elo, elo); atomicMax(&S.e, ehi); }
+                if (bad) S.bad = 1;
+            }
+            __syncthreads();
+            double ulp = 0, sqd = 0, dqd = 0;
+            bool ok = !S.bad && (S.e == INT_MIN || S.e == S.elo);
+            if (ok && S.e != INT_MIN) {
+                int e = S.e;
+                ulp = __longlong_as_double((long long)(e - 52 + 1023) << 52);
+                double inv_ulp = __longlong_as_double((long long)(1023 - (e - 52)) << 52);
+                sqd = sh * inv_ulp;
+                double dqx = dg * inv_ulp;
+                dqd = rint(dqx);
+                double fr2 = fabs(dqx - floor(dqx) - 0.5);
+                // short must be a whole number of ulps, diag must not sit on a rounding tie, and the distances
+                // must stay inside the range the integer form is trusted for
+                ok = sqd >= 1.0 && sqd == rint(sqd) && dqd >= 1.0 && fr2 > 1e-9 && dqd < (double)(1 << 27) &&
+                     sqd < (double)(1 << 27) && S.dmax < D_LIMIT;
+            }
+            if (ok && S.e == INT_MIN) {
+                solved = true;                      // no lake cell in the tile or its apron: nothing to do
+            } else if (ok) {
+                if (tid == 0) S.dirty[0] = nf_region(S.flags);
                 __syncthreads();
+                RelaxI32 rx{sdi, (int)sqd, (int)dqd, &S.bad};
 #ifdef NF_STATS
                 tc1 = clock64();
 #endif
-                RelaxF64<CAP> rx{sw, sz, sh, dg, capB};
                 int its = nf_tile_iterate(rx, S);
 #ifdef NF_STATS
                 nit = its;
 #endif
                 (void)its;
-                // write back the blocks that changed: a warp writes 8 rows of 8 doubles (lane: row l/4, 2 columns)
-                unsigned long long mm = S.chgmask;
+                solved = !S.bad;                    // a distance left the trusted range: redo the tile in float64
+                // write back the blocks that changed: W = F + D * ulp (exact)
+                unsigned long long mm = solved ? S.chgmask : 0ull;
                 for (int idx = 0; mm; idx++) {
                     int b = __ffsll((long long)mm) - 1;
                     mm &= mm - 1;
                     if ((idx & 7) != warp) continue;
                     int lr = (b >> 3) * 8 + (lane >> 2), lc = (b & 7) * 8 + (lane & 3) * 2;
                     int r = r0 + lr, c = c0 + lc;
-                    const double *p = sw + (lr + 1) * NF_LD + (lc + 1);
+                    const int *p = sdi + (lr + 1) * NF_ILD + (lc + 1);
                     if (r < rows) {
-                        if (c < cols) W[(size_t)r * cols + c] = p[0];
-                        if (c + 1 < cols) W[(size_t)r * cols + c + 1] = p[1];
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            int d = p[q];
+                            if (c + q < cols && d < D_INF) {
+                                size_t i = (size_t)r * cols + c + q;
+                                W[i] = __dadd_rn((double)__ldg(zsrc + i), __dmul_rn((double)d, ulp));
+                            }
+                        }
                     }
                 }
             }
-#ifdef NF_STATS
-            tc2 = clock64();
-            if (tid == 0 && round < 4096) {
-                atomicMax(&g_nf_dbg[6 + 8 * round], (unsigned long long)(tc1 - tc0));
-                atomicMax(&g_nf_dbg[7 + 8 * round], (unsigned long long)(tc2 - tc1));
-                atomicMax(&g_nf_dbg[8 + 8 * round], (unsigned long long)nit);
-                atomicAdd(&g_nf_dbg[9 + 8 * round], (unsigned long long)(tc2 - tc1));
-                atomicAdd(&g_nf_dbg[10 + 8 * round], (unsigned long long)nit);
-            }
-#endif
-            if (S.chgmask == 0) continue;
-            __threadfence();
-            __syncthreads();
+            if (!solved) __syncthreads();          // everybody is done with the integer tile before it is overwritten
+        }
+        if (!solved) {
+            // ---- float64 form
             if (tid == 0) {
-                int ring = S.ring;
-                bool top = ring & 1, bot = ring & 2, lef = ring & 4, rig = ring & 8;
-                for (int dy = -1; dy <= 1; dy++)
-                    for (int dx = -1; dx <= 1; dx++) {
-                        if (!dy && !dx) continue;
-                        // a diagonal neighbour only sees our corner cell: it is covered by either adjoining side
-                        bool hit = (dy < 0 && top) || (dy > 0 && bot) || (dx < 0 && lef) || (dx > 0 && rig);
-                        if (!hit) continue;
-                        int y = ty + dy, x = tx + dx;
-                        if (y < 0 || y >= tiles_y || x < 0 || x >= tiles_x) continue;
-                        int nb = y * tiles_x + x;
-                        // which side of the neighbour looks at us
-                        int bits = (dy < 0 ? 2 : 0) | (dy > 0 ? 1 : 0) | (dx < 0 ? 8 : 0) | (dx > 0 ? 4 : 0);
-                        if (dy && dx) bits = dy < 0 ? 2 : 1;      // a corner: one block of that side is enough
-                        if (atomicOr(tileflag + nb, bits) == 0) listn[atomicAdd(&ctl->count[nxt], 1)] = nb;
-                    }
+                S.dirty[0] = nf_region(S.flags);
+                S.dirty[1] = 0;
+                S.dirty[2] = 0;
+                S.chgmask = 0;
+                S.ring = 0;
+            }
+            for (int q = tid; q < (NF_T + 2) * (NF_T + 2); q += 256) {
+                int lr = q / (NF_T + 2), lc = q - lr * (NF_T + 2);
+                int r = r0 + lr - 1, c = c0 + lc - 1;
+                double v = INFINITY;
+                if (r >= 0 && r < rows && c >= 0 && c < cols) v = __ldcg(W + (size_t)r * cols + c);
+                sw[lr * NF_LD + lc] = v;
+            }
+            for (int q = tid; q < NF_T * NF_T; q += 256) {
+                int lr = q >> 6, lc = q & 63;
+                int r = r0 + lr, c = c0 + lc;
+                sz[q] = (r < rows && c < cols) ? __ldg(zsrc + (size_t)r * cols + c) : INFINITY;
+            }
+            __syncthreads();
+#ifdef NF_STATS
+            tc1 = clock64();
+#endif
+            RelaxF64<CAP> rx{sw, sz, sh, dg, capB};
+            int its = nf_tile_iterate(rx, S);
+#ifdef NF_STATS
+            nit = its;
+#endif
+            (void)its;
+            // write back the blocks that changed: a warp writes 8 rows of 8 doubles (lane: row l/4, 2 columns)
+            unsigned long long mm = S.chgmask;
+            for (int idx = 0; mm; idx++) {
+                int b = __ffsll((long long)mm) - 1;
+                mm &= mm - 1;
+                if ((idx & 7) != warp) continue;
+                int lr = (b >> 3) * 8 + (lane >> 2), lc = (b & 7) * 8 + (lane & 3) * 2;
+                int r = r0 + lr, c = c0 + lc;
+                const double *p = sw + (lr + 1) * NF_LD + (lc + 1);
+                if (r < rows) {
+                    if (c < cols) W[(size_t)r * cols + c] = p[0];
+                    if (c + 1 < cols) W[(size_t)r * cols + c + 1] = p[1];
+                }
             }
         }
-        __threadfence();
-        grid.sync();
 #ifdef NF_STATS
-        if (blockIdx.x == 0 && tid == 0 && round < 4096) {
-            g_nf_dbg[4 + 8 * round] = n;
-            g_nf_dbg[5 + 8 * round] = gtimer() - t_round;
+        tc2 = clock64();
+        if (tid == 0) {
+            atomicAdd(&g_nf_dbg[1], (unsigned long long)(tc1 ? tc1 - tc0 : 0));
+            atomicAdd(&g_nf_dbg[2], (unsigned long long)(tc1 ? tc2 - tc1 : 0));
+            atomicAdd(&g_nf_dbg[3], (unsigned long long)nit);
+            atomicMax(&g_nf_dbg[4], (unsigned long long)(tc1 ? tc2 - tc1 : 0));
         }
 #endif
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            int ringbits = S.chgmask ? S.ring : 0;
+            bool top = ringbits & 1, bot = ringbits & 2, lef = ringbits & 4, rig = ringbits & 8;
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    if (!dy && !dx) continue;
+                    // a diagonal neighbour only sees our corner cell: it is covered by either adjoining side
+                    bool hit = (dy < 0 && top) || (dy > 0 && bot) || (dx < 0 && lef) || (dx > 0 && rig);
+                    if (!hit) continue;
+                    int y = ty + dy, x = tx + dx;
+                    if (y < 0 || y >= tiles_y || x < 0 || x >= tiles_x) continue;
+                    int nb = y * tiles_x + x;
+                    // which side of the neighbour looks at us
+                    int bits = (dy < 0 ? 2 : 0) | (dy > 0 ? 1 : 0) | (dx < 0 ? 8 : 0) | (dx > 0 ? 4 : 0);
+                    if (dy && dx) bits = dy < 0 ? 2 : 1;      // a corner: one block of that side is enough
+                    if (!(__ldg(tilesides + nb) & bits)) continue;      // nothing there that could change
+                    // an idle tile (no side bits yet, not running) is queued by whoever sets its first side bit
+                    if (atomicOr(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb);
+                }
+            // this tile: side bits that arrived while it ran mean it has to run again
+            if (atomicAnd(tileflag + t, ~NF_RUNNING) & NF_SIDES) nf_push(ring, cap, ctl, t);
+            __threadfence();
+            if (atomicSub(&ctl->pending, 1) == 1) atomicExch(&ctl->done, 1);
+        }
     }
 }
 
@@ -597,8 +635,9 @@ __global__ void __launch_bounds__(256) k_nf_verify(const float *__restrict__ z, 
 int g_nf_use_int = 1;      // MS_NF_INT=0 in the environment keeps every tile in the float64 form (debugging)
 
 template <bool CAP>
-static int nf_launch_solve(const float *zsrc, double *W, int *lists, int *tileflag, NfCtl *ctl, int rows, int cols,
-                           int tiles_x, int tiles_y, int ntiles, double sh, double dg, int max_rounds, int use_int,
+static int nf_launch_solve(const float *zsrc, double *W, int *ring, int cap, int *tileflag, const int *tilesides,
+                           NfCtl *ctl, int rows,
+                           int cols, int tiles_x, int tiles_y, int ntiles, double sh, double dg, int use_int,
                            int64_t units, cudaStream_t s) {
     static int grid_blocks = 0;
     if (!grid_blocks) {
@@ -610,9 +649,11 @@ static int nf_launch_solve(const float *zsrc, double *W, int *lists, int *tilefl
         if (per_sm < 1) { set_error("fill_terrain_no_flats: solver kernel does not fit on an SM"); return MS_ERR_CUDA; }
         grid_blocks = sms * per_sm;
     }
-    void *args[] = {(void *)&zsrc, (void *)&W, (void *)&lists, (void *)&tileflag, (void *)&ctl, (void *)&rows,
-                    (void *)&cols, (void *)&tiles_x, (void *)&tiles_y, (void *)&ntiles, (void *)&sh, (void *)&dg,
-                    (void *)&max_rounds, (void *)&use_int};
+    void *args[] = {(void *)&zsrc, (void *)&W, (void *)&ring, (void *)&cap, (void *)&tileflag, (void *)&tilesides,
+                    (void *)&ctl,
+                    (void *)&rows, (void *)&cols, (void *)&tiles_x, (void *)&tiles_y, (void *)&sh, (void *)&dg,
+                    (void *)&use_int};
+    // consumers wait on the FIFO, so every CTA must be resident: cooperative launch guarantees it (or fails)
     int g = grid_blocks < ntiles ? grid_blocks : ntiles;
     prof_units(units);
     if (g_prof) prof_begin(CAP ? "k_nf_solve<true>" : "k_nf_solve<false>", s);
@@ -649,39 +690,41 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
     }
     int tiles_x = (int)cdiv(cols, NF_T), tiles_y = (int)cdiv(rows, NF_T);
     int ntiles = tiles_x * tiles_y;
-    DevBuf<int> tileflag, lists;
+    int cap_ring = ntiles + 64;          // a tile is in the FIFO at most once
+    DevBuf<int> tileflag, tilesides, ring;
     DevBuf<uint8_t> banned;
     DevBuf<NfCtl> ctl;
     MS_TRY(tileflag.alloc((size_t)ntiles, s));
-    MS_TRY(lists.alloc((size_t)ntiles * 3, s));
+    MS_TRY(tilesides.alloc((size_t)ntiles, s));
+    MS_TRY(ring.alloc((size_t)cap_ring, s));
     MS_TRY(ctl.alloc(1, s));
     bool cap = sh > 0 && dg > 0;      // capped fast path first; a verification failure falls back to the generic one
     dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
-    // every round moves a wave at least one tile; waves can wind, so the bound is generous
-    int max_rounds = 64 * (tiles_x + tiles_y) + 1024;
-    int64_t rounds = 0, visits = 0, tries = 0;
+    int64_t visits = 0, tries = 0;
     for (;;) {
         tries++;
         MS_CUDA(cudaMemsetAsync(tileflag.p, 0, (size_t)ntiles * sizeof(int), s));
+        MS_CUDA(cudaMemsetAsync(tilesides.p, 0, (size_t)ntiles * sizeof(int), s));
+        MS_CUDA(cudaMemsetAsync(ring.p, 0xff, (size_t)cap_ring * sizeof(int), s));
         MS_CUDA(cudaMemsetAsync(ctl.p, 0, sizeof(NfCtl), s));
-        MS_LAUNCH(k_nf_init, g2, 256, 0, s, dtm, filled, out, banned.p, tileflag.p, ctl.p, (int)rows, (int)cols, tiles_x);
-        MS_LAUNCH(k_nf_compact, cdiv(ntiles, 256), 256, 0, s, tileflag.p, lists.p, ctl.p, ntiles);
+        MS_LAUNCH(k_nf_init, g2, 256, 0, s, dtm, filled, out, banned.p, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols,
+                  tiles_x);
+        MS_LAUNCH(k_nf_compact, cdiv(ntiles, 256), 256, 0, s, tileflag.p, ring.p, ctl.p, ntiles);
         if (cap) {
             MS_LAUNCH(k_nf_seedcand, g2, 256, 0, s, filled, out, ctl.p, (int)rows, (int)cols, sh, dg);
-            MS_TRY(nf_launch_solve<true>(filled, out, lists.p, tileflag.p, ctl.p, (int)rows, (int)cols, tiles_x, tiles_y,
-                                         ntiles, sh, dg, max_rounds, g_nf_use_int, n, s));
+            MS_TRY(nf_launch_solve<true>(filled, out, ring.p, cap_ring, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols, tiles_x,
+                                         tiles_y, ntiles, sh, dg, g_nf_use_int, n, s));
         } else {
-            MS_TRY(nf_launch_solve<false>(dtm, out, lists.p, tileflag.p, ctl.p, (int)rows, (int)cols, tiles_x, tiles_y,
-                                          ntiles, sh, dg, max_rounds, 0, n, s));
+            MS_TRY(nf_launch_solve<false>(dtm, out, ring.p, cap_ring, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols, tiles_x,
+                                          tiles_y, ntiles, sh, dg, 0, n, s));
         }
         MS_LAUNCH(k_nf_verify, g2, 256, 0, s, dtm, out, banned.p, ctl.p, (int)rows, (int)cols, sh, dg);
         MS_CUDA(cudaMemcpyAsync(h, ctl.p, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
         MS_TRY(ms::stream_sync(s));
-        rounds += h->rounds;
         visits += h->visits;
-        if (h->rounds >= max_rounds) {
-            set_error("fill_terrain_no_flats: relaxation did not converge in %d rounds", max_rounds);
+        if (h->done != 1 && h->tail != 0) {
+            set_error("fill_terrain_no_flats: tile solver stopped early (done=%d, pending=%d)", h->done, h->pending);
             return MS_ERR_NOCONV;
         }
         if (h->nviol == 0) break;
@@ -700,7 +743,7 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
             return MS_ERR_NOCONV;
         }
     }
-    if (stats) { stats[0] = rounds; stats[1] = visits; stats[2] = tries - 1; }
+    if (stats) { stats[0] = tries; stats[1] = visits; stats[2] = tries - 1; }
     return MS_OK;
 }
 
@@ -739,7 +782,7 @@ int ms_fill_terrain_no_flats(const float *dtm, double short_eps, double diag_eps
 #ifdef NF_STATS
 int ms_nf_debug(unsigned long long *out, int n, int reset) {
     if (out) cudaMemcpyFromSymbol(out, ms::g_nf_dbg, sizeof(unsigned long long) * n);
-    if (reset) { static unsigned long long z[4 + 8 * 4096]; cudaMemcpyToSymbol(ms::g_nf_dbg, z, sizeof(z)); }
+    if (reset) { static unsigned long long z[16]; cudaMemcpyToSymbol(ms::g_nf_dbg, z, sizeof(z)); }
     return 0;
 }
 #endif

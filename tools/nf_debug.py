@@ -15,21 +15,19 @@ fnf = torch.empty((S, S), dtype=torch.float64, device=dev)
 sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 assert L.ms_fill_terrain_dev(dem.data_ptr(), filled.data_ptr(), depths.data_ptr(), S, S, sp) == 0
 mv = np.float64(float(dem.abs().max())); sh = float((np.nextafter(mv, np.inf) - mv) * 1024); dg = sh * 2 ** 0.5
-out = (ctypes.c_ulonglong * (4 + 8 * 4096))()
+out = (ctypes.c_ulonglong * 16)()
 dbg = raw.ms_nf_debug
 dbg.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
-for rep in range(2):
+import time
+for rep in range(3):
     dbg(None, 0, 1)
     st = (ctypes.c_int64 * 8)()
-    assert L.ms_fill_terrain_no_flats_dev(dem.data_ptr(), filled.data_ptr(), sh, dg, fnf.data_ptr(), S, S, st, sp) == 0
-    torch.cuda.synchronize()
-    dbg(out, 4 + 8 * 4096, 0)
-rounds = st[0]
-print("rounds", rounds, "visits", st[1], "tile iterations", out[0], "block visits", out[1], "block iterations", out[2])
-tot = 0
-for r in range(rounds):
-    n, ns, mload, msolve, mit, ssolve, sit = [out[4 + 8 * r + k] for k in range(7)]
-    tot += ns
-    print("round %3d tiles %6d  %8.1f us | max load %6d cyc  max solve %7d cyc  max iters %3d | mean solve %7d cyc  mean iters %.1f"
-          % (r, n, ns / 1e3, mload, msolve, mit, ssolve // max(n, 1), sit / max(n, 1)))
-print("sum of rounds %.2f ms" % (tot / 1e6))
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    rc = L.ms_fill_terrain_no_flats_dev(dem.data_ptr(), filled.data_ptr(), sh, dg, fnf.data_ptr(), S, S, st, sp)
+    if rc != 0:
+        print("rc", rc, L.ms_last_error()); break
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    dbg(out, 16, 0)
+    v = max(st[1], 1)
+    print("wall %.2f ms  visits %d  mean load %d cyc  mean solve %d cyc  mean iters %.2f  max solve %d cyc" %
+          ((t1 - t0) * 1e3, st[1], out[1] // v, out[2] // v, out[3] / v, out[4]))
