@@ -135,6 +135,96 @@ int ms_keep_labels(const int32_t *labels, int64_t n, const uint8_t *keep, int64_
 int ms_keep_labels_dev(const int32_t *labels, int64_t n, const uint8_t *keep, int64_t nkeep, uint8_t *out,
                        void *stream);
 
+
+/* ---- row bands: one raster split by rows across GPUs --------------------------------
+ * The reference has no distributed path; these entry points are the per-band halves of the stage
+ * functions above, with the exchange steps left to the caller (malstroem_b200/bands.py drives them over
+ * torch.distributed / NCCL).  Conventions: every raster pointer points at the band's FIRST OWN row; if the band is
+ * open at the top (MS_OPEN_TOP: another band continues above) the row before it in memory is a halo row holding the
+ * neighbour's last own row, likewise MS_OPEN_BOTTOM and the row after the last own row.  A band that is open at
+ * the bottom must have a multiple of 64 rows.  rows * cols <= 2^29 per band.  All pointers are device pointers
+ * unless stated; functions returning a count synchronise the stream. */
+#define MS_OPEN_TOP 1
+#define MS_OPEN_BOTTOM 2
+typedef struct ms_band ms_band;
+int ms_band_create(int64_t rows, int64_t cols, int open, ms_band **out);
+int ms_band_destroy(ms_band *band);
+
+/* fill.fill_terrain (fill.py:112-171) on a band.  local: Boruvka contraction inside the band; components whose
+ * lowest way out crosses a band edge stay "frozen" (*n_frozen of them).  edge_ids: global ids (gid_base + rank + 1;
+ * 0 = outside) of the components of the first / last own row, to be exchanged as halo ids.  edges: the boundary
+ * graph of this band (frozen components x their neighbours, lowest cell-pair edge each), at most `capacity`.
+ * ms_graph_minimax_dev: minimax height to node 0 over the union of all bands' edges (every rank solves the same
+ * small graph).  finish: filled (and depths = filled - dem, may be NULL) for the band. */
+int ms_band_fill_local_dev(ms_band *band, const float *dem, int64_t *n_frozen, void *stream);
+int ms_band_fill_edge_ids_dev(ms_band *band, int64_t gid_base, int32_t *gid_top, int32_t *gid_bot, void *stream);
+int ms_band_fill_edges_dev(ms_band *band, const float *dem, const int32_t *halo_gid_top, const int32_t *halo_gid_bot,
+                           int32_t *edge_a, int32_t *edge_b, float *edge_w, int64_t capacity, int64_t *n_edges,
+                           void *stream);
+int ms_graph_minimax_dev(int64_t n_nodes, const int32_t *edge_a, const int32_t *edge_b, const float *edge_w,
+                         int64_t n_edges, float *out_x, void *stream);
+int ms_band_fill_finish_dev(ms_band *band, const float *dem, const float *graph_x, float *filled, float *depths,
+                            void *stream);
+
+/* fill.fill_terrain_no_flats (fill.py:174-232) on a band: init (needs the halo rows of `filled`; returns the
+ * band's count of lake / flat cells), solve (mode 0: first solve, after the halo rows of fnf were exchanged; mode 1:
+ * again after the halo rows named by `edges` changed), verify (the fixed-point stencil incl. halo rows). */
+int ms_band_nf_init_dev(ms_band *band, const float *dem, const float *filled, double *fnf, int64_t *nonseed,
+                        void *stream);
+int ms_band_nf_solve_dev(ms_band *band, const float *dem, const float *filled, double *fnf, double short_eps,
+                         double diag_eps, double cap_bound, int cap, int mode, int edges, int64_t *tile_visits,
+                         void *stream);
+int ms_band_nf_verify_dev(ms_band *band, const float *dem, const double *fnf, double short_eps, double diag_eps,
+                          int64_t *nviol, void *stream);
+
+/* flow.terrain_flowdirection (flow.py:142-167) on a band (needs the halo rows of the terrain) */
+int ms_band_flowdir_dev(ms_band *band, const double *terrain, uint8_t *flowdir, int edges_flow_outward, void *stream);
+
+/* flow.accumulated_flow (flow.py:344-364) on a band (needs the halo rows of flowdir).  local: arrays of 2 * cols
+ * entries (first the top row's cells, then the bottom row's): exit_to = column at which the path leaving the band
+ * at this cell enters the neighbour (-1: not an exit), exit_val = the count it carries from inside the band,
+ * entry_root = side * cols + col of the band exit this cell's own path ends at (-1: it ends inside the band).
+ * ms_forest_accumulate_dev: totals over the forest of all bands' exits.  finish: halo_total_top / _bot[c] = total
+ * of the neighbour's edge-row cell in column c (used where that cell flows into this band). */
+int ms_band_accum_local_dev(ms_band *band, const uint8_t *flowdir, int32_t *exit_to, double *exit_val,
+                            int32_t *entry_root, void *stream);
+int ms_forest_accumulate_dev(int64_t n, const int32_t *parent, double *totals, void *stream);
+int ms_band_accum_finish_dev(ms_band *band, const uint8_t *flowdir, const double *halo_total_top,
+                             const double *halo_total_bot, double *accum, void *stream);
+
+/* label.connected_components (label.py:19-40) on a band.  local: roots (global cell index = cell_offset + local
+ * index, -1 = background) of the first / last own row.  ms_cc_boundary_merge (HOST pointers, CPU): merges the
+ * components that touch across band edges; out_root ascending, out_global = smallest root of the merged component.
+ * count: `rerooted` = local indices of this band's roots that are not their component's smallest; returns how many
+ * components the band numbers.  root_labels: final labels of roots this band owns.  finish: writes the labels. */
+int ms_band_cc_local_dev(ms_band *band, const void *data, int dtype, int64_t cell_offset, int64_t *root_top,
+                         int64_t *root_bot, void *stream);
+int ms_cc_boundary_merge(int nbands, int64_t cols, const int64_t *root_top, const int64_t *root_bot,
+                         int64_t *out_root, int64_t *out_global, int64_t capacity, int64_t *n_out);
+int ms_band_cc_count_dev(ms_band *band, const int32_t *rerooted, int64_t n_rerooted, int64_t *count, void *stream);
+int ms_band_cc_root_labels_dev(ms_band *band, const int32_t *roots, int64_t n_roots, int64_t label_offset,
+                               int32_t *labels_out, void *stream);
+int ms_band_cc_finish_dev(ms_band *band, const int32_t *rerooted, const int32_t *rerooted_label, int64_t n_rerooted,
+                          int64_t label_offset, int32_t *labels, void *stream);
+
+/* flow.watersheds_from_labels (flow.py:398-412) on a band, int32 labels.  local: edge_res[2 * cols] = what each cell
+ * of the first / last own row resolves to: >= 0 a label (0: none), < 0: -(1 + side * cols + col) of the band exit it
+ * waits for; exit_to as above.  ms_chain_resolve_dev follows such references to their final value.  finish:
+ * exit_label[side * cols + col] = label for cells draining through that exit. */
+int ms_band_ws_local_dev(ms_band *band, const uint8_t *flowdir, const int32_t *labelled, int32_t unassigned,
+                         int32_t *edge_res, int32_t *exit_to, void *stream);
+int ms_chain_resolve_dev(int64_t n, const int32_t *arr, int32_t *out, void *stream);
+int ms_band_ws_finish_dev(ms_band *band, const uint8_t *flowdir, int32_t *labelled, int32_t unassigned,
+                          const int32_t *exit_label, void *stream);
+
+/* label.label_min_index / label_max_index (label.py:101-166) in two phases whose tables combine across bands with
+ * min / max all-reduces: the extreme value per label, then the smallest global flat index holding it
+ * (INT64_MAX: label not seen). */
+int ms_band_extreme_value_dev(const double *data, const int32_t *labels, int64_t n, int64_t nlabels, int want_max,
+                              double *out_value, void *stream);
+int ms_band_extreme_index_dev(const double *data, const int32_t *labels, int64_t n, int64_t nlabels,
+                              const double *value, int64_t cell_offset, int64_t *out_index, void *stream);
+
 /* ---- the whole path, device resident (what bench.py times) -------------------------------------- */
 typedef struct ms_rasters {
     int64_t rows, cols;

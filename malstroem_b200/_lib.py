@@ -60,6 +60,30 @@ SIGNATURES = {
     "ms_label_count_dev": (c_int, [c_p, c_i64, c_i64, c_p, c_p]),
     "ms_keep_labels": (c_int, [c_p, c_i64, c_p, c_i64, c_p]),
     "ms_keep_labels_dev": (c_int, [c_p, c_i64, c_p, c_i64, c_p, c_p]),
+    "ms_band_create": (c_int, [c_i64, c_i64, c_int, c_p]),
+    "ms_band_destroy": (c_int, [c_p]),
+    "ms_band_fill_local_dev": (c_int, [c_p, c_p, c_p, c_p]),
+    "ms_band_fill_edge_ids_dev": (c_int, [c_p, c_i64, c_p, c_p, c_p]),
+    "ms_band_fill_edges_dev": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p]),
+    "ms_graph_minimax_dev": (c_int, [c_i64, c_p, c_p, c_p, c_i64, c_p, c_p]),
+    "ms_band_fill_finish_dev": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p]),
+    "ms_band_nf_init_dev": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p]),
+    "ms_band_nf_solve_dev": (c_int, [c_p, c_p, c_p, c_p, c_dbl, c_dbl, c_dbl, c_int, c_int, c_int, c_p, c_p]),
+    "ms_band_nf_verify_dev": (c_int, [c_p, c_p, c_p, c_dbl, c_dbl, c_p, c_p]),
+    "ms_band_flowdir_dev": (c_int, [c_p, c_p, c_p, c_int, c_p]),
+    "ms_band_accum_local_dev": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p]),
+    "ms_forest_accumulate_dev": (c_int, [c_i64, c_p, c_p, c_p]),
+    "ms_band_accum_finish_dev": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p]),
+    "ms_band_cc_local_dev": (c_int, [c_p, c_p, c_int, c_i64, c_p, c_p, c_p]),
+    "ms_cc_boundary_merge": (c_int, [c_int, c_i64, c_p, c_p, c_p, c_p, c_i64, c_p]),
+    "ms_band_cc_count_dev": (c_int, [c_p, c_p, c_i64, c_p, c_p]),
+    "ms_band_cc_root_labels_dev": (c_int, [c_p, c_p, c_i64, c_i64, c_p, c_p]),
+    "ms_band_cc_finish_dev": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p]),
+    "ms_band_ws_local_dev": (c_int, [c_p, c_p, c_p, ctypes.c_int32, c_p, c_p, c_p]),
+    "ms_chain_resolve_dev": (c_int, [c_i64, c_p, c_p, c_p]),
+    "ms_band_ws_finish_dev": (c_int, [c_p, c_p, c_p, ctypes.c_int32, c_p, c_p]),
+    "ms_band_extreme_value_dev": (c_int, [c_p, c_p, c_i64, c_i64, c_int, c_p, c_p]),
+    "ms_band_extreme_index_dev": (c_int, [c_p, c_p, c_i64, c_i64, c_p, c_i64, c_p, c_p]),
     "ms_pipeline_dev": (c_int, [c_p, c_p]),
     "ms_synth_fractal_dev": (c_int, [c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_p]),
 }

@@ -1,0 +1,492 @@
+"""Row-band driver: ONE raster split by rows across GPUs, one band per rank.
+
+Every stage of the hot path runs as "band-local kernel phase -> small exchange -> band-local kernel phase":
+
+    stage                     exchanged between the phases
+    K0 min/max                2 floats (all-reduce)
+    K1 fill                   halo row of the DEM; counts + ids of the components that wait for a neighbour; the
+                              boundary graph (lowest edge between such components), solved redundantly on every rank
+    K2 no-flats fill          halo rows of the plain fill and of the surface, repeated until no band changes
+    K3 D8                     halo rows of the surface (already there)
+    K4 accumulation           per edge cell: where it leaves / which exit it ends at / the count it carries;
+                              totals over the forest of all band exits
+    K5/6 bluespot labels      roots of the edge rows; merged on the host (CPU, O(cols)); per-band counts
+    K7 watersheds             per edge cell what it resolves to; chains followed across bands
+    K8-K10 tables             all-reduces of the per-label tables (min / max / sum)
+
+The kernels are the library's (`ms_band_*` of include/malstroem_b200.h); torch is used for device memory, the
+stream, index arithmetic on the O(cols) boundary arrays and torch.distributed (NCCL on GPUs; gloo in the CPU tests
+of the exchange layer).  `ThreadComm` runs G bands as G threads of one process on one GPU — the same code path, used
+by the single-GPU tests of the decomposition.  Results are bit-identical to the single-GPU path.
+"""
+import ctypes
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+
+OPEN_TOP, OPEN_BOTTOM = 1, 2
+BAND_ALIGN = 64
+
+
+def band_rows(rows, size):
+    """Row ranges [(r0, r1)] of the bands: boundaries on multiples of 64 rows, every band non-empty."""
+    per = -(-rows // size)
+    per = -(-per // BAND_ALIGN) * BAND_ALIGN
+    out = []
+    for g in range(size):
+        r0, r1 = g * per, min(rows, (g + 1) * per)
+        if r1 - r0 < 2:
+            raise ValueError("raster of %d rows is too small for %d bands of a multiple of %d rows"
+                             % (rows, size, BAND_ALIGN))
+        out.append((r0, r1))
+    return out
+
+
+# ------------------------------------------------------------------------------------------- communicators
+class ThreadGroup(object):
+    """Shared state of `size` ThreadComm ranks living in one process."""
+
+    def __init__(self, size):
+        self.size = size
+        self.barrier = threading.Barrier(size)
+        self.slots = [None] * size
+
+
+class ThreadComm(object):
+    def __init__(self, group, rank):
+        self.g, self.rank, self.size = group, rank, group.size
+
+    def _swap(self, item):
+        self.g.slots[self.rank] = item
+        self.g.barrier.wait()
+        got = list(self.g.slots)
+        self.g.barrier.wait()
+        return got
+
+    def all_gather(self, t):
+        return torch.stack([x.clone() for x in self._swap(t)])
+
+    def all_gather_var(self, t):
+        return [x.clone() for x in self._swap(t)]
+
+    def all_reduce(self, t, op):
+        got = torch.stack(self._swap(t.clone()))
+        r = {"sum": got.sum(0), "min": got.min(0).values, "max": got.max(0).values}[op]
+        t.copy_(r.to(t.dtype))
+        return t
+
+    def exchange(self, up, down):
+        got = self._swap((up, down))
+        a = got[self.rank - 1][1].clone() if self.rank > 0 else None
+        b = got[self.rank + 1][0].clone() if self.rank + 1 < self.size else None
+        return a, b
+
+
+class DistComm(object):
+    """torch.distributed (NCCL on GPUs, gloo on CPU tensors)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.size = dist.get_rank(group), dist.get_world_size(group)
+
+    def all_gather(self, t):
+        t = t.contiguous()
+        out = torch.empty((self.size,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t, group=self.group)
+        return out
+
+    def all_gather_var(self, t):
+        n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+        ns = self.all_gather(n).view(-1).tolist()
+        m = max(max(ns), 1)
+        pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        pad[: t.shape[0]] = t
+        got = self.all_gather(pad)
+        return [got[i, : ns[i]] for i in range(self.size)]
+
+    def all_reduce(self, t, op):
+        d = self.dist
+        self.dist.all_reduce(t, op={"sum": d.ReduceOp.SUM, "min": d.ReduceOp.MIN, "max": d.ReduceOp.MAX}[op],
+                             group=self.group)
+        return t
+
+    def exchange(self, up, down):
+        d, ops = self.dist, []
+        a = torch.empty_like(up) if self.rank > 0 else None
+        b = torch.empty_like(down) if self.rank + 1 < self.size else None
+        if self.rank > 0:
+            ops += [d.P2POp(d.isend, up.contiguous(), self.rank - 1, self.group),
+                    d.P2POp(d.irecv, a, self.rank - 1, self.group)]
+        if self.rank + 1 < self.size:
+            ops += [d.P2POp(d.isend, down.contiguous(), self.rank + 1, self.group),
+                    d.P2POp(d.irecv, b, self.rank + 1, self.group)]
+        if ops:
+            for w in d.batch_isend_irecv(ops):
+                w.wait()
+        return a, b
+
+
+# -------------------------------------------------------------------------------------- boundary arithmetic
+# (device-agnostic torch code on O(cols) arrays; unit-tested on CPU in tests/test_bands_cpu.py)
+def accum_forest(exit_to, entry_root, cols):
+    """Parent index of every node (band g, side s, column c) -> node id (g*2+s)*cols+c in the forest of band exits.
+    exit_to, entry_root: int tensors [G, 2*cols] as produced by ms_band_accum_local_dev."""
+    G = exit_to.shape[0]
+    dev = exit_to.device
+    e = exit_to.view(G, 2, cols).long()
+    root = entry_root.view(G, 2, cols).long()
+    g = torch.arange(G, device=dev).view(G, 1, 1).expand(G, 2, cols)
+    s = torch.arange(2, device=dev).view(1, 2, 1).expand(G, 2, cols)
+    gn = torch.where(s == 0, g - 1, g + 1)                 # the band the exit leads into
+    valid = (e >= 0) & (gn >= 0) & (gn < G)
+    gn_c, to_c = gn.clamp(0, G - 1), e.clamp(0, cols - 1)
+    r = root[gn_c, 1 - s, to_c]                            # exit (side*cols+col) of band gn the entry's path ends at
+    parent = torch.where(valid & (r >= 0), gn_c * 2 * cols + r, torch.full_like(r, -1))
+    return parent.reshape(-1).to(torch.int32)
+
+
+def watershed_chain(edge_res, exit_to, cols):
+    """Reference array for ms_chain_resolve_dev over nodes (g, s, c): >= 0 final label, < 0 -> -(1 + node)."""
+    G = edge_res.shape[0]
+    dev = edge_res.device
+    res = edge_res.view(G, 2, cols).long()
+    e = exit_to.view(G, 2, cols).long()
+    g = torch.arange(G, device=dev).view(G, 1, 1).expand(G, 2, cols)
+    k = (-(res + 1)).clamp(min=0)                          # side'*cols + col' of the band's own exit
+    s2, c2 = k // cols, k % cols
+    to = e[g, s2, c2]
+    gn = torch.where(s2 == 0, g - 1, g + 1)
+    ok = (res < 0) & (to >= 0) & (gn >= 0) & (gn < G)
+    node = (gn.clamp(0, G - 1) * 2 + (1 - s2)) * cols + to.clamp(0, cols - 1)
+    arr = torch.where(res >= 0, res, torch.where(ok, -(1 + node), torch.zeros_like(res)))
+    return arr.reshape(-1).to(torch.int32)
+
+
+def exit_targets(exit_to, cols, g):
+    """For band g: node ids (in the (G,2,cols) numbering) its exits lead into, and a mask of real exits."""
+    G = exit_to.shape[0]
+    e = exit_to.view(G, 2, cols)[g].long()
+    s = torch.arange(2, device=e.device).view(2, 1).expand(2, cols)
+    gn = torch.where(s == 0, torch.full_like(s, g - 1), torch.full_like(s, g + 1))
+    ok = (e >= 0) & (gn >= 0) & (gn < G)
+    node = (gn.clamp(0, G - 1) * 2 + (1 - s)) * cols + e.clamp(0, cols - 1)
+    return node.reshape(-1), ok.reshape(-1)
+
+
+def cc_plan(roots, globals_, cell_lo, cell_hi):
+    """From the merged boundary roots (numpy int64, ascending `roots`, their component's smallest root `globals_`):
+    the band's re-rooted local roots, the component roots it owns, and the sorted list of all component roots."""
+    comp_roots = np.unique(globals_)
+    mine = (roots >= cell_lo) & (roots < cell_hi)
+    rer = mine & (globals_ != roots)
+    own = (comp_roots >= cell_lo) & (comp_roots < cell_hi)
+    return {"rerooted_local": (roots[rer] - cell_lo).astype(np.int32),
+            "rerooted_global": globals_[rer],
+            "comp_roots": comp_roots,
+            "owned_pos": np.nonzero(own)[0],
+            "owned_local": (comp_roots[own] - cell_lo).astype(np.int32)}
+
+
+# ------------------------------------------------------------------------------------------------ pipeline
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class BandPipeline(object):
+    """Buffers of one band of a `rows x cols` raster and the staged run over `comm`."""
+
+    RASTERS = (("filled", torch.float32, True), ("depths", torch.float32, False), ("fnf", torch.float64, True),
+               ("flowdir", torch.uint8, True), ("accum", torch.float64, False), ("labels", torch.int32, False),
+               ("wsheds", torch.int32, False))
+
+    def __init__(self, rows, cols, comm, device=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("malstroem_b200.bands needs a CUDA device (there is no CPU fallback)")
+        self.R, self.cols, self.comm = int(rows), int(cols), comm
+        self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
+        self.r0, self.r1 = band_rows(self.R, comm.size)[comm.rank]
+        self.rows = self.r1 - self.r0
+        self.open = (OPEN_TOP if comm.rank > 0 else 0) | (OPEN_BOTTOM if comm.rank + 1 < comm.size else 0)
+        self.cell_offset = self.r0 * self.cols
+        L = _lib.lib()
+        with _lib.lock:
+            _lib.check(L.ms_init(self.device.index or 0), "ms_init")
+            h = ctypes.c_void_p()
+            _lib.check(L.ms_band_create(self.rows, self.cols, self.open, ctypes.byref(h)), "ms_band_create")
+        self.h = h
+        dev = self.device
+        self.dem_ext = torch.zeros((self.rows + 2, self.cols), dtype=torch.float32, device=dev)
+        self.ext, self.out = {}, {}
+        for name, dt, halo in self.RASTERS:
+            if halo:
+                self.ext[name] = torch.zeros((self.rows + 2, self.cols), dtype=dt, device=dev)
+                self.out[name] = self.ext[name][1:1 + self.rows]
+            else:
+                self.out[name] = torch.empty((self.rows, self.cols), dtype=dt, device=dev)
+        self.dem = self.dem_ext[1:1 + self.rows]
+        self.tables, self.nlabels, self.stats = {}, 0, {}
+
+    def close(self):
+        if self.h is not None:
+            with _lib.lock:
+                _lib.lib().ms_band_destroy(self.h)
+            self.h = None
+
+    # ---- helpers
+    def _call(self, name, *args):
+        with _lib.lock:
+            _lib.check(getattr(_lib.lib(), name)(*args), name)
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _halo(self, ext):
+        """Send the first / last own row to the neighbours, receive their rows into the halo rows."""
+        a, b = self.comm.exchange(ext[1], ext[self.rows])
+        if a is not None:
+            ext[0].copy_(a)
+        if b is not None:
+            ext[self.rows + 1].copy_(b)
+
+    # ---- the staged run (order and operands: DemTool.process dem.py:53-93, BluespotTool.process bluespots.py:138-216)
+    def run(self):
+        L, comm, dev, cols, rows, n = _lib.lib(), self.comm, self.device, self.cols, self.rows, self.rows * self.cols
+        st = self._stream()
+        i64 = ctypes.c_int64
+        # K1 fill (+ depths)
+        self._halo(self.dem_ext)
+        nF = i64(0)
+        self._call("ms_band_fill_local_dev", self.h, _p(self.dem), ctypes.byref(nF), st)
+        counts = comm.all_gather(torch.tensor([nF.value], dtype=torch.int64, device=dev)).view(-1)
+        total_f = int(counts.sum())
+        graph_x = None
+        if total_f:
+            base = int(counts[: comm.rank].sum())
+            gids = torch.zeros((2, cols), dtype=torch.int32, device=dev)
+            self._call("ms_band_fill_edge_ids_dev", self.h, base, _p(gids[0]), _p(gids[1]), st)
+            h_top, h_bot = comm.exchange(gids[0], gids[1])
+            cap = 16 * (nF.value + cols) + 1024
+            ea = torch.empty(cap, dtype=torch.int32, device=dev)
+            eb = torch.empty(cap, dtype=torch.int32, device=dev)
+            ew = torch.empty(cap, dtype=torch.float32, device=dev)
+            ne = i64(0)
+            self._call("ms_band_fill_edges_dev", self.h, _p(self.dem), _p(h_top), _p(h_bot), _p(ea), _p(eb), _p(ew), cap,
+                       ctypes.byref(ne), st)
+            k = ne.value
+            ea = torch.cat(comm.all_gather_var(ea[:k])).contiguous()
+            eb = torch.cat(comm.all_gather_var(eb[:k])).contiguous()
+            ew = torch.cat(comm.all_gather_var(ew[:k])).contiguous()
+            graph_x = torch.empty(total_f + 1, dtype=torch.float32, device=dev)
+            self._call("ms_graph_minimax_dev", total_f + 1, _p(ea), _p(eb), _p(ew), ea.numel(), _p(graph_x), st)
+            self.stats["fill_graph_edges"] = int(ea.numel())
+        self.stats["fill_frozen"] = total_f
+        self._call("ms_band_fill_finish_dev", self.h, _p(self.dem), _p(graph_x), _p(self.out["filled"]),
+                   _p(self.out["depths"]), st)
+        self._halo(self.ext["filled"])
+        # short / diag (fill.py:235-250)
+        mm = torch.empty(2, dtype=torch.float32, device=dev)
+        self._call("ms_minmax_f32_dev", _p(self.dem), n, _p(mm), st)
+        lo, hi = mm[:1].clone(), mm[1:].clone()
+        comm.all_reduce(lo, "min")
+        comm.all_reduce(hi, "max")
+        maxval = np.float64(max(abs(np.float32(hi.item())), abs(np.float32(lo.item()))))
+        self.short = float((np.nextafter(maxval, np.inf) - maxval) * 1024.0)
+        self.diag = float(self.short * 2 ** 0.5)
+        # K2 no-flats fill
+        self._noflats(st)
+        # K3 D8
+        self._call("ms_band_flowdir_dev", self.h, _p(self.out["fnf"]), _p(self.out["flowdir"]), 1, st)
+        self._halo(self.ext["flowdir"])
+        # K4 accumulation
+        self._accum(st)
+        # K5/K6 bluespot labels, K8 stats
+        self._labels(st)
+        self._stats(st)
+        # K7 watersheds, K10 counts
+        self._watersheds(st)
+        # K8'/K8'' pour points
+        self._pour_points(st)
+        return self
+
+    def _noflats(self, st):
+        comm, dev, cols = self.comm, self.device, self.cols
+        fnf = self.ext["fnf"]
+        i64 = ctypes.c_int64
+        for cap in (1, 0):
+            ns = i64(0)
+            self._call("ms_band_nf_init_dev", self.h, _p(self.dem), _p(self.out["filled"]), _p(self.out["fnf"]),
+                       ctypes.byref(ns), st)
+            tot = comm.all_reduce(torch.tensor([ns.value], dtype=torch.float64, device=dev), "sum")
+            cap_bound = (float(tot.item()) + 16.0) * self.diag * 1.001
+            self._halo(fnf)
+            visits = i64(0)
+            self._call("ms_band_nf_solve_dev", self.h, _p(self.dem), _p(self.out["filled"]), _p(self.out["fnf"]),
+                       self.short, self.diag, cap_bound, cap, 0, 0, ctypes.byref(visits), st)
+            total_visits, sweeps = visits.value, 0
+            for sweeps in range(1, 100000):
+                old_top, old_bot = fnf[0].clone(), fnf[self.rows + 1].clone()
+                self._halo(fnf)
+                ch = 0
+                if self.open & OPEN_TOP and not torch.equal(old_top, fnf[0]):
+                    ch |= 1
+                if self.open & OPEN_BOTTOM and not torch.equal(old_bot, fnf[self.rows + 1]):
+                    ch |= 2
+                anyc = comm.all_reduce(torch.tensor([ch], dtype=torch.int32, device=dev), "max")
+                if int(anyc.item()) == 0:
+                    break
+                if ch:
+                    self._call("ms_band_nf_solve_dev", self.h, _p(self.dem), _p(self.out["filled"]), _p(self.out["fnf"]),
+                               self.short, self.diag, cap_bound, cap, 1, ch, ctypes.byref(visits), st)
+                    total_visits += visits.value
+            nv = i64(0)
+            self._call("ms_band_nf_verify_dev", self.h, _p(self.dem), _p(self.out["fnf"]), self.short, self.diag,
+                       ctypes.byref(nv), st)
+            bad = comm.all_reduce(torch.tensor([nv.value], dtype=torch.int64, device=dev), "sum")
+            self.stats.update(noflat_exchanges=sweeps, noflat_tile_visits=total_visits, noflat_capped=cap)
+            if int(bad.item()) == 0:
+                return
+        raise RuntimeError("band no-flats fill: the fixed-point verification failed (seed repair is not available in "
+                           "band mode)")
+
+    def _accum(self, st):
+        comm, dev, cols = self.comm, self.device, self.cols
+        G, g = comm.size, comm.rank
+        exit_to = torch.empty(2 * cols, dtype=torch.int32, device=dev)
+        exit_val = torch.empty(2 * cols, dtype=torch.float64, device=dev)
+        entry_root = torch.empty(2 * cols, dtype=torch.int32, device=dev)
+        self._call("ms_band_accum_local_dev", self.h, _p(self.out["flowdir"]), _p(exit_to), _p(exit_val),
+                   _p(entry_root), st)
+        all_to, all_val, all_root = comm.all_gather(exit_to), comm.all_gather(exit_val), comm.all_gather(entry_root)
+        parent = accum_forest(all_to, all_root, cols).contiguous()
+        totals = all_val.reshape(-1).clone()
+        self._call("ms_forest_accumulate_dev", totals.numel(), _p(parent), _p(totals), st)
+        totals = totals.view(G, 2, cols)
+        top = totals[g - 1, 1].contiguous() if g > 0 else None
+        bot = totals[g + 1, 0].contiguous() if g + 1 < G else None
+        self._call("ms_band_accum_finish_dev", self.h, _p(self.out["flowdir"]), _p(top), _p(bot), _p(self.out["accum"]),
+                   st)
+
+    def _labels(self, st):
+        comm, dev, cols = self.comm, self.device, self.cols
+        G = comm.size
+        L = _lib.lib()
+        roots_tb = torch.empty((2, cols), dtype=torch.int64, device=dev)
+        self._call("ms_band_cc_local_dev", self.h, _p(self.out["depths"]), _lib.MS_F32, self.cell_offset,
+                   _p(roots_tb[0]), _p(roots_tb[1]), st)
+        allr = comm.all_gather(roots_tb).cpu().numpy()              # [G, 2, cols]
+        top = np.ascontiguousarray(allr[:, 0, :])
+        bot = np.ascontiguousarray(allr[:, 1, :])
+        capn = 2 * G * cols
+        out_root = np.empty(capn, dtype=np.int64)
+        out_glob = np.empty(capn, dtype=np.int64)
+        k = ctypes.c_int64(0)
+        with _lib.lock:
+            _lib.check(L.ms_cc_boundary_merge(G, cols, _lib.ptr(top), _lib.ptr(bot), _lib.ptr(out_root),
+                                              _lib.ptr(out_glob), capn, ctypes.byref(k)), "ms_cc_boundary_merge")
+        plan = cc_plan(out_root[: k.value], out_glob[: k.value], self.cell_offset, self.cell_offset + self.rows * cols)
+        rer = torch.from_numpy(plan["rerooted_local"]).to(dev)
+        cnt = ctypes.c_int64(0)
+        self._call("ms_band_cc_count_dev", self.h, _p(rer) if rer.numel() else None, rer.numel(), ctypes.byref(cnt), st)
+        counts = comm.all_gather(torch.tensor([cnt.value], dtype=torch.int64, device=dev)).view(-1)
+        label_offset = int(counts[: comm.rank].sum())
+        self.nlabels = int(counts.sum())
+        # labels of the component roots that touch a band edge, published by their owners
+        ncomp = len(plan["comp_roots"])
+        lab_of = torch.zeros(max(ncomp, 1), dtype=torch.int64, device=dev)
+        if len(plan["owned_local"]):
+            idx = torch.from_numpy(plan["owned_local"]).to(dev)
+            lab = torch.empty(idx.numel(), dtype=torch.int32, device=dev)
+            self._call("ms_band_cc_root_labels_dev", self.h, _p(idx), idx.numel(), label_offset, _p(lab), st)
+            lab_of[torch.from_numpy(plan["owned_pos"]).to(dev)] = lab.long()
+        comm.all_reduce(lab_of, "sum")
+        rer_lab = None
+        if rer.numel():
+            pos = np.searchsorted(plan["comp_roots"], plan["rerooted_global"])
+            rer_lab = lab_of[torch.from_numpy(pos).to(dev)].to(torch.int32).contiguous()
+        self._call("ms_band_cc_finish_dev", self.h, _p(rer) if rer.numel() else None, _p(rer_lab), rer.numel(),
+                   label_offset, _p(self.out["labels"]), st)
+        self.stats["cc_boundary_roots"] = int(k.value)
+
+    def _table(self, name, dtype):
+        t = torch.empty(self.nlabels + 1, dtype=dtype, device=self.device)
+        self.tables[name] = t
+        return t
+
+    def _stats(self, st):
+        comm, n = self.comm, self.rows * self.cols
+        tmin, tmax, tsum = (self._table(k, torch.float64) for k in ("st_min", "st_max", "st_sum"))
+        tcnt = self._table("st_count", torch.int64)
+        self._call("ms_label_stats_dev", _p(self.out["depths"]), _lib.MS_F32, _p(self.out["labels"]), n, self.nlabels,
+                   _p(tmin), _p(tmax), _p(tsum), _p(tcnt), st)
+        comm.all_reduce(tmin, "min")
+        comm.all_reduce(tmax, "max")
+        comm.all_reduce(tsum, "sum")
+        comm.all_reduce(tcnt, "sum")
+
+    def _watersheds(self, st):
+        comm, dev, cols = self.comm, self.device, self.cols
+        G, g = comm.size, comm.rank
+        ws = self.out["wsheds"]
+        ws.copy_(self.out["labels"])
+        edge_res = torch.empty(2 * cols, dtype=torch.int32, device=dev)
+        exit_to = torch.empty(2 * cols, dtype=torch.int32, device=dev)
+        self._call("ms_band_ws_local_dev", self.h, _p(self.out["flowdir"]), _p(ws), 0, _p(edge_res), _p(exit_to), st)
+        all_res, all_to = comm.all_gather(edge_res), comm.all_gather(exit_to)
+        arr = watershed_chain(all_res, all_to, cols).contiguous()
+        final = torch.empty_like(arr)
+        self._call("ms_chain_resolve_dev", arr.numel(), _p(arr), _p(final), st)
+        node, ok = exit_targets(all_to, cols, g)
+        exit_label = torch.where(ok, final[node.clamp(0, arr.numel() - 1)], torch.zeros_like(final[:1])).to(torch.int32)
+        self._call("ms_band_ws_finish_dev", self.h, _p(self.out["flowdir"]), _p(ws), 0, _p(exit_label.contiguous()), st)
+        cnt = self._table("ws_count", torch.int64)
+        self._call("ms_label_count_dev", _p(ws), self.rows * cols, self.nlabels + 1, _p(cnt), st)
+        comm.all_reduce(cnt, "sum")
+
+    def _pour_points(self, st):
+        comm, n, cols = self.comm, self.rows * self.cols, self.cols
+        for key, data, want_max in (("ppmin", self.out["fnf"], 0), ("ppmax", self.out["accum"], 1)):
+            val = self._table(key + "_value", torch.float64)
+            self._call("ms_band_extreme_value_dev", _p(data), _p(self.out["labels"]), n, self.nlabels, want_max, _p(val),
+                       st)
+            comm.all_reduce(val, "max" if want_max else "min")
+            idx = torch.empty(self.nlabels + 1, dtype=torch.int64, device=self.device)
+            self._call("ms_band_extreme_index_dev", _p(data), _p(self.out["labels"]), n, self.nlabels, _p(val),
+                       self.cell_offset, _p(idx), st)
+            comm.all_reduce(idx, "min")
+            none = idx == torch.iinfo(torch.int64).max
+            self.tables[key + "_row"] = torch.where(none, torch.full_like(idx, -1), idx // cols)
+            self.tables[key + "_col"] = torch.where(none, torch.full_like(idx, -1), idx % cols)
+
+
+def run_threaded(dem, nbands, device=0):
+    """One process, one GPU, `nbands` bands as threads (the decomposition without NCCL): returns the BandPipelines
+    after the run.  `dem`: cuda float32 tensor [rows, cols]."""
+    rows, cols = dem.shape
+    grp = ThreadGroup(nbands)
+    pipes, errs = [None] * nbands, []
+
+    def work(rank):
+        try:
+            torch.cuda.set_device(device)
+            p = BandPipeline(rows, cols, ThreadComm(grp, rank), device=device)
+            pipes[rank] = p
+            p.dem.copy_(dem[p.r0:p.r1])
+            p.run()
+        except BaseException as e:      # noqa: BLE001 - report and release the other threads
+            errs.append(e)
+            grp.barrier.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(nbands)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errs:
+        real = [e for e in errs if not isinstance(e, threading.BrokenBarrierError)]
+        raise (real or errs)[0]
+    torch.cuda.synchronize()
+    return pipes

@@ -44,19 +44,25 @@ struct AccSmem {
     unsigned char dir[AH * AH];
 };
 
+// Row bands: `open` bit 0 / 1 = a halo row of flow directions lies above the first / below the last row; a path
+// stepping into it leaves the band through an "exit" like any other tile exit, and (FINAL) a halo cell flowing
+// into the band brings halo_top / halo_bot[its column] = its full count.
 template <bool FINAL>
 __global__ void __launch_bounds__(256) k_acc_tile(const uint8_t *__restrict__ fd, int rows, int cols, int tiles_x,
                                                   double *__restrict__ nodeX, int *__restrict__ entry_next,
-                                                  uint8_t *__restrict__ is_exit, double *__restrict__ accum) {
+                                                  uint8_t *__restrict__ is_exit, double *__restrict__ accum, int open,
+                                                  const double *__restrict__ halo_top,
+                                                  const double *__restrict__ halo_bot) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     AccSmem &S = *reinterpret_cast<AccSmem *>(smem_raw);
     int tile = blockIdx.x;
     int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     int r0 = ty * AT, c0 = tx * AT, tid = threadIdx.x;
+    const int rlo = (open & 1) ? -1 : 0, rhi = rows + ((open & 2) ? 1 : 0);
     for (int k = tid; k < AH * AH; k += 256) {
         int lr = k / AH, lc = k - lr * AH;
         int r = r0 + lr - 1, c = c0 + lc - 1;
-        S.dir[k] = (r >= 0 && r < rows && c >= 0 && c < cols) ? fd[(size_t)r * cols + c] : (unsigned char)255;
+        S.dir[k] = (r >= rlo && r < rhi && c >= 0 && c < cols) ? fd[(long long)r * cols + c] : (unsigned char)255;
     }
     __syncthreads();
     for (int k = tid; k < AT * AT; k += 256) {
@@ -82,8 +88,12 @@ __global__ void __launch_bounds__(256) k_acc_tile(const uint8_t *__restrict__ fd
                 } else if (FINAL) {
                     // upstream neighbour in another tile: it is an exit there; add its full count
                     int gr = r0 + nr, gc = c0 + nc;
-                    int nt = (gr / AT) * tiles_x + (gc / AT);
-                    start += (unsigned long long)nodeX[(size_t)nt * A_SLOTS + perim_slot(gr % AT, gc % AT)];
+                    if (gr < 0) start += (unsigned long long)halo_top[gc];
+                    else if (gr >= rows) start += (unsigned long long)halo_bot[gc];
+                    else {
+                        int nt = (gr / AT) * tiles_x + (gc / AT);
+                        start += (unsigned long long)nodeX[(size_t)nt * A_SLOTS + perim_slot(gr % AT, gc % AT)];
+                    }
                 }
             }
         } else {
@@ -137,13 +147,13 @@ __global__ void __launch_bounds__(256) k_acc_tile(const uint8_t *__restrict__ fd
             int d = S.dir[(er + 1) * AH + (ec + 1)];
             if (d <= 7 && S.dn[cur] == A_OUT) {
                 int gr = r0 + er + kDR[d], gc = c0 + ec + kDC[d];
-                if (gr >= 0 && gr < rows && gc >= 0 && gc < cols) nxt = tile * A_SLOTS + perim_slot(er, ec);
+                if (gr >= rlo && gr < rhi && gc >= 0 && gc < cols) nxt = tile * A_SLOTS + perim_slot(er, ec);
             }
             // is this perimeter cell itself an exit?
             int d0 = S.dir[(lr + 1) * AH + (lc + 1)];
             if (d0 <= 7 && S.dn[lr * AT + lc] == A_OUT) {
                 int gr = r + kDR[d0], gc = c + kDC[d0];
-                if (gr >= 0 && gr < rows && gc >= 0 && gc < cols) {
+                if (gr >= rlo && gr < rhi && gc >= 0 && gc < cols) {
                     ex = 1;
                     nodeX[slot] = (double)S.acc[lr * AT + lc];
                 }
@@ -155,7 +165,7 @@ __global__ void __launch_bounds__(256) k_acc_tile(const uint8_t *__restrict__ fd
 }
 
 // exit u -> entry e = down(u) in the neighbouring tile -> the exit e's in-tile path ends at
-__global__ void __launch_bounds__(256) k_acc_links(const uint8_t *__restrict__ fd, const uint8_t *__restrict__ is_exit,
+__global__ void __launch_bounds__(256) k_acc_links(const uint8_t *__restrict__ fd, uint8_t *__restrict__ is_exit,
                                                    const int *__restrict__ entry_next, int *__restrict__ next,
                                                    int *indeg, int rows, int cols, int tiles_x, int nslots) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,9 +178,13 @@ __global__ void __launch_bounds__(256) k_acc_links(const uint8_t *__restrict__ f
         int r = (tile / tiles_x) * AT + lr, c = (tile % tiles_x) * AT + lc;
         int d = fd[(size_t)r * cols + c];
         int gr = r + kDR[d], gc = c + kDC[d];
-        int nt = (gr / AT) * tiles_x + (gc / AT);
-        nx = entry_next[(size_t)nt * A_SLOTS + perim_slot(gr % AT, gc % AT)];
-        if (nx >= 0) atomicAdd(indeg + nx, 1);
+        if (gr < 0 || gr >= rows) {
+            is_exit[s] = 2;          // leaves the band: a root of the band's link forest (row bands only)
+        } else {
+            int nt = (gr / AT) * tiles_x + (gc / AT);
+            nx = entry_next[(size_t)nt * A_SLOTS + perim_slot(gr % AT, gc % AT)];
+            if (nx >= 0) atomicAdd(indeg + nx, 1);
+        }
     }
     next[s] = nx;
 }
@@ -222,15 +236,208 @@ int accum_dev_impl(const uint8_t *fd, double *acc, int64_t rows, int64_t cols, c
     MS_CUDA(cudaMemsetAsync(indeg.p, 0, (size_t)nslots * sizeof(int), s));
     prof_units(rows * cols);
     MS_LAUNCH(k_acc_tile<false>, ntiles, 256, sizeof(AccSmem), s, fd, (int)rows, (int)cols, tiles_x, X.p, entry_next.p,
-              is_exit.p, (double *)nullptr);
+              is_exit.p, (double *)nullptr, 0, (const double *)nullptr, (const double *)nullptr);
     MS_LAUNCH(k_acc_links, cdiv(nslots, 256), 256, 0, s, fd, is_exit.p, entry_next.p, next.p, indeg.p, (int)rows,
               (int)cols, tiles_x, nslots);
     MS_CUDA(cudaMemcpyAsync(indeg0.p, indeg.p, (size_t)nslots * sizeof(int), cudaMemcpyDeviceToDevice, s));
     MS_LAUNCH(k_acc_node_trace, cdiv(nslots, 256), 256, 0, s, is_exit.p, next.p, indeg0.p, indeg.p, X.p, nslots);
     prof_units(rows * cols);
     MS_LAUNCH(k_acc_tile<true>, ntiles, 256, sizeof(AccSmem), s, fd, (int)rows, (int)cols, tiles_x, X.p, entry_next.p,
-              is_exit.p, acc);
+              is_exit.p, acc, 0, (const double *)nullptr, (const double *)nullptr);
+    return MS_OK;
+}
+
+
+// =====================================================================================================
+// Row-band accumulation.  Phase 1 (accum_band_local): the tile pass and the band's own link
+// forest with nothing flowing in; per band-edge cell it reports (a) where a path leaving the band there enters the
+// neighbour and the count it carries, (b) for a cell that receives flow from the neighbour, the band exit its own
+// path ends at.  The host side joins these into the forest of band exits of all bands (forest_accumulate).  Phase 2
+// (accum_band_finish): the neighbour's totals are injected at the entry cells, the link forest is traced again and
+// the tile pass writes the final counts.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_acc_band_out(const uint8_t *__restrict__ fd, const uint8_t *__restrict__ is_exit,
+                                                      const double *__restrict__ X, const int *__restrict__ entry_next,
+                                                      const int *__restrict__ next, int rows, int cols, int tiles_x,
+                                                      int open, int32_t *exit_to, double *exit_val, int32_t *entry_root) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 2 * cols) return;
+    int side = k / cols, c = k - side * cols;
+    int to = -1, root = -1;
+    double val = 0.0;
+    if (open & (1 << side)) {
+        int r = side ? rows - 1 : 0;
+        int tile = (r / AT) * tiles_x + (c / AT);
+        int slot = tile * A_SLOTS + perim_slot(r % AT, c % AT);
+        int d = fd[(size_t)r * cols + c];
+        if (is_exit[slot] == 2 && d <= 7 && kDR[d] == (side ? 1 : -1)) {
+            to = c + kDC[d];
+            val = X[slot];
+        }
+        int s = entry_next[slot];
+        if (s >= 0) {
+            for (int guard = 0; guard < (1 << 24) && next[s] >= 0; guard++) s = next[s];
+            if (is_exit[s] == 2) {
+                int t2 = s / A_SLOTS, p = s - t2 * A_SLOTS, lr, lc;
+                perim_cell(p, &lr, &lc);
+                int rr = (t2 / tiles_x) * AT + lr, cc = (t2 % tiles_x) * AT + lc;
+                int d2 = fd[(size_t)rr * cols + cc];
+                root = (kDR[d2] > 0 ? cols : 0) + cc;
+            }
+        }
+    }
+    exit_to[k] = to;
+    exit_val[k] = val;
+    entry_root[k] = root;
+}
+
+__global__ void __launch_bounds__(256) k_acc_band_inject(const uint8_t *__restrict__ fd, const int *__restrict__ entry_next,
+                                                         double *X, int rows, int cols, int tiles_x, int open,
+                                                         const double *__restrict__ halo_top,
+                                                         const double *__restrict__ halo_bot) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 2 * cols) return;
+    int side = k / cols, c = k - side * cols;
+    if (!(open & (1 << side))) return;
+    int r = side ? rows - 1 : 0;
+    long long hrow = side ? (long long)rows * cols : -(long long)cols;      // the halo row of flow directions
+    const double *hT = side ? halo_bot : halo_top;
+    double inflow = 0.0;
+    for (int dc = -1; dc <= 1; dc++) {
+        int cu = c + dc;
+        if (cu < 0 || cu >= cols) continue;
+        int d = fd[hrow + cu];
+        if (d > 7) continue;
+        if (kDR[d] == (side ? -1 : 1) && cu + kDC[d] == c) inflow += hT[cu];
+    }
+    if (inflow == 0.0) return;
+    int tile = (r / AT) * tiles_x + (c / AT);
+    int s = entry_next[tile * A_SLOTS + perim_slot(r % AT, c % AT)];
+    if (s >= 0) atomicAdd(X + s, inflow);
+}
+
+__global__ void __launch_bounds__(256) k_fa_indeg(const int32_t *__restrict__ parent, int *indeg, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && parent[i] >= 0) atomicAdd(indeg + parent[i], 1);
+}
+
+__global__ void __launch_bounds__(256) k_fa_trace(const int32_t *__restrict__ parent, const int *__restrict__ indeg0,
+                                                  int *indeg, double *T, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || indeg0[i] != 0) return;
+    double carried = T[i];
+    int cur = i;
+    for (;;) {
+        int nx = parent[cur];
+        if (nx < 0) return;
+        atomicAdd(T + nx, carried);
+        __threadfence();
+        if (atomicSub(indeg + nx, 1) != 1) return;
+        __threadfence();
+        carried = __ldcg(T + nx);
+        cur = nx;
+    }
+}
+
+static int acc_band_bufs(ms_band *B, int *ntiles_out, int *nslots_out) {
+    int tiles_x = (int)cdiv(B->cols, AT), tiles_y = (int)cdiv(B->rows, AT);
+    int ntiles = tiles_x * tiles_y, nslots = ntiles * A_SLOTS;
+    *ntiles_out = ntiles;
+    *nslots_out = nslots;
+    if (!band_buf(B, BB_ACC_X, (size_t)nslots * 8) || !band_buf(B, BB_ACC_X0, (size_t)nslots * 8) ||
+        !band_buf(B, BB_ACC_ENTRY_NEXT, (size_t)nslots * 4) || !band_buf(B, BB_ACC_NEXT, (size_t)nslots * 4) ||
+        !band_buf(B, BB_ACC_INDEG, (size_t)nslots * 4) || !band_buf(B, BB_ACC_INDEG0, (size_t)nslots * 4) ||
+        !band_buf(B, BB_ACC_ISEXIT, (size_t)nslots))
+        return MS_ERR_CUDA;
+    return MS_OK;
+}
+
+static int acc_attr() {
+    static bool attr_done = false;
+    if (!attr_done) {
+        MS_CUDA(cudaFuncSetAttribute(k_acc_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccSmem)));
+        MS_CUDA(cudaFuncSetAttribute(k_acc_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccSmem)));
+        attr_done = true;
+    }
     return MS_OK;
 }
 
 }  // namespace ms
+
+extern "C" {
+
+int ms_band_accum_local_dev(ms_band *B, const uint8_t *fd, int32_t *exit_to, double *exit_val, int32_t *entry_root,
+                            void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !fd || !exit_to || !exit_val || !entry_root) { set_error("band accumulation: null pointer"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    MS_TRY(acc_attr());
+    int ntiles, nslots;
+    MS_TRY(acc_band_bufs(B, &ntiles, &nslots));
+    int rows = (int)B->rows, cols = (int)B->cols, tiles_x = (int)cdiv(cols, AT);
+    double *X = (double *)B->buf[BB_ACC_X], *X0 = (double *)B->buf[BB_ACC_X0];
+    int *entry_next = (int *)B->buf[BB_ACC_ENTRY_NEXT], *next = (int *)B->buf[BB_ACC_NEXT];
+    int *indeg = (int *)B->buf[BB_ACC_INDEG], *indeg0 = (int *)B->buf[BB_ACC_INDEG0];
+    uint8_t *is_exit = (uint8_t *)B->buf[BB_ACC_ISEXIT];
+    MS_CUDA(cudaMemsetAsync(indeg, 0, (size_t)nslots * sizeof(int), s));
+    MS_CUDA(cudaMemsetAsync(X, 0, (size_t)nslots * sizeof(double), s));
+    prof_units(B->rows * B->cols);
+    MS_LAUNCH(k_acc_tile<false>, ntiles, 256, sizeof(AccSmem), s, fd, rows, cols, tiles_x, X, entry_next, is_exit,
+              (double *)nullptr, B->open, (const double *)nullptr, (const double *)nullptr);
+    MS_LAUNCH(k_acc_links, cdiv(nslots, 256), 256, 0, s, fd, is_exit, entry_next, next, indeg, rows, cols, tiles_x, nslots);
+    MS_CUDA(cudaMemcpyAsync(indeg0, indeg, (size_t)nslots * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    MS_CUDA(cudaMemcpyAsync(X0, X, (size_t)nslots * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    MS_LAUNCH(k_acc_node_trace, cdiv(nslots, 256), 256, 0, s, is_exit, next, indeg0, indeg, X, nslots);
+    MS_LAUNCH(k_acc_band_out, cdiv(2 * cols, 256), 256, 0, s, fd, is_exit, X, entry_next, next, rows, cols, tiles_x,
+              B->open, exit_to, exit_val, entry_root);
+    return MS_OK;
+}
+
+/* totals over a forest given by parent indices (-1 = root): T[i] += sum of T over the subtree below i */
+int ms_forest_accumulate_dev(int64_t n, const int32_t *parent, double *T, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (n < 0 || (n && (!parent || !T))) { set_error("forest_accumulate: bad argument"); return MS_ERR_ARG; }
+    if (n == 0) return MS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    DevBuf<int> indeg, indeg0;
+    MS_TRY(indeg.alloc((size_t)n, s));
+    MS_TRY(indeg0.alloc((size_t)n, s));
+    MS_CUDA(cudaMemsetAsync(indeg.p, 0, (size_t)n * sizeof(int), s));
+    MS_LAUNCH(k_fa_indeg, cdiv(n, 256), 256, 0, s, parent, indeg.p, (int)n);
+    MS_CUDA(cudaMemcpyAsync(indeg0.p, indeg.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    MS_LAUNCH(k_fa_trace, cdiv(n, 256), 256, 0, s, parent, indeg0.p, indeg.p, T, (int)n);
+    return MS_OK;
+}
+
+int ms_band_accum_finish_dev(ms_band *B, const uint8_t *fd, const double *halo_total_top, const double *halo_total_bot,
+                             double *accum, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !fd || !accum || !B->buf[BB_ACC_X0]) { set_error("band accumulation: finish before the local phase"); return MS_ERR_ARG; }
+    if (((B->open & 1) && !halo_total_top) || ((B->open & 2) && !halo_total_bot)) {
+        set_error("band accumulation: halo totals missing for an open band edge");
+        return MS_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int ntiles, nslots;
+    MS_TRY(acc_band_bufs(B, &ntiles, &nslots));
+    int rows = (int)B->rows, cols = (int)B->cols, tiles_x = (int)cdiv(cols, AT);
+    double *X = (double *)B->buf[BB_ACC_X], *X0 = (double *)B->buf[BB_ACC_X0];
+    int *entry_next = (int *)B->buf[BB_ACC_ENTRY_NEXT], *next = (int *)B->buf[BB_ACC_NEXT];
+    int *indeg = (int *)B->buf[BB_ACC_INDEG], *indeg0 = (int *)B->buf[BB_ACC_INDEG0];
+    uint8_t *is_exit = (uint8_t *)B->buf[BB_ACC_ISEXIT];
+    MS_CUDA(cudaMemcpyAsync(X, X0, (size_t)nslots * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    MS_CUDA(cudaMemcpyAsync(indeg, indeg0, (size_t)nslots * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    if (B->open)
+        MS_LAUNCH(k_acc_band_inject, cdiv(2 * cols, 256), 256, 0, s, fd, entry_next, X, rows, cols, tiles_x, B->open,
+                  halo_total_top, halo_total_bot);
+    MS_LAUNCH(k_acc_node_trace, cdiv(nslots, 256), 256, 0, s, is_exit, next, indeg0, indeg, X, nslots);
+    prof_units(B->rows * B->cols);
+    MS_LAUNCH(k_acc_tile<true>, ntiles, 256, sizeof(AccSmem), s, fd, rows, cols, tiles_x, X, entry_next, is_exit, accum,
+              B->open, halo_total_top, halo_total_bot);
+    return MS_OK;
+}
+
+}  // extern "C"

@@ -146,6 +146,29 @@ int exclusive_scan_i32(const int *flags, int *out, int64_t n, int64_t *total_dev
 // rounds_out (host, optional) receives the number of rounds.  MS_ERR_NOCONV after 64 rounds (cycles).
 int forest_resolve(int *ptr, int64_t n, int64_t *rounds_out, cudaStream_t s);
 
+// ---- row-band context ------------------------------------------------------------
+// One band of a raster split by rows across GPUs.  Raster pointers handed to the band entry points point at the
+// band's first own row; when `open & MS_OPEN_TOP` the row before it in memory is a halo row (the last row of the
+// band above), when `open & MS_OPEN_BOTTOM` a halo row follows the last own row.  The context keeps the device
+// state that has to survive between the phases of a stage (the exchanges happen on the host side in between).
+enum BandBuf {
+    BB_LAB, BB_COMP, BB_E, BB_FROZEN, BB_FRANK, BB_HASHK, BB_HASHV,
+    BB_ACC_X, BB_ACC_X0, BB_ACC_ENTRY_NEXT, BB_ACC_NEXT, BB_ACC_INDEG, BB_ACC_INDEG0, BB_ACC_ISEXIT,
+    BB_CC_PARENT, BB_CC_RANK, BB_WS_PTR, BB_NF_FLAG, BB_NF_SIDES, BB_NF_RING, BB_NF_CTL, BB_MISC, BB_COUNT
+};
+}  // namespace ms
+struct ms_band {
+    int64_t rows, cols;
+    int open;
+    void *buf[ms::BB_COUNT];
+    size_t cap[ms::BB_COUNT];
+    int nC;            // catchments of the band (fill)
+    int nF;            // frozen components (fill)
+    int gid_base;      // global id of the band's first frozen component
+};
+namespace ms {
+void *band_buf(ms_band *b, int slot, size_t bytes);      // grow-only cudaMalloc'ed buffer of the context
+
 // internal device-pointer stage entry points used by the pipeline (pipeline.cu)
 int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_t rows, int64_t cols,
                           int64_t *stats, cudaStream_t s);

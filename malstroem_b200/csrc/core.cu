@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <chrono>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -149,6 +150,27 @@ static int init_device(int device) {
     return MS_OK;
 }
 
+void *band_buf(ms_band *b, int slot, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b->cap[slot] >= bytes) return b->buf[slot];
+    if (b->buf[slot]) {
+        cudaDeviceSynchronize();
+        cudaFree(b->buf[slot]);
+        b->buf[slot] = nullptr;
+        b->cap[slot] = 0;
+    }
+    size_t want = bytes + (bytes >> 3);
+    void *p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("band context: cudaMalloc(%zu) failed", want);
+        return nullptr;
+    }
+    b->buf[slot] = p;
+    b->cap[slot] = want;
+    return p;
+}
+
 int ensure_init() {
     if (g_device >= 0) {
         // another library (torch) may have switched the current device of this thread
@@ -165,7 +187,78 @@ int ensure_init() {
 
 extern "C" {
 
-int ms_version(void) { return 100; }
+/* Host side of the row-band connected components: components that touch across a band edge
+ * are merged; a merged component keeps its smallest root (global cell index).  root_top / root_bot hold, for each
+ * of the G bands, the root of every cell of the band's first / last row (-1 = background), G * cols entries each.
+ * Output: every distinct root seen on an interior band edge, ascending, with the root of its merged component.
+ * Pure CPU code (a few thousand cells): runs identically on every rank. */
+int ms_cc_boundary_merge(int nbands, int64_t cols, const int64_t *root_top, const int64_t *root_bot,
+                         int64_t *out_root, int64_t *out_global, int64_t capacity, int64_t *n_out) {
+    if (nbands < 1 || cols < 1 || !root_top || !root_bot || !n_out) { ms::set_error("cc_boundary_merge: bad argument"); return MS_ERR_ARG; }
+    std::vector<int64_t> ids;
+    for (int g = 0; g + 1 < nbands; g++)
+        for (int64_t c = 0; c < cols; c++) {
+            int64_t a = root_bot[(int64_t)g * cols + c], b = root_top[(int64_t)(g + 1) * cols + c];
+            if (a >= 0) ids.push_back(a);
+            if (b >= 0) ids.push_back(b);
+        }
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    std::vector<int> parent(ids.size());
+    for (size_t k = 0; k < ids.size(); k++) parent[k] = (int)k;
+    auto find = [&](int x) {
+        while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+        return x;
+    };
+    auto index_of = [&](int64_t v) { return (int)(std::lower_bound(ids.begin(), ids.end(), v) - ids.begin()); };
+    for (int g = 0; g + 1 < nbands; g++)
+        for (int64_t c = 0; c < cols; c++) {
+            int64_t a = root_bot[(int64_t)g * cols + c];
+            if (a < 0) continue;
+            int ia = index_of(a);
+            for (int64_t d = -1; d <= 1; d++) {
+                if (c + d < 0 || c + d >= cols) continue;
+                int64_t b = root_top[(int64_t)(g + 1) * cols + c + d];
+                if (b < 0) continue;
+                int x = find(ia), y = find(index_of(b));
+                if (x == y) continue;
+                if (x < y) parent[y] = x; else parent[x] = y;      // ids ascend with the cell index: smaller index wins
+            }
+        }
+    *n_out = (int64_t)ids.size();
+    if ((int64_t)ids.size() > capacity) { ms::set_error("cc_boundary_merge: %zu roots do not fit capacity %lld", ids.size(), (long long)capacity); return MS_ERR_ARG; }
+    for (size_t k = 0; k < ids.size(); k++) {
+        if (out_root) out_root[k] = ids[k];
+        if (out_global) out_global[k] = ids[find((int)k)];
+    }
+    return MS_OK;
+}
+
+int ms_version(void) { return 110; }
+
+int ms_band_create(int64_t rows, int64_t cols, int open, ms_band **out) {
+    MS_TRY(ms::ensure_init());
+    if (!out || rows < 2 || cols < 3 || rows * cols > (1ll << 29) || (open & ~3) || ((open & 2) && (rows % 64))) {
+        ms::set_error("ms_band_create: unsupported band %lld x %lld (open %d)", (long long)rows, (long long)cols, open);
+        return MS_ERR_SHAPE;
+    }
+    ms_band *b = new ms_band();
+    memset(b, 0, sizeof(*b));
+    b->rows = rows;
+    b->cols = cols;
+    b->open = open;
+    *out = b;
+    return MS_OK;
+}
+
+int ms_band_destroy(ms_band *b) {
+    if (!b) return MS_OK;
+    cudaDeviceSynchronize();
+    for (int k = 0; k < ms::BB_COUNT; k++)
+        if (b->buf[k]) cudaFree(b->buf[k]);
+    delete b;
+    return MS_OK;
+}
 
 int ms_init(int device) {
     if (ms::g_device == device) return MS_OK;

@@ -77,13 +77,15 @@ int minmax_dev(const float *z, int64_t n, float *out2, cudaStream_t s) {
 }
 
 // ---- K1 -------------------------------------------------------------------------------------------
+// `open` (row bands): bit 0 / 1 = the first / last row is not the raster border but continues in another band;
+// its cells are ordinary cells whose window is clipped to the band (a catchment never crosses a band edge).
 __global__ void __launch_bounds__(256) k_descent(const float *__restrict__ z, int *__restrict__ ptr, int rows,
-                                                 int cols) {
+                                                 int cols, int open) {
     int c = blockIdx.x * 64 + (threadIdx.x & 63);
     int r = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (r >= rows || c >= cols) return;
     int i = r * cols + c;
-    if (r == 0 || c == 0 || r == rows - 1 || c == cols - 1) {
+    if ((r == 0 && !(open & 1)) || c == 0 || (r == rows - 1 && !(open & 2)) || c == cols - 1) {
         ptr[i] = 0;
         return;
     }
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(256) k_descent(const float *__restrict__ z, in
 #pragma unroll
         for (int dc = -1; dc <= 1; dc++) {
             if (dr == 0 && dc == 0) continue;
+            if (r + dr < 0 || r + dr >= rows) continue;
             int j = i + dr * cols + dc;
             float zj = __ldg(z + j);
             if (zj < bz || (zj == bz && j < bi)) { bz = zj; bi = j; }
@@ -120,10 +123,14 @@ __global__ void __launch_bounds__(256) k_boruvka_init(int *comp, uint32_t *E, in
     }
 }
 
-// lowest outgoing edge of every component that has not reached "outside" (component 0) yet
+// lowest outgoing edge of every component that has not reached "outside" (component 0) yet.
+// Row bands: an edge into a halo row (the neighbouring band) is "foreign": its key carries FOREIGN_BIT, which also
+// sorts it behind every local edge of the same weight; a component whose lowest edge is foreign freezes (k_hook).
+constexpr unsigned FOREIGN_BIT = 0x80000000u;
+
 __global__ void __launch_bounds__(256) k_minedge(const float *__restrict__ z, const int *__restrict__ lab,
-                                                 const int *__restrict__ comp, unsigned long long *best,
-                                                 int rows, int cols) {
+                                                 const int *__restrict__ comp, const uint8_t *__restrict__ frozen,
+                                                 unsigned long long *best, int rows, int cols) {
     int c = blockIdx.x * 64 + (threadIdx.x & 63);
     int r = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (r >= rows || c >= cols) return;
@@ -132,15 +139,22 @@ __global__ void __launch_bounds__(256) k_minedge(const float *__restrict__ z, co
     if (l == 0) return;
     int cc = comp[l];
     if (cc == 0) return;
+    if (frozen && frozen[cc]) return;
     float zc = z[i];
     unsigned long long bk = KEY_NONE;
-    // interior cell (label != 0 implies not on the border): all 8 neighbours are in the raster
+    // interior cell (label != 0 implies not on the border): all 8 neighbours are in the raster, or in a halo row
 #pragma unroll
     for (int dr = -1; dr <= 1; dr++)
 #pragma unroll
         for (int dc = -1; dc <= 1; dc++) {
             if (dr == 0 && dc == 0) continue;
             int j = i + dr * cols + dc;
+            if (r + dr < 0 || r + dr >= rows) {
+                float w = fmaxf(zc, __ldg(z + j));
+                unsigned long long key = ((unsigned long long)okey32(w) << 32) | FOREIGN_BIT | (unsigned)c;
+                bk = key < bk ? key : bk;
+                continue;
+            }
             int lj = __ldg(lab + j);
             if (lj == l) continue;
             if (__ldg(comp + lj) == cc) continue;
@@ -161,7 +175,7 @@ __device__ inline int edge_other(int lo, int code, int cols) {
 // every live component hooks to the component across its lowest edge; mutual pairs keep the smaller id
 __global__ void __launch_bounds__(256) k_hook(const unsigned long long *__restrict__ best,
                                               const int *__restrict__ comp, const int *__restrict__ lab,
-                                              int *parent, uint32_t *wk, int nC, int cols) {
+                                              int *parent, uint32_t *wk, uint8_t *frozen, int nC, int cols) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nC) return;
     parent[k] = k;
@@ -170,6 +184,11 @@ __global__ void __launch_bounds__(256) k_hook(const unsigned long long *__restri
     unsigned long long b = best[k];
     if (b == KEY_NONE) return;
     unsigned id = (unsigned)(b & 0xffffffffu);
+    if (frozen && (id & FOREIGN_BIT)) {
+        // lowest way out leads into another band: the component waits for the boundary graph (fill_band_*)
+        frozen[k] = 1;
+        return;
+    }
     int lo = (int)(id >> 2), code = (int)(id & 3u);
     int hi = edge_other(lo, code, cols);
     int ca = comp[lab[lo]], cb = comp[lab[hi]];
@@ -192,7 +211,8 @@ __device__ inline int uf_find(int *parent, int k) {
 
 // E = max(E, weight of the edge the catchment's component left through); component := merged root
 __global__ void __launch_bounds__(256) k_boruvka_update(int *comp, uint32_t *E, int *parent,
-                                                        const uint32_t *__restrict__ wk, int nC,
+                                                        const uint32_t *__restrict__ wk,
+                                                        const uint8_t *__restrict__ frozen, int nC,
                                                         unsigned long long *best, int *remaining) {
     int l = blockIdx.x * blockDim.x + threadIdx.x;
     int live = 0;
@@ -204,7 +224,7 @@ __global__ void __launch_bounds__(256) k_boruvka_update(int *comp, uint32_t *E, 
             if (w > e) E[l] = w;
             int r = uf_find(parent, k);
             comp[l] = r;
-            live = (r == l);      // still the representative of a component that has not reached 0
+            live = (r == l) && !(frozen && frozen[r]);      // still searching: neither at 0 nor frozen
         }
     }
     int cnt = __syncthreads_count(live);
@@ -239,7 +259,7 @@ int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_
     unsigned g1 = cdiv(n, 256);
     int64_t *h = host_flags().h;
 
-    MS_LAUNCH(k_descent, g2, 256, 0, s, dtm, lab.p, (int)rows, (int)cols);
+    MS_LAUNCH(k_descent, g2, 256, 0, s, dtm, lab.p, (int)rows, (int)cols, 0);
     int64_t jump_rounds = 0;
     MS_TRY(forest_resolve(lab.p, n, &jump_rounds, s));
     MS_LAUNCH(k_rootflag, g1, 256, 0, s, lab.p, tmp.p, n);
@@ -265,10 +285,11 @@ int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_
     int rounds = 0;
     int64_t live = nC - 1;       // live components; each round every one of them merges with another
     while (live > 0) {
-        MS_LAUNCH(k_minedge, g2, 256, 0, s, dtm, lab.p, comp.p, best.p, (int)rows, (int)cols);
-        MS_LAUNCH(k_hook, gc, 256, 0, s, best.p, comp.p, lab.p, parent.p, wk.p, nC, (int)cols);
+        MS_LAUNCH(k_minedge, g2, 256, 0, s, dtm, lab.p, comp.p, (const uint8_t *)nullptr, best.p, (int)rows, (int)cols);
+        MS_LAUNCH(k_hook, gc, 256, 0, s, best.p, comp.p, lab.p, parent.p, wk.p, (uint8_t *)nullptr, nC, (int)cols);
         MS_CUDA(cudaMemsetAsync(remaining.p, 0, sizeof(int), s));
-        MS_LAUNCH(k_boruvka_update, gc, 256, 0, s, comp.p, E.p, parent.p, wk.p, nC, best.p, remaining.p);
+        MS_LAUNCH(k_boruvka_update, gc, 256, 0, s, comp.p, E.p, parent.p, wk.p, (const uint8_t *)nullptr, nC, best.p,
+                  remaining.p);
         MS_CUDA(cudaMemcpyAsync(h, remaining.p, sizeof(int), cudaMemcpyDeviceToHost, s));
         MS_TRY(ms::stream_sync(s));
         int64_t now = *(int *)h;
@@ -285,9 +306,308 @@ int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_
     return MS_OK;
 }
 
+
+// =====================================================================================================
+// Row-band fill.  The band runs the same Boruvka contraction on its own rows; a component
+// whose lowest outgoing edge leads into a neighbouring band cannot decide locally and freezes (every hook made
+// before that is a hook the global algorithm makes too, because a component that hooks knows all its edges).
+// What is left is a small graph: frozen components of all bands + "outside", joined by the lowest cell-pair edge
+// between each pair (inside a band and across band edges).  By the same claim as in the single-GPU case the spill
+// elevation of a catchment is max(E collected so far, minimax height from its frozen component to "outside" in
+// that graph).  Phases: fill_band_local -> (all-gather of counts) -> fill_band_edge_ids -> (halo exchange of ids)
+// -> fill_band_edges -> (all-gather of edge lists) -> graph_minimax (every rank, same result) -> fill_band_finish.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_frozen_flags(const int *comp, const uint8_t *frozen, int *flag, int nC) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nC) flag[k] = (k != 0 && comp[k] == k && frozen[k]) ? 1 : 0;
+}
+
+__device__ inline int band_gid(int K, const int *frank, int base) { return K ? 1 + base + frank[K] : 0; }
+
+__global__ void __launch_bounds__(256) k_band_edge_ids(const int *__restrict__ lab, const int *__restrict__ comp,
+                                                       const int *__restrict__ frank, int base, int rows, int cols,
+                                                       int32_t *top, int32_t *bot) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    top[c] = band_gid(comp[lab[c]], frank, base);
+    bot[c] = band_gid(comp[lab[(size_t)(rows - 1) * cols + c]], frank, base);
+}
+
+constexpr unsigned long long HASH_EMPTY = ~0ull;
+
+__device__ inline void edge_insert(unsigned long long *hk, uint32_t *hv, unsigned H, int ga, int gb, uint32_t w,
+                                   int *overflow) {
+    int a = ga < gb ? ga : gb, b = ga < gb ? gb : ga;
+    unsigned long long key = ((unsigned long long)(unsigned)a << 32) | (unsigned)b;
+    unsigned long long x = key * 0x9E3779B97F4A7C15ull;
+    unsigned h = (unsigned)(x >> 32) & (H - 1);
+    for (unsigned probes = 0; probes < H; probes++) {
+        unsigned long long cur = hk[h];
+        if (cur == HASH_EMPTY) {
+            unsigned long long old = atomicCAS(hk + h, HASH_EMPTY, key);
+            cur = (old == HASH_EMPTY) ? key : old;
+        }
+        if (cur == key) {
+            if (w < hv[h]) atomicMin(hv + h, w);
+            return;
+        }
+        h = (h + 1) & (H - 1);
+    }
+    *overflow = 1;
+}
+
+// lowest cell-pair edge between every frozen component of the band and each different neighbour (another frozen
+// component, "outside" incl. the components that reached it, or a component of the neighbouring band)
+__global__ void __launch_bounds__(256) k_band_edges(const float *__restrict__ z, const int *__restrict__ lab,
+                                                    const int *__restrict__ comp, const int *__restrict__ frank,
+                                                    int base, const int32_t *__restrict__ halo_top,
+                                                    const int32_t *__restrict__ halo_bot, int rows, int cols,
+                                                    unsigned long long *hk, uint32_t *hv, unsigned H, int *overflow) {
+    int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (r >= rows || c >= cols) return;
+    int i = r * cols + c;
+    int l = lab[i];
+    if (l == 0) return;
+    int K = comp[l];
+    if (K == 0) return;
+    int ga = band_gid(K, frank, base);
+    float zc = z[i];
+    int last_gb = -1;
+    uint32_t last_w = 0;
+#pragma unroll
+    for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+        for (int dc = -1; dc <= 1; dc++) {
+            if (dr == 0 && dc == 0) continue;
+            int j = i + dr * cols + dc;
+            int gb;
+            if (r + dr < 0) gb = halo_top[c + dc];
+            else if (r + dr >= rows) gb = halo_bot[c + dc];
+            else {
+                int lj = __ldg(lab + j);
+                if (lj == l) continue;
+                int Kj = lj ? __ldg(comp + lj) : 0;
+                if (Kj == K) continue;
+                gb = band_gid(Kj, frank, base);
+            }
+            uint32_t w = okey32(fmaxf(zc, __ldg(z + j)));
+            if (gb == last_gb && w >= last_w) continue;      // same neighbour component again, no better
+            last_gb = gb;
+            last_w = w;
+            edge_insert(hk, hv, H, ga, gb, w, overflow);
+        }
+}
+
+__global__ void __launch_bounds__(256) k_band_edges_compact(const unsigned long long *hk, const uint32_t *hv,
+                                                            unsigned H, int32_t *ea, int32_t *eb, float *ew,
+                                                            int64_t cap, int *count) {
+    unsigned h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    unsigned long long key = hk[h];
+    if (key == HASH_EMPTY) return;
+    int k = atomicAdd(count, 1);
+    if (k < cap) {
+        ea[k] = (int32_t)(key >> 32);
+        eb[k] = (int32_t)(key & 0xffffffffu);
+        ew[k] = okey32_inv(hv[h]);
+    }
+}
+
+// minimax height to node 0 on a small undirected graph: Bellman-Ford with (max, min), one CTA
+__global__ void __launch_bounds__(1024) k_graph_minimax(int nn, const int32_t *__restrict__ ea,
+                                                        const int32_t *__restrict__ eb, const float *__restrict__ ew,
+                                                        int ne, uint32_t *X, float *out, int *iters) {
+    for (int k = threadIdx.x; k < nn; k += blockDim.x) X[k] = k ? 0xffffffffu : okey32(-INFINITY);
+    __syncthreads();
+    int it = 0;
+    for (;; it++) {
+        int changed = 0;
+        for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+            int a = ea[e], b = eb[e];
+            uint32_t w = okey32(ew[e]);
+            uint32_t xa = *(volatile uint32_t *)(X + a), xb = *(volatile uint32_t *)(X + b);
+            uint32_t ca = w > xb ? w : xb, cb = w > xa ? w : xa;
+            if (ca < xa) { atomicMin(X + a, ca); changed = 1; }
+            if (cb < xb) { atomicMin(X + b, cb); changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    for (int k = threadIdx.x; k < nn; k += blockDim.x) out[k] = okey32_inv(X[k]);
+    if (threadIdx.x == 0 && iters) *iters = it;
+}
+
+__global__ void __launch_bounds__(256) k_band_raise(uint32_t *E, const int *__restrict__ comp,
+                                                    const int *__restrict__ frank, int base,
+                                                    const float *__restrict__ X, int nC) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= nC || l == 0) return;
+    int K = comp[l];
+    if (K == 0) return;
+    uint32_t x = okey32(X[band_gid(K, frank, base)]);
+    if (x > E[l]) E[l] = x;
+}
+
+int fill_band_local(ms_band *B, const float *dem, int64_t *n_frozen, cudaStream_t s) {
+    int64_t rows = B->rows, cols = B->cols, n = rows * cols;
+    int *lab = (int *)band_buf(B, BB_LAB, (size_t)n * sizeof(int));
+    if (!lab) return MS_ERR_CUDA;
+    DevBuf<int> tmp;
+    DevBuf<int64_t> total;
+    MS_TRY(tmp.alloc((size_t)n, s));
+    MS_TRY(total.alloc(1, s));
+    dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
+    unsigned g1 = cdiv(n, 256);
+    int64_t *h = host_flags().h;
+    MS_LAUNCH(k_descent, g2, 256, 0, s, dem, lab, (int)rows, (int)cols, B->open);
+    MS_TRY(forest_resolve(lab, n, nullptr, s));
+    MS_LAUNCH(k_rootflag, g1, 256, 0, s, lab, tmp.p, n);
+    MS_TRY(exclusive_scan_i32(tmp.p, tmp.p, n, total.p, s));
+    MS_LAUNCH(k_catchment_ids, g1, 256, 0, s, lab, tmp.p, n);
+    MS_CUDA(cudaMemcpyAsync(h, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    int nC = (int)h[0];
+    tmp.release();
+    B->nC = nC;
+    int *comp = (int *)band_buf(B, BB_COMP, (size_t)nC * sizeof(int));
+    uint32_t *E = (uint32_t *)band_buf(B, BB_E, (size_t)nC * sizeof(uint32_t));
+    uint8_t *frozen = (uint8_t *)band_buf(B, BB_FROZEN, (size_t)nC);
+    int *frank = (int *)band_buf(B, BB_FRANK, (size_t)nC * sizeof(int));
+    if (!comp || !E || !frozen || !frank) return MS_ERR_CUDA;
+    DevBuf<int> parent, remaining;
+    DevBuf<uint32_t> wk;
+    DevBuf<unsigned long long> best;
+    MS_TRY(parent.alloc(nC, s));
+    MS_TRY(wk.alloc(nC, s));
+    MS_TRY(best.alloc(nC, s));
+    MS_TRY(remaining.alloc(1, s));
+    unsigned gc = cdiv(nC, 256);
+    MS_LAUNCH(k_boruvka_init, gc, 256, 0, s, comp, E, nC);
+    MS_CUDA(cudaMemsetAsync(best.p, 0xff, (size_t)nC * sizeof(unsigned long long), s));
+    MS_CUDA(cudaMemsetAsync(frozen, 0, (size_t)nC, s));
+    int rounds = 0;
+    int64_t live = nC - 1;
+    while (live > 0) {
+        MS_LAUNCH(k_minedge, g2, 256, 0, s, dem, lab, comp, (const uint8_t *)frozen, best.p, (int)rows, (int)cols);
+        MS_LAUNCH(k_hook, gc, 256, 0, s, best.p, comp, lab, parent.p, wk.p, frozen, nC, (int)cols);
+        MS_CUDA(cudaMemsetAsync(remaining.p, 0, sizeof(int), s));
+        MS_LAUNCH(k_boruvka_update, gc, 256, 0, s, comp, E, parent.p, wk.p, (const uint8_t *)frozen, nC, best.p,
+                  remaining.p);
+        MS_CUDA(cudaMemcpyAsync(h, remaining.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MS_TRY(ms::stream_sync(s));
+        int64_t now = *(int *)h;
+        rounds++;
+        if (now >= live || rounds > 64) {
+            set_error("band fill: Boruvka contraction stalled (%lld -> %lld live components, round %d)",
+                      (long long)live, (long long)now, rounds);
+            return MS_ERR_NOCONV;
+        }
+        live = now;
+    }
+    // dense ranks of the frozen component roots
+    MS_LAUNCH(k_frozen_flags, gc, 256, 0, s, comp, frozen, frank, nC);
+    MS_TRY(exclusive_scan_i32(frank, frank, nC, total.p, s));
+    MS_CUDA(cudaMemcpyAsync(h, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    B->nF = (int)h[0];
+    if (n_frozen) *n_frozen = B->nF;
+    return MS_OK;
+}
+
 }  // namespace ms
 
 extern "C" {
+
+int ms_band_fill_local_dev(ms_band *B, const float *dem, int64_t *n_frozen, void *stream) {
+    MS_TRY(ms::ensure_init());
+    if (!B || !dem) { ms::set_error("band fill: null pointer"); return MS_ERR_ARG; }
+    return ms::fill_band_local(B, dem, n_frozen, (cudaStream_t)stream);
+}
+
+int ms_band_fill_edge_ids_dev(ms_band *B, int64_t gid_base, int32_t *gid_top, int32_t *gid_bot, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !gid_top || !gid_bot || !B->buf[BB_LAB]) { set_error("band fill: edge ids before the local phase"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    B->gid_base = (int)gid_base;
+    MS_LAUNCH(k_band_edge_ids, cdiv(B->cols, 256), 256, 0, s, (const int *)B->buf[BB_LAB], (const int *)B->buf[BB_COMP],
+              (const int *)B->buf[BB_FRANK], B->gid_base, (int)B->rows, (int)B->cols, gid_top, gid_bot);
+    return MS_OK;
+}
+
+int ms_band_fill_edges_dev(ms_band *B, const float *dem, const int32_t *halo_gid_top, const int32_t *halo_gid_bot,
+                           int32_t *edge_a, int32_t *edge_b, float *edge_w, int64_t capacity, int64_t *n_edges,
+                           void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !dem || !edge_a || !edge_b || !edge_w || !n_edges) { set_error("band fill: null pointer"); return MS_ERR_ARG; }
+    if (((B->open & 1) && !halo_gid_top) || ((B->open & 2) && !halo_gid_bot)) {
+        set_error("band fill: halo component ids missing for an open band edge");
+        return MS_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t *h = host_flags().h;
+    unsigned H = 4096;
+    while ((int64_t)H < 16ll * ((int64_t)B->nF + B->cols)) H <<= 1;
+    for (int attempt = 0; attempt < 6; attempt++, H <<= 1) {
+        unsigned long long *hk = (unsigned long long *)band_buf(B, BB_HASHK, (size_t)H * 8);
+        uint32_t *hv = (uint32_t *)band_buf(B, BB_HASHV, (size_t)H * 4);
+        int *cnt = (int *)band_buf(B, BB_MISC, 64);
+        if (!hk || !hv || !cnt) return MS_ERR_CUDA;
+        MS_CUDA(cudaMemsetAsync(hk, 0xff, (size_t)H * 8, s));
+        MS_CUDA(cudaMemsetAsync(hv, 0xff, (size_t)H * 4, s));
+        MS_CUDA(cudaMemsetAsync(cnt, 0, 64, s));
+        dim3 g2(cdiv(B->cols, 64), cdiv(B->rows, 4));
+        MS_LAUNCH(k_band_edges, g2, 256, 0, s, dem, (const int *)B->buf[BB_LAB], (const int *)B->buf[BB_COMP],
+                  (const int *)B->buf[BB_FRANK], B->gid_base, halo_gid_top, halo_gid_bot, (int)B->rows, (int)B->cols, hk,
+                  hv, H, cnt + 1);
+        MS_LAUNCH(k_band_edges_compact, cdiv(H, 256), 256, 0, s, hk, hv, H, edge_a, edge_b, edge_w, capacity, cnt);
+        MS_CUDA(cudaMemcpyAsync(h, cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        MS_TRY(ms::stream_sync(s));
+        int ne = ((int *)h)[0], overflow = ((int *)h)[1];
+        if (overflow) continue;      // table too small: double it
+        if (ne > capacity) {
+            set_error("band fill: %d boundary-graph edges do not fit the caller's capacity %lld", ne, (long long)capacity);
+            *n_edges = ne;
+            return MS_ERR_ARG;
+        }
+        *n_edges = ne;
+        return MS_OK;
+    }
+    set_error("band fill: boundary-graph edge table overflow");
+    return MS_ERR_NOCONV;
+}
+
+int ms_graph_minimax_dev(int64_t n_nodes, const int32_t *edge_a, const int32_t *edge_b, const float *edge_w,
+                         int64_t n_edges, float *out_x, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (n_nodes < 1 || n_edges < 0 || !out_x || (n_edges && (!edge_a || !edge_b || !edge_w))) {
+        set_error("graph_minimax: bad argument");
+        return MS_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    DevBuf<uint32_t> X;
+    MS_TRY(X.alloc((size_t)n_nodes, s));
+    MS_LAUNCH(k_graph_minimax, 1, 1024, 0, s, (int)n_nodes, edge_a, edge_b, edge_w, (int)n_edges, X.p, out_x,
+              (int *)nullptr);
+    return MS_OK;
+}
+
+int ms_band_fill_finish_dev(ms_band *B, const float *dem, const float *graph_x, float *filled, float *depths,
+                            void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !dem || !filled || !B->buf[BB_LAB] || (B->nF && !graph_x)) { set_error("band fill: bad argument"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t n = B->rows * B->cols;
+    if (B->nF)
+        MS_LAUNCH(k_band_raise, cdiv(B->nC, 256), 256, 0, s, (uint32_t *)B->buf[BB_E], (const int *)B->buf[BB_COMP],
+                  (const int *)B->buf[BB_FRANK], B->gid_base, graph_x, B->nC);
+    MS_LAUNCH(k_fill_final, cdiv(n, 256), 256, 0, s, dem, (const int *)B->buf[BB_LAB], (const uint32_t *)B->buf[BB_E],
+              filled, depths, n);
+    return MS_OK;
+}
 
 int ms_minmax_f32_dev(const float *dem, int64_t n, float *out_minmax_dev2, void *stream) {
     MS_TRY(ms::ensure_init());

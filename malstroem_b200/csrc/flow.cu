@@ -12,14 +12,16 @@ namespace ms {
 // the first maximum wins; 8 when no neighbour is lower.  Border rule flow.py:118-139 applied in the
 // reference's assignment order (rows, then columns, then corners).
 // ------------------------------------------------------------------------------------------------
+// `open` (row bands): bit 0 / 1 = the first / last row is not the raster border (a halo row lies beyond it).
 __global__ void __launch_bounds__(256) k_flowdir(const double *__restrict__ t, uint8_t *__restrict__ out, int rows,
-                                                 int cols, int edges, double inv_sqrt2) {
+                                                 int cols, int edges, double inv_sqrt2, int open) {
     int c = blockIdx.x * 64 + (threadIdx.x & 63);
     int r = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (r >= rows || c >= cols) return;
     size_t i = (size_t)r * cols + c;
     int code = 8;
-    if (r >= 1 && r <= rows - 2 && c >= 1 && c <= cols - 2) {
+    const bool top_border = (r == 0) && !(open & 1), bot_border = (r == rows - 1) && !(open & 2);
+    if (!top_border && !bot_border && c >= 1 && c <= cols - 2) {
         const double *p = t + i;
         double z = *p, dzmax = 0.0, dz;
         dz = __dsub_rn(z, __ldg(p - cols));                              if (dz > dzmax) { dzmax = dz; code = 0; }
@@ -32,20 +34,21 @@ __global__ void __launch_bounds__(256) k_flowdir(const double *__restrict__ t, u
         dz = __dmul_rn(__dsub_rn(z, __ldg(p - cols - 1)), inv_sqrt2);    if (dz > dzmax) { dzmax = dz; code = 7; }
     }
     if (edges) {
-        int mr = rows - 1, mc = cols - 1;
-        if (r == 0) code = 0;
-        if (r == mr) code = 4;
+        int mc = cols - 1;
+        if (top_border) code = 0;
+        if (bot_border) code = 4;
         if (c == 0) code = 6;
         if (c == mc) code = 2;
-        if (r == 0 && c == 0) code = 7;
-        if (r == 0 && c == mc) code = 1;
-        if (r == mr && c == 0) code = 5;
-        if (r == mr && c == mc) code = 3;
+        if (top_border && c == 0) code = 7;
+        if (top_border && c == mc) code = 1;
+        if (bot_border && c == 0) code = 5;
+        if (bot_border && c == mc) code = 3;
     }
     out[i] = (uint8_t)code;
 }
 
-int flowdir_dev_impl(const double *t, uint8_t *out, int64_t rows, int64_t cols, int edges, cudaStream_t s) {
+int flowdir_dev_impl(const double *t, uint8_t *out, int64_t rows, int64_t cols, int edges, cudaStream_t s,
+                     int open) {
     if (!t || !out) { set_error("terrain_flowdirection: null pointer"); return MS_ERR_ARG; }
     if (rows < 1 || cols < 1 || rows * cols > (1ll << 30)) {
         set_error("terrain_flowdirection: unsupported shape %lld x %lld", (long long)rows, (long long)cols);
@@ -53,7 +56,7 @@ int flowdir_dev_impl(const double *t, uint8_t *out, int64_t rows, int64_t cols, 
     }
     const double inv_sqrt2 = 1.0 / pow(2.0, 0.5);     // _flow.pyx:93-94: SQRT2 = 2**0.5; INV_SQRT2 = 1 / SQRT2
     dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
-    MS_LAUNCH(k_flowdir, g2, 256, 0, s, t, out, (int)rows, (int)cols, edges, inv_sqrt2);
+    MS_LAUNCH(k_flowdir, g2, 256, 0, s, t, out, (int)rows, (int)cols, edges, inv_sqrt2, open);
     return MS_OK;
 }
 
@@ -149,14 +152,134 @@ int watersheds_dev_impl(const uint8_t *fd, void *lab, int label_bytes, int64_t r
     return MS_ERR_ARG;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Row-band watersheds.  Inside the band a path that leaves through an open band edge ends at
+// a "band exit" root.  Phase 1 reports, for every cell of the first / last own row, what its path resolves to: a
+// label, nothing (0), or "whatever band exit (side, col) resolves to"; and where each exit enters the neighbour.
+// The host side chains these across bands (chain_resolve).  Phase 2 writes the labels, taking exit_label[] for
+// cells whose root is an unlabelled band exit.  Only the int32, unassigned-label form with every path ending on
+// the raster border is supported in band mode (the D8 surface of the no-flats fill has no interior sinks).
+// ------------------------------------------------------------------------------------------------
+__device__ inline bool band_exit_side(const uint8_t *fd, int i, int rows, int cols, int open, int *side, int *to) {
+    int r = i / cols, c = i - r * cols;
+    int d = fd[i];
+    if (d > 7) return false;
+    int nr = r + kDR[d], nc = c + kDC[d];
+    if (nc < 0 || nc >= cols) return false;
+    if (nr < 0 && (open & 1)) { *side = 0; *to = nc; return true; }
+    if (nr >= rows && (open & 2)) { *side = 1; *to = nc; return true; }
+    return false;
+}
+
+__global__ void __launch_bounds__(256) k_ws_band_out(const uint8_t *__restrict__ fd, const int32_t *__restrict__ lab,
+                                                     const int *__restrict__ ptr, int32_t unassigned, int rows,
+                                                     int cols, int open, int32_t *edge_res, int32_t *exit_to) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 2 * cols) return;
+    int side = k / cols, c = k - side * cols;
+    int res = 0, to = -1;
+    if (open & (1 << side)) {
+        int i = (side ? rows - 1 : 0) * cols + c;
+        int s2, t2;
+        if (band_exit_side(fd, i, rows, cols, open, &s2, &t2) && s2 == side) to = t2;
+        int root = ptr[i];
+        int32_t v = lab[root];
+        if (v != unassigned) res = v;
+        else if (band_exit_side(fd, root, rows, cols, open, &s2, &t2)) res = -(1 + s2 * cols + (root % cols));
+        else res = 0;
+    }
+    edge_res[k] = res;
+    exit_to[k] = to;
+}
+
+__global__ void __launch_bounds__(256) k_chain_resolve(const int32_t *__restrict__ arr, int32_t *out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t v = arr[i];
+    for (int guard = 0; v < 0 && guard < n; guard++) v = arr[-(v + 1)];
+    out[i] = v < 0 ? 0 : v;
+}
+
+__global__ void __launch_bounds__(256) k_ws_assign_band(const uint8_t *__restrict__ fd, int32_t *lab,
+                                                        const int *__restrict__ ptr, int32_t unassigned, int64_t n,
+                                                        int rows, int cols, int open,
+                                                        const int32_t *__restrict__ exit_label) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (lab[i] != unassigned && ptr[i] == (int)i) return;      // labelled cells are their own roots
+    int root = ptr[i];
+    int32_t v = lab[root];
+    if (v == unassigned) {
+        int s2, t2;
+        if (band_exit_side(fd, root, rows, cols, open, &s2, &t2)) v = exit_label[s2 * cols + (root % cols)];
+        else if (root == (int)i) return;                        // unlabelled terminal: stays as it is
+    }
+    if (root != (int)i || v != unassigned) lab[i] = v;
+}
+
 }  // namespace ms
 
 extern "C" {
 
+int ms_band_ws_local_dev(ms_band *B, const uint8_t *fd, const int32_t *labelled, int32_t unassigned, int32_t *edge_res,
+                         int32_t *exit_to, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !fd || !labelled || !edge_res || !exit_to) { set_error("band watersheds: null pointer"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t rows = B->rows, cols = B->cols, n = rows * cols;
+    int *ptr = (int *)band_buf(B, BB_WS_PTR, (size_t)n * sizeof(int));
+    if (!ptr) return MS_ERR_CUDA;
+    DevBuf<int> flag;
+    MS_TRY(flag.alloc(1, s));
+    MS_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
+    dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
+    MS_LAUNCH(k_ws_ptr<int32_t>, g2, 256, 0, s, fd, labelled, ptr, (int *)nullptr, flag.p, unassigned, (int)rows, (int)cols);
+    int64_t *h = host_flags().h;
+    MS_CUDA(cudaMemcpyAsync(h + 8, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MS_TRY(forest_resolve(ptr, n, nullptr, s));
+    if (*(int *)(h + 8)) {
+        set_error("band watersheds: an interior cell without flow direction (band mode needs every path to end on "
+                  "the raster border)");
+        return MS_ERR_ARG;
+    }
+    MS_LAUNCH(k_ws_band_out, cdiv(2 * cols, 256), 256, 0, s, fd, labelled, (const int *)ptr, unassigned, (int)rows,
+              (int)cols, B->open, edge_res, exit_to);
+    return MS_OK;
+}
+
+/* arr[i] >= 0: final value; arr[i] < 0: same as entry -(arr[i] + 1).  out[i] = the final value the chain ends at */
+int ms_chain_resolve_dev(int64_t n, const int32_t *arr, int32_t *out, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (n < 0 || (n && (!arr || !out))) { set_error("chain_resolve: bad argument"); return MS_ERR_ARG; }
+    if (n) MS_LAUNCH(k_chain_resolve, cdiv(n, 256), 256, 0, (cudaStream_t)stream, arr, out, (int)n);
+    return MS_OK;
+}
+
+int ms_band_ws_finish_dev(ms_band *B, const uint8_t *fd, int32_t *labelled, int32_t unassigned,
+                          const int32_t *exit_label, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !fd || !labelled || !B->buf[BB_WS_PTR] || (B->open && !exit_label)) { set_error("band watersheds: bad argument"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t n = B->rows * B->cols;
+    MS_LAUNCH(k_ws_assign_band, cdiv(n, 256), 256, 0, s, fd, labelled, (const int *)B->buf[BB_WS_PTR], unassigned, n,
+              (int)B->rows, (int)B->cols, B->open, exit_label);
+    return MS_OK;
+}
+
 int ms_flowdir_dev(const double *terrain, uint8_t *flowdir, int64_t rows, int64_t cols, int edges_flow_outward,
                    void *stream) {
     MS_TRY(ms::ensure_init());
-    return ms::flowdir_dev_impl(terrain, flowdir, rows, cols, edges_flow_outward, (cudaStream_t)stream);
+    return ms::flowdir_dev_impl(terrain, flowdir, rows, cols, edges_flow_outward, (cudaStream_t)stream, 0);
+}
+
+int ms_band_flowdir_dev(ms_band *B, const double *terrain, uint8_t *flowdir, int edges_flow_outward, void *stream) {
+    MS_TRY(ms::ensure_init());
+    if (!B) { ms::set_error("band flowdir: null context"); return MS_ERR_ARG; }
+    return ms::flowdir_dev_impl(terrain, flowdir, B->rows, B->cols, edges_flow_outward, (cudaStream_t)stream, B->open);
 }
 
 int ms_flowdir(const double *terrain, uint8_t *flowdir, int64_t rows, int64_t cols, int edges_flow_outward) {
@@ -169,7 +292,7 @@ int ms_flowdir(const double *terrain, uint8_t *flowdir, int64_t rows, int64_t co
     MS_TRY(t.alloc(n, s));
     MS_TRY(o.alloc(n, s));
     MS_CUDA(cudaMemcpyAsync(t.p, terrain, n * sizeof(double), cudaMemcpyHostToDevice, s));
-    MS_TRY(ms::flowdir_dev_impl(t.p, o.p, rows, cols, edges_flow_outward, s));
+    MS_TRY(ms::flowdir_dev_impl(t.p, o.p, rows, cols, edges_flow_outward, s, 0));
     MS_CUDA(cudaMemcpyAsync(flowdir, o.p, n, cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
     return MS_OK;

@@ -117,6 +117,140 @@ int cc_dev_impl(const void *data, int dtype, int32_t *labels, int64_t rows, int6
     return MS_ERR_ARG;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Row-band connected components.  Phase 1: union-find on the band's own rows; the roots
+// of the first / last row go to the host side as global cell indices.  The host merges components that touch
+// across band edges (ms_cc_boundary_merge, CPU, a few thousand cells) — a component keeps the smallest global
+// root.  Phase 2: roots that lost their rank to a root of another band (or of this band, through another band)
+// are taken out of the numbering, every band counts its surviving roots, the counts are scanned across bands
+// (host side) and the labels are written with the band's offset; the few re-rooted components get the label
+// their new root received from its owner.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cc_edge_roots(const int *__restrict__ parent, int64_t cell_offset, int rows,
+                                                       int cols, int64_t *top, int64_t *bot) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    int a = parent[c], b = parent[(size_t)(rows - 1) * cols + c];
+    top[c] = a < 0 ? -1 : cell_offset + a;
+    bot[c] = b < 0 ? -1 : cell_offset + b;
+}
+
+__global__ void __launch_bounds__(256) k_scatter_i32(int *dst, const int32_t *__restrict__ idx,
+                                                     const int32_t *__restrict__ val, int constant, int64_t offset,
+                                                     int n) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) dst[idx[k]] = val ? (int)(val[k] - offset - 1) : constant;
+}
+
+__global__ void __launch_bounds__(256) k_gather_labels(const int *__restrict__ rank, const int32_t *__restrict__ idx,
+                                                       int64_t offset, int32_t *out, int n) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = (int32_t)(rank[idx[k]] + offset + 1);
+}
+
+__global__ void __launch_bounds__(256) k_cc_number_off(const int *__restrict__ parent, const int *__restrict__ rank,
+                                                       int64_t offset, int32_t *__restrict__ labels, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int p = parent[i];
+    labels[i] = p < 0 ? 0 : (int32_t)(rank[p] + offset + 1);
+}
+
+template <typename T>
+int cc_band_local_t(ms_band *B, const T *data, int64_t cell_offset, int64_t *root_top, int64_t *root_bot,
+                    cudaStream_t s) {
+    int64_t rows = B->rows, cols = B->cols, n = rows * cols;
+    int *parent = (int *)band_buf(B, BB_CC_PARENT, (size_t)n * sizeof(int));
+    int *rank = (int *)band_buf(B, BB_CC_RANK, (size_t)n * sizeof(int));
+    if (!parent || !rank) return MS_ERR_CUDA;
+    dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
+    MS_LAUNCH(k_cc_init<T>, g2, 256, 0, s, data, parent, (int)rows, (int)cols);
+    MS_LAUNCH(k_cc_merge, g2, 256, 0, s, parent, (int)rows, (int)cols);
+    MS_LAUNCH(k_cc_flatten, cdiv(n, 256), 256, 0, s, parent, rank, n);
+    MS_LAUNCH(k_cc_edge_roots, cdiv(cols, 256), 256, 0, s, parent, cell_offset, (int)rows, (int)cols, root_top, root_bot);
+    return MS_OK;
+}
+
+}  // namespace ms
+
+extern "C" {
+
+int ms_band_cc_local_dev(ms_band *B, const void *data, int dtype, int64_t cell_offset, int64_t *root_top,
+                         int64_t *root_bot, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !data || !root_top || !root_bot) { set_error("band connected_components: null pointer"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (dtype) {
+        case MS_F32: return cc_band_local_t<float>(B, (const float *)data, cell_offset, root_top, root_bot, s);
+        case MS_F64: return cc_band_local_t<double>(B, (const double *)data, cell_offset, root_top, root_bot, s);
+        case MS_U8: return cc_band_local_t<uint8_t>(B, (const uint8_t *)data, cell_offset, root_top, root_bot, s);
+        case MS_I32: return cc_band_local_t<int32_t>(B, (const int32_t *)data, cell_offset, root_top, root_bot, s);
+        case MS_I64: return cc_band_local_t<int64_t>(B, (const int64_t *)data, cell_offset, root_top, root_bot, s);
+    }
+    set_error("band connected_components: unsupported dtype code %d", dtype);
+    return MS_ERR_ARG;
+}
+
+/* `rerooted` (device, int32 local cell indices, n_rerooted of them): roots of this band that are not the smallest
+ * cell of their (cross-band) component.  Returns the number of components this band numbers. */
+int ms_band_cc_count_dev(ms_band *B, const int32_t *rerooted, int64_t n_rerooted, int64_t *count, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !count || !B->buf[BB_CC_RANK] || (n_rerooted && !rerooted)) { set_error("band connected_components: bad argument"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t n = B->rows * B->cols;
+    int *rank = (int *)B->buf[BB_CC_RANK];
+    if (n_rerooted)
+        MS_LAUNCH(k_scatter_i32, cdiv(n_rerooted, 256), 256, 0, s, rank, rerooted, (const int32_t *)nullptr, 0, (int64_t)0,
+                  (int)n_rerooted);
+    DevBuf<int64_t> tot;
+    MS_TRY(tot.alloc(1, s));
+    MS_TRY(exclusive_scan_i32(rank, rank, n, tot.p, s));
+    int64_t *h = host_flags().h;
+    MS_CUDA(cudaMemcpyAsync(h, tot.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    *count = h[0];
+    return MS_OK;
+}
+
+/* labels (offset + rank + 1) of the given root cells of this band */
+int ms_band_cc_root_labels_dev(ms_band *B, const int32_t *roots, int64_t n_roots, int64_t label_offset,
+                               int32_t *labels_out, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !B->buf[BB_CC_RANK] || (n_roots && (!roots || !labels_out))) { set_error("band connected_components: bad argument"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_roots)
+        MS_LAUNCH(k_gather_labels, cdiv(n_roots, 256), 256, 0, s, (const int *)B->buf[BB_CC_RANK], roots, label_offset,
+                  labels_out, (int)n_roots);
+    return MS_OK;
+}
+
+int ms_band_cc_finish_dev(ms_band *B, const int32_t *rerooted, const int32_t *rerooted_label, int64_t n_rerooted,
+                          int64_t label_offset, int32_t *labels, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !labels || !B->buf[BB_CC_RANK] || (n_rerooted && (!rerooted || !rerooted_label))) {
+        set_error("band connected_components: bad argument");
+        return MS_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t n = B->rows * B->cols;
+    int *rank = (int *)B->buf[BB_CC_RANK];
+    if (n_rerooted)
+        MS_LAUNCH(k_scatter_i32, cdiv(n_rerooted, 256), 256, 0, s, rank, rerooted, rerooted_label, 0, label_offset,
+                  (int)n_rerooted);
+    MS_LAUNCH(k_cc_number_off, cdiv(n, 256), 256, 0, s, (const int *)B->buf[BB_CC_PARENT], (const int *)rank, label_offset,
+              labels, n);
+    return MS_OK;
+}
+
+}  // extern "C"
+
+namespace ms {
+
 // ------------------------------------------------------------------------------------------------
 // label range (the `nlabels = np.max(labelled)` default, label.py:57,116,150)
 // ------------------------------------------------------------------------------------------------
@@ -410,6 +544,84 @@ int label_extreme_dev_impl(const double *data, const int32_t *lab, int64_t rows,
     MS_LAUNCH(k_extreme_finish, gm, 256, 0, s, data, tidx.p, m, (int)cols, want_max, oval, orow, ocol);
     return MS_OK;
 }
+
+
+// Row-band arg-min / arg-max (K8', K8''): phase 1 = the band's extreme value per label (as float64, so the bands'
+// tables combine with an ordinary min / max all-reduce); phase 2 = with the global extreme per label, the
+// smallest GLOBAL flat index among the band's cells that hold it (combined with a min all-reduce).
+__global__ void __launch_bounds__(256) k_key_to_val(const unsigned long long *__restrict__ tkey, double *val, int64_t m,
+                                                    int want_max) {
+    int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= m) return;
+    unsigned long long k = tkey[l];
+    if (want_max) val[l] = (k == 0ull) ? (double)-INFINITY : okey64_inv(k);
+    else val[l] = (k == ~0ull) ? (double)INFINITY : okey64_inv(k);
+}
+
+__global__ void __launch_bounds__(256) k_val_to_key(const double *__restrict__ val, unsigned long long *tkey, int *tidx,
+                                                    int64_t m) {
+    int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= m) return;
+    tkey[l] = okey64(val[l]);
+    tidx[l] = INT32_MAX;
+}
+
+__global__ void __launch_bounds__(256) k_idx_global(const int *__restrict__ tidx, int64_t cell_offset, int64_t *idx,
+                                                    int64_t m) {
+    int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < m) idx[l] = tidx[l] == INT32_MAX ? INT64_MAX : cell_offset + tidx[l];
+}
+
+}  // namespace ms
+
+extern "C" {
+
+int ms_band_extreme_value_dev(const double *data, const int32_t *labels, int64_t n, int64_t nlabels, int want_max,
+                              double *out_value, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!data || !labels || !out_value || n < 1 || nlabels < 0) { set_error("band label_min/max_index: bad argument"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t m = nlabels + 1;
+    DevBuf<unsigned long long> tkey;
+    DevBuf<int> tidx, err;
+    MS_TRY(tkey.alloc((size_t)m, s));
+    MS_TRY(tidx.alloc((size_t)m, s));
+    MS_TRY(err.alloc(1, s));
+    MS_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), s));
+    unsigned gm = cdiv(m, 256);
+    MS_LAUNCH(k_fill_u64, gm, 256, 0, s, tkey.p, want_max ? 0ull : ~0ull, tidx.p, INT32_MAX, m);
+    int64_t want = (n + 255) / 256;
+    int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
+    if (want_max) MS_LAUNCH(k_extreme_key<true>, blocks, 256, 0, s, data, labels, n, nlabels, tkey.p, err.p);
+    else MS_LAUNCH(k_extreme_key<false>, blocks, 256, 0, s, data, labels, n, nlabels, tkey.p, err.p);
+    MS_LAUNCH(k_key_to_val, gm, 256, 0, s, tkey.p, out_value, m, want_max);
+    return MS_OK;
+}
+
+int ms_band_extreme_index_dev(const double *data, const int32_t *labels, int64_t n, int64_t nlabels,
+                              const double *value, int64_t cell_offset, int64_t *out_index, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!data || !labels || !value || !out_index || n < 1 || nlabels < 0) { set_error("band label_min/max_index: bad argument"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t m = nlabels + 1;
+    DevBuf<unsigned long long> tkey;
+    DevBuf<int> tidx;
+    MS_TRY(tkey.alloc((size_t)m, s));
+    MS_TRY(tidx.alloc((size_t)m, s));
+    unsigned gm = cdiv(m, 256);
+    MS_LAUNCH(k_val_to_key, gm, 256, 0, s, value, tkey.p, tidx.p, m);
+    int64_t want = (n + 255) / 256;
+    int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
+    MS_LAUNCH(k_extreme_index, blocks, 256, 0, s, data, labels, n, nlabels, tkey.p, tidx.p);
+    MS_LAUNCH(k_idx_global, gm, 256, 0, s, tidx.p, cell_offset, out_index, m);
+    return MS_OK;
+}
+
+}  // extern "C"
+
+namespace ms {
 
 // ------------------------------------------------------------------------------------------------
 // K10.  label.label_count (label.py:169-180, np.bincount) and K9 label.keep_labels (label.py:78-98)

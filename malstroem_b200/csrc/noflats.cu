@@ -68,14 +68,14 @@ __device__ inline double dmin4(double a, double b, double c, double d) { return 
 __global__ void __launch_bounds__(256) k_nf_init(const float *__restrict__ z, const float *__restrict__ F,
                                                  double *__restrict__ W, const uint8_t *__restrict__ banned,
                                                  int *tileflag, int *tilesides, NfCtl *ctl, int rows, int cols,
-                                                 int tiles_x) {
+                                                 int tiles_x, int open) {
     int c = blockIdx.x * 64 + (threadIdx.x & 63);
     int r = blockIdx.y * 4 + (threadIdx.x >> 6);
     bool nonseed = false;
     if (r < rows && c < cols) {
         int i = r * cols + c;
         float zc = z[i];
-        if (r == 0 || c == 0 || r == rows - 1 || c == cols - 1) {
+        if ((r == 0 && !(open & 1)) || c == 0 || (r == rows - 1 && !(open & 2)) || c == cols - 1) {
             W[i] = (double)zc;
         } else {
             float f = F[i];
@@ -344,14 +344,17 @@ struct NfRowRegs {
 template <bool CAP>
 __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc, double *W, int *ring, int cap,
                                                   int *tileflag, const int *__restrict__ tilesides, NfCtl *ctl, int rows, int cols, int tiles_x,
-                                                  int tiles_y, double sh, double dg, int use_int) {
+                                                  int tiles_y, double sh, double dg, int use_int, double capB_in,
+                                                  int open) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sw = reinterpret_cast<double *>(smem_raw);
     float *sz = reinterpret_cast<float *>(smem_raw + (NF_T + 2) * NF_LD * 8);
     int *sdi = reinterpret_cast<int *>(smem_raw);
     __shared__ NfTileShared S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const double capB = CAP ? ((double)ctl->nonseed + 16.0) * dg * 1.001 : 0.0;
+    const double capB = CAP ? (capB_in >= 0 ? capB_in : ((double)ctl->nonseed + 16.0) * dg * 1.001) : 0.0;
+    // rows the aprons may read: a band that continues above / below has a halo row there
+    const int rlo = (open & 1) ? -1 : 0, rhi = rows + ((open & 2) ? 1 : 0);
     if (*(volatile unsigned *)&ctl->tail == 0) return;      // nothing was queued (tail only grows)
 
     for (;;) {
@@ -407,9 +410,9 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
                     int r = r0 + lr - 1;
                     rg[j].w0 = rg[j].w1 = rg[j].wa = 0.0;
                     rg[j].f0 = rg[j].f1 = rg[j].fa = 0.f;          // w == f: a wall
-                    if (lr < NF_T + 2 && r >= 0 && r < rows) {
-                        const double *wr = W + (size_t)r * cols;
-                        const float *fr = zsrc + (size_t)r * cols;
+                    if (lr < NF_T + 2 && r >= rlo && r < rhi) {
+                        const double *wr = W + (long long)r * cols;
+                        const float *fr = zsrc + (long long)r * cols;
                         int c = c0 + 2 * lane;
                         if (vec) {
                             double2 wv = __ldcg(reinterpret_cast<const double2 *>(wr + c));
@@ -512,7 +515,7 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
                 int lr = q / (NF_T + 2), lc = q - lr * (NF_T + 2);
                 int r = r0 + lr - 1, c = c0 + lc - 1;
                 double v = INFINITY;
-                if (r >= 0 && r < rows && c >= 0 && c < cols) v = __ldcg(W + (size_t)r * cols + c);
+                if (r >= rlo && r < rhi && c >= 0 && c < cols) v = __ldcg(W + (long long)r * cols + c);
                 sw[lr * NF_LD + lc] = v;
             }
             for (int q = tid; q < NF_T * NF_T; q += 256) {
@@ -587,13 +590,15 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
 // best candidate its fixed neighbours offer, unless that lies above F + capB.  A neighbour is fixed iff W == F
 // there (seed: W = z = F; border: W = z = F); lake cells hold +inf or, once written by this kernel, a value > F.
 __global__ void __launch_bounds__(256) k_nf_seedcand(const float *__restrict__ F, double *W, const NfCtl *ctl,
-                                                     int rows, int cols, double sh, double dg) {
+                                                     int rows, int cols, double sh, double dg, double capB_in,
+                                                     int open) {
     int c = blockIdx.x * 64 + (threadIdx.x & 63);
     int r = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (r < 1 || c < 1 || r >= rows - 1 || c >= cols - 1) return;
+    if (r >= rows || c < 1 || c >= cols - 1) return;
+    if ((r == 0 && !(open & 1)) || (r == rows - 1 && !(open & 2))) return;
     size_t i = (size_t)r * cols + c;
     if (__ldcg(W + i) != INFINITY) return;
-    const double capB = ((double)ctl->nonseed + 16.0) * dg * 1.001;
+    const double capB = capB_in >= 0 ? capB_in : ((double)ctl->nonseed + 16.0) * dg * 1.001;
     double best = INFINITY;
 #pragma unroll
     for (int dr = -1; dr <= 1; dr++)
@@ -611,11 +616,11 @@ __global__ void __launch_bounds__(256) k_nf_seedcand(const float *__restrict__ F
 
 __global__ void __launch_bounds__(256) k_nf_verify(const float *__restrict__ z, const double *__restrict__ W,
                                                    uint8_t *banned, NfCtl *ctl, int rows, int cols, double sh,
-                                                   double dg) {
+                                                   double dg, int open) {
     int c = blockIdx.x * 64 + (threadIdx.x & 63);
     int r = blockIdx.y * 4 + (threadIdx.x >> 6);
     int bad = 0;
-    if (r > 0 && c > 0 && r < rows - 1 && c < cols - 1) {
+    if (r < rows && (r > 0 || (open & 1)) && c > 0 && (r < rows - 1 || (open & 2)) && c < cols - 1) {
         size_t i = (size_t)r * cols + c;
         const double *p = W + i;
         double d = dmin2(p[-cols - 1], dmin2(p[-cols + 1], dmin2(p[cols - 1], p[cols + 1])));
@@ -638,7 +643,7 @@ template <bool CAP>
 static int nf_launch_solve(const float *zsrc, double *W, int *ring, int cap, int *tileflag, const int *tilesides,
                            NfCtl *ctl, int rows,
                            int cols, int tiles_x, int tiles_y, int ntiles, double sh, double dg, int use_int,
-                           int64_t units, cudaStream_t s) {
+                           double capB_in, int open, int64_t units, cudaStream_t s) {
     static int grid_blocks = 0;
     if (!grid_blocks) {
         MS_CUDA(cudaFuncSetAttribute(k_nf_solve<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, NF_SMEM));
@@ -652,7 +657,7 @@ static int nf_launch_solve(const float *zsrc, double *W, int *ring, int cap, int
     void *args[] = {(void *)&zsrc, (void *)&W, (void *)&ring, (void *)&cap, (void *)&tileflag, (void *)&tilesides,
                     (void *)&ctl,
                     (void *)&rows, (void *)&cols, (void *)&tiles_x, (void *)&tiles_y, (void *)&sh, (void *)&dg,
-                    (void *)&use_int};
+                    (void *)&use_int, (void *)&capB_in, (void *)&open};
     // consumers wait on the FIFO, so every CTA must be resident: cooperative launch guarantees it (or fails)
     int g = grid_blocks < ntiles ? grid_blocks : ntiles;
     prof_units(units);
@@ -709,17 +714,17 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
         MS_CUDA(cudaMemsetAsync(ring.p, 0xff, (size_t)cap_ring * sizeof(int), s));
         MS_CUDA(cudaMemsetAsync(ctl.p, 0, sizeof(NfCtl), s));
         MS_LAUNCH(k_nf_init, g2, 256, 0, s, dtm, filled, out, banned.p, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols,
-                  tiles_x);
+                  tiles_x, 0);
         MS_LAUNCH(k_nf_compact, cdiv(ntiles, 256), 256, 0, s, tileflag.p, ring.p, ctl.p, ntiles);
         if (cap) {
-            MS_LAUNCH(k_nf_seedcand, g2, 256, 0, s, filled, out, ctl.p, (int)rows, (int)cols, sh, dg);
+            MS_LAUNCH(k_nf_seedcand, g2, 256, 0, s, filled, out, ctl.p, (int)rows, (int)cols, sh, dg, -1.0, 0);
             MS_TRY(nf_launch_solve<true>(filled, out, ring.p, cap_ring, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols, tiles_x,
-                                         tiles_y, ntiles, sh, dg, g_nf_use_int, n, s));
+                                         tiles_y, ntiles, sh, dg, g_nf_use_int, -1.0, 0, n, s));
         } else {
             MS_TRY(nf_launch_solve<false>(dtm, out, ring.p, cap_ring, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols, tiles_x,
-                                          tiles_y, ntiles, sh, dg, 0, n, s));
+                                          tiles_y, ntiles, sh, dg, 0, -1.0, 0, n, s));
         }
-        MS_LAUNCH(k_nf_verify, g2, 256, 0, s, dtm, out, banned.p, ctl.p, (int)rows, (int)cols, sh, dg);
+        MS_LAUNCH(k_nf_verify, g2, 256, 0, s, dtm, out, banned.p, ctl.p, (int)rows, (int)cols, sh, dg, 0);
         MS_CUDA(cudaMemcpyAsync(h, ctl.p, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
         MS_TRY(ms::stream_sync(s));
         visits += h->visits;
@@ -736,7 +741,7 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
             // first failure: allocate the ban map and mark the failing seeds
             MS_TRY(banned.alloc((size_t)n, s));
             MS_CUDA(cudaMemsetAsync(banned.p, 0, (size_t)n, s));
-            MS_LAUNCH(k_nf_verify, g2, 256, 0, s, dtm, out, banned.p, ctl.p, (int)rows, (int)cols, sh, dg);
+            MS_LAUNCH(k_nf_verify, g2, 256, 0, s, dtm, out, banned.p, ctl.p, (int)rows, (int)cols, sh, dg, 0);
         }
         if (tries > 1000) {
             set_error("fill_terrain_no_flats: seed verification did not settle");
@@ -747,9 +752,126 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
     return MS_OK;
 }
 
+
+// =====================================================================================================
+// Row-band no-flats fill.  The band solves its own rows with the halo rows as fixed data;
+// the host side exchanges the first / last own row with the neighbours and calls the solver again on the tiles
+// along a band edge whose halo changed, until no band changes any more; the verification stencil (with halos)
+// certifies the result as in the single-GPU case.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_nf_activate_edges(int *tileflag, const int *__restrict__ tilesides,
+                                                           int tiles_x, int tiles_y, int which) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= tiles_x) return;
+    if ((which & 1) && (tilesides[x] & 1)) atomicOr(tileflag + x, 1);
+    int t = (tiles_y - 1) * tiles_x + x;
+    if ((which & 2) && (tilesides[t] & 2)) atomicOr(tileflag + t, 2);
+}
+
+struct NfBandBufs {
+    int *tileflag, *tilesides, *ring;
+    NfCtl *ctl;
+    int tiles_x, tiles_y, ntiles, cap_ring;
+};
+
+static int nf_band_bufs(ms_band *B, NfBandBufs *o) {
+    o->tiles_x = (int)cdiv(B->cols, NF_T);
+    o->tiles_y = (int)cdiv(B->rows, NF_T);
+    o->ntiles = o->tiles_x * o->tiles_y;
+    o->cap_ring = o->ntiles + 64;
+    o->tileflag = (int *)band_buf(B, BB_NF_FLAG, (size_t)o->ntiles * sizeof(int));
+    o->tilesides = (int *)band_buf(B, BB_NF_SIDES, (size_t)o->ntiles * sizeof(int));
+    o->ring = (int *)band_buf(B, BB_NF_RING, (size_t)o->cap_ring * sizeof(int));
+    o->ctl = (NfCtl *)band_buf(B, BB_NF_CTL, sizeof(NfCtl));
+    if (!o->tileflag || !o->tilesides || !o->ring || !o->ctl) return MS_ERR_CUDA;
+    return MS_OK;
+}
+
 }  // namespace ms
 
 extern "C" {
+
+int ms_band_nf_init_dev(ms_band *B, const float *dem, const float *filled, double *fnf, int64_t *nonseed,
+                        void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !dem || !filled || !fnf) { set_error("band no-flats: null pointer"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NfBandBufs nb;
+    MS_TRY(nf_band_bufs(B, &nb));
+    MS_CUDA(cudaMemsetAsync(nb.tileflag, 0, (size_t)nb.ntiles * sizeof(int), s));
+    MS_CUDA(cudaMemsetAsync(nb.tilesides, 0, (size_t)nb.ntiles * sizeof(int), s));
+    MS_CUDA(cudaMemsetAsync(nb.ctl, 0, sizeof(NfCtl), s));
+    dim3 g2(cdiv(B->cols, 64), cdiv(B->rows, 4));
+    MS_LAUNCH(k_nf_init, g2, 256, 0, s, dem, filled, fnf, (const uint8_t *)nullptr, nb.tileflag, nb.tilesides, nb.ctl,
+              (int)B->rows, (int)B->cols, nb.tiles_x, B->open);
+    NfCtl *h = (NfCtl *)(host_flags().h + 32);
+    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    if (nonseed) *nonseed = h->nonseed;
+    return MS_OK;
+}
+
+/* mode 0: first solve after ms_band_nf_init_dev (+ halo exchange of fnf); mode 1: solve again after the halo rows
+ * named by `edges` (bit 0 top, bit 1 bottom) changed.  cap = 1: capped fast path (cap_bound = the bound on
+ * solution - plain fill, the same on every band); cap = 0: generic float64 path.  *changed_edges: bit 0 / 1 = the
+ * band's first / last own row may have changed (conservative: any tile of that row wrote something). */
+int ms_band_nf_solve_dev(ms_band *B, const float *dem, const float *filled, double *fnf, double short_eps,
+                         double diag_eps, double cap_bound, int cap, int mode, int edges, int64_t *tile_visits,
+                         void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !dem || !filled || !fnf) { set_error("band no-flats: null pointer"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NfBandBufs nb;
+    MS_TRY(nf_band_bufs(B, &nb));
+    int rows = (int)B->rows, cols = (int)B->cols;
+    dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
+    MS_CUDA(cudaMemsetAsync(nb.ring, 0xff, (size_t)nb.cap_ring * sizeof(int), s));
+    MS_CUDA(cudaMemsetAsync(nb.ctl, 0, sizeof(NfCtl), s));
+    if (mode == 0) {
+        if (cap) MS_LAUNCH(k_nf_seedcand, g2, 256, 0, s, filled, fnf, nb.ctl, rows, cols, short_eps, diag_eps, cap_bound, B->open);
+    } else {
+        MS_LAUNCH(k_nf_activate_edges, cdiv(nb.tiles_x, 256), 256, 0, s, nb.tileflag, nb.tilesides, nb.tiles_x, nb.tiles_y, edges);
+    }
+    MS_LAUNCH(k_nf_compact, cdiv(nb.ntiles, 256), 256, 0, s, nb.tileflag, nb.ring, nb.ctl, nb.ntiles);
+    if (cap)
+        MS_TRY(nf_launch_solve<true>(filled, fnf, nb.ring, nb.cap_ring, nb.tileflag, nb.tilesides, nb.ctl, rows, cols,
+                                     nb.tiles_x, nb.tiles_y, nb.ntiles, short_eps, diag_eps, g_nf_use_int, cap_bound,
+                                     B->open, B->rows * B->cols, s));
+    else
+        MS_TRY(nf_launch_solve<false>(dem, fnf, nb.ring, nb.cap_ring, nb.tileflag, nb.tilesides, nb.ctl, rows, cols,
+                                      nb.tiles_x, nb.tiles_y, nb.ntiles, short_eps, diag_eps, 0, -1.0, B->open,
+                                      B->rows * B->cols, s));
+    NfCtl *h = (NfCtl *)(host_flags().h + 32);
+    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    if (h->done != 1 && h->tail != 0) {
+        set_error("band no-flats: tile solver stopped early (done=%d, pending=%d)", h->done, h->pending);
+        return MS_ERR_NOCONV;
+    }
+    if (tile_visits) *tile_visits = h->visits;
+    return MS_OK;
+}
+
+int ms_band_nf_verify_dev(ms_band *B, const float *dem, const double *fnf, double short_eps, double diag_eps,
+                          int64_t *nviol, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !dem || !fnf || !nviol) { set_error("band no-flats: null pointer"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NfBandBufs nb;
+    MS_TRY(nf_band_bufs(B, &nb));
+    MS_CUDA(cudaMemsetAsync(nb.ctl, 0, sizeof(NfCtl), s));
+    dim3 g2(cdiv(B->cols, 64), cdiv(B->rows, 4));
+    MS_LAUNCH(k_nf_verify, g2, 256, 0, s, dem, fnf, (uint8_t *)nullptr, nb.ctl, (int)B->rows, (int)B->cols, short_eps,
+              diag_eps, B->open);
+    NfCtl *h = (NfCtl *)(host_flags().h + 32);
+    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    *nviol = h->nviol;
+    return MS_OK;
+}
 
 int ms_fill_terrain_no_flats_dev(const float *dtm, const float *filled, double short_eps, double diag_eps,
                                  double *out, int64_t rows, int64_t cols, int64_t *stats, void *stream) {

@@ -11,7 +11,7 @@ namespace ms {
 int minmax_dev(const float *z, int64_t n, float *out2, cudaStream_t s);
 int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, double dg, double *out, int64_t rows,
                            int64_t cols, int64_t *stats, cudaStream_t s);
-int flowdir_dev_impl(const double *t, uint8_t *out, int64_t rows, int64_t cols, int edges, cudaStream_t s);
+int flowdir_dev_impl(const double *t, uint8_t *out, int64_t rows, int64_t cols, int edges, cudaStream_t s, int open);
 int accum_dev_impl(const uint8_t *fd, double *acc, int64_t rows, int64_t cols, cudaStream_t s);
 int watersheds_dev_impl(const uint8_t *fd, void *lab, int label_bytes, int64_t rows, int64_t cols, int64_t unassigned,
                         int64_t *stats, cudaStream_t s);
@@ -52,7 +52,7 @@ extern "C" int ms_pipeline_dev(ms_rasters *io, void *stream) {
     int64_t nfstats[3] = {0, 0, 0};
     MS_TRY(fill_no_flats_dev_impl(io->dem, io->filled, io->short_eps, io->diag_eps, io->fnf, rows, cols, nfstats, s));
     io->stats[2] = nfstats[0]; io->stats[3] = nfstats[1]; io->stats[4] = nfstats[2];
-    MS_TRY(flowdir_dev_impl(io->fnf, io->flowdir, rows, cols, 1, s));
+    MS_TRY(flowdir_dev_impl(io->fnf, io->flowdir, rows, cols, 1, s, 0));
     // dem.py:87-91
     if (io->accum) MS_TRY(accum_dev_impl(io->flowdir, io->accum, rows, cols, s));
     // bluespots.py:158-160
