@@ -7,8 +7,10 @@ One "step" = one pass of the whole raster hot path (malstroem_b200.pipeline.Rast
 ms_pipeline_dev) over one S x S synthetic fractal DEM per GPU (default S = 8192, BASELINE.json configs[1]).
 `value` is timed with the DEM already resident in HBM; `e2e` is the same path through the host-buffer front end
 (RasterPipeline.run_host: pinned host DEM -> H2D -> all stages -> D2H of every raster and table).
-For N > 1 (torchrun, one rank per GPU) every rank owns an independent S x S raster (weak scaling, no data-path
-collective — the row-band exchange of one large DEM is not built yet).
+For N > 1 (torchrun, one rank per GPU) the ranks share ONE (N*S) x S raster split into N row bands of S rows
+(malstroem_b200.bands.BandPipeline over NCCL: halo rows, the fill's boundary graph, the accumulation / watershed
+exit forests, the bluespot boundary merge and the table all-reduces); per-GPU work is fixed, so the
+scaling is weak.  `--independent` instead gives every rank its own S x S raster (no exchange).
 `--impl reference` times the reference's own compiled Cython path (oracle/_ref) on the host, one core, on a
 bounded window of the same DEM.
 """
@@ -32,8 +34,8 @@ BYTES_PER_CELL = 79.0     # compulsory traffic of the eight st
 STAGE_BYTES = {
     "k_descent": 12, "k_forest_jump": 12, "k_rootflag": 12, "k_catchment_ids": 12, "k_minedge": 12,
     "k_fill_final": 12, "k_scan_reduce": 8, "k_scan_final": 8,
-    "k_nf_init": 12, "k_nf_relax": 12, "k_nf_verify": 12,
-    "k_flowdir": 9, "k_acc_indeg": 9, "k_acc_trace": 9,
+    "k_nf_init": 12, "k_nf_seedcand": 12, "k_nf_solve<true>": 12, "k_nf_solve<false>": 12, "k_nf_verify": 12,
+    "k_flowdir": 9, "k_acc_tile<false>": 9, "k_acc_tile<true>": 9, "k_acc_links": 9, "k_acc_node_trace": 9,
     "k_cc_init<T>": 8, "k_cc_merge": 8, "k_cc_flatten": 8, "k_cc_number": 8,
     "k_label_stats<T>": 8, "k_ws_ptr<L>": 9, "k_ws_assign<L>": 9, "k_label_count": 9,
     "k_extreme_key<true>": 12, "k_extreme_key<false>": 12, "k_extreme_index": 12, "k_minmax": 4,
@@ -227,8 +229,15 @@ def run_ours(args):
     lib = _lib.lib()
     S = args.size
     n = S * S
-    pipe = RasterPipeline(S, S, device=local, with_accum=True)
-    # every rank gets its own window of the (unbounded) synthetic terrain: rank r starts at row r*S
+    banded = world > 1 and not args.independent
+    if banded:
+        # one (world*S) x S raster, rank r owns rows [r*S, (r+1)*S)
+        from malstroem_b200 import bands
+        pipe = bands.BandPipeline(world * S, S, bands.DistComm(), device=local)
+        assert pipe.rows == S and pipe.r0 == rank * S
+    else:
+        pipe = RasterPipeline(S, S, device=local, with_accum=True)
+    # the band / the independent raster of rank r is the window of the synthetic terrain that starts at row r*S
     synth_fractal(S, S, seed=1, row0=rank * S, col0=0, device=local, out=pipe.dem)
     torch.cuda.synchronize()
 
@@ -294,7 +303,9 @@ def run_ours(args):
                 "config": {"workload": "synthetic fractal DEM %dx%d float32 per GPU (seed 1, 1 mm quantised): "
                                        "fill+depths, no-flats fill, D8, accum, bluespot labels, stats, watersheds, "
                                        "pour points" % (S, S),
-                           "parallelism": "1 GPU" if world == 1 else "%d independent rasters, one per GPU" % world,
+                           "parallelism": "1 GPU" if world == 1 else (
+                               "%d row bands of %d rows of ONE %dx%d raster, one band per GPU, exchanges over NCCL"
+                               % (world, S, world * S, S) if banded else "%d independent rasters, one per GPU" % world),
                            "l2": "inputs (%.0f MB DEM, %.1f GB working set) exceed the 126 MB L2; no flush" %
                                  (n * 4 / 1e6, n * 37 / 1e9),
                            "nlabels": pipe.nlabels, "stats": pipe.stats},
@@ -339,13 +350,20 @@ def main():
     ap.add_argument("--ref-size", type=int, default=1024, help="window edge per step of --impl reference")
     ap.add_argument("--ref-size-baseline", type=int, default=2048, help="window edge of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--independent", action="store_true", help="N > 1: one independent raster per rank, no exchange")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3
+    # exactly one JSON line on stdout: libraries that write to fd 1 (NCCL's version banner) go to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -95,9 +95,9 @@ class DistComm(object):
 
     def all_gather(self, t):
         t = t.contiguous()
-        out = torch.empty((self.size,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        self.dist.all_gather_into_tensor(out, t, group=self.group)
-        return out
+        out = torch.empty(self.size * t.numel(), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t.view(-1), group=self.group)
+        return out.view((self.size,) + tuple(t.shape))
 
     def all_gather_var(self, t):
         n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
@@ -460,6 +460,37 @@ class BandPipeline(object):
             none = idx == torch.iinfo(torch.int64).max
             self.tables[key + "_row"] = torch.where(none, torch.full_like(idx, -1), idx // cols)
             self.tables[key + "_col"] = torch.where(none, torch.full_like(idx, -1), idx % cols)
+
+
+    # ---- host-buffer front end (bench `e2e`): H2D of the band's DEM rows, the run, D2H of every raster + table
+    def host_buffers(self):
+        if getattr(self, "_host", None) is None:
+            h = {"dem": torch.empty((self.rows, self.cols), dtype=torch.float32).pin_memory()}
+            for name, t in self.out.items():
+                h[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            self._host = h
+        return self._host
+
+    def run_host(self, dem_host=None):
+        h = self.host_buffers()
+        if dem_host is not None:
+            h["dem"].copy_(torch.from_numpy(dem_host) if isinstance(dem_host, np.ndarray) else dem_host)
+        self.dem.copy_(h["dem"], non_blocking=True)
+        self.run()
+        for name, t in self.out.items():
+            h[name].copy_(t, non_blocking=True)
+        tabs = {k: v.cpu() for k, v in self.tables.items()}
+        torch.cuda.current_stream(self.device).synchronize()
+        h["tables"] = tabs
+        return h
+
+    def bytes_h2d(self):
+        return self.rows * self.cols * 4
+
+    def bytes_d2h(self):
+        per_cell = sum(t.element_size() for t in self.out.values())
+        per_label = sum(t.element_size() for t in self.tables.values())
+        return self.rows * self.cols * per_cell + (self.nlabels + 1) * per_label
 
 
 def run_threaded(dem, nbands, device=0):

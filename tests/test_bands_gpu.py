@@ -1,0 +1,79 @@
+"""Row-band decomposition on one GPU, bands as threads of one process: every raster and table of
+the banded run must equal the CPU oracle's result on the WHOLE raster bit for bit (label_stats 'sum' within 1e-6),
+for several band counts, including bands whose lakes, flow paths and bluespots straddle the band edges."""
+import numpy as np
+import pytest
+import torch
+
+from malstroem_b200 import bands, synth
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_all(dem):
+    filled = port.fill_terrain(dem)
+    short, diag = port.minimum_safe_short_and_diag(dem)
+    fnf = port.fill_terrain_no_flats(dem, short, diag)
+    fd = port.terrain_flowdirection(fnf)
+    acc = port.accumulated_flow(fd, fast=True)
+    depths = filled - dem
+    lab, n = port.connected_components(depths)
+    ws = lab.copy()
+    port.watersheds_from_labels(fd, ws, 0)
+    return dict(filled=filled, depths=depths, fnf=fnf, flowdir=fd, accum=acc, labels=lab, wsheds=ws, n=n,
+                stats=port.label_stats(depths, lab, n), count=port.label_count(ws),
+                ppmin=port.label_min_index(fnf, lab, n), ppmax=port.label_max_index(acc, lab, n))
+
+
+def check(pipes, want):
+    for name in ("filled", "depths", "fnf", "flowdir", "accum", "labels", "wsheds"):
+        got = torch.cat([p.out[name] for p in pipes]).cpu().numpy()
+        assert np.array_equal(got, want[name]), name
+    for p in pipes:                                   # every rank holds the same, complete tables
+        assert p.nlabels == want["n"]
+        t = {k: v.cpu().numpy() for k, v in p.tables.items()}
+        for k in ("min", "max", "count"):
+            assert np.array_equal(t["st_" + k], want["stats"][k]), k
+        np.testing.assert_allclose(t["st_sum"], want["stats"]["sum"], rtol=1e-6, atol=1e-300)
+        m = len(want["count"])
+        assert np.array_equal(t["ws_count"][:m], want["count"]) and not t["ws_count"][m:].any()
+        for key in ("ppmin", "ppmax"):
+            assert np.array_equal(t[key + "_row"], want[key]["row"]), key
+            assert np.array_equal(t[key + "_col"], want[key]["col"]), key
+            assert np.array_equal(t[key + "_value"], want[key]["value"]), key
+
+
+@pytest.mark.parametrize("shape,nbands,seed", [((320, 256), 2, 11), ((448, 200), 3, 12), ((512, 384), 4, 13),
+                                               ((200, 330), 2, 14), ((640, 129), 5, 15)])
+def test_bands_equal_oracle(shape, nbands, seed):
+    dem = synth.fractal_dem(shape[0], shape[1], seed=seed)
+    want = oracle_all(dem)
+    pipes = bands.run_threaded(torch.from_numpy(dem).cuda(), nbands)
+    try:
+        check(pipes, want)
+    finally:
+        for p in pipes:
+            p.close()
+
+
+def test_bands_lake_across_every_edge():
+    """One basin spanning all bands (a bowl with a rim and a single outlet), plus a flat plateau: the spill graph,
+    the no-flats wave, the accumulation forest and one bluespot all cross every band edge."""
+    rows, cols = 384, 192
+    y, x = np.mgrid[0:rows, 0:cols].astype(np.float64)
+    bowl = ((y - rows / 2) / rows) ** 2 + ((x - cols / 2) / cols) ** 2
+    dem = (50.0 + 40.0 * bowl).astype(np.float32)
+    dem[:, :3] = dem[:, -3:] = 80.0
+    dem[:3, :] = dem[-3:, :] = 80.0
+    dem[rows // 3, :40] = 55.0                      # the outlet channel through the rim
+    dem[200:260, 100:150] = np.float32(52.0)        # a plateau inside the lake area (exact flat)
+    dem = (np.round(dem * 1000) / 1000).astype(np.float32)
+    want = oracle_all(dem)
+    for nb in (2, 3, 6):
+        pipes = bands.run_threaded(torch.from_numpy(dem).cuda(), nb)
+        try:
+            check(pipes, want)
+        finally:
+            for p in pipes:
+                p.close()
