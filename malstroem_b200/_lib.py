@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmalstroem_b200.so")
+LIB_PATH = os.environ.get("MS_LIB") or os.path.join(_HERE, "libmalstroem_b200.so")
 
 MS_F32, MS_F64, MS_U8, MS_I32, MS_I64 = 0, 1, 2, 3, 4
 DTYPE_CODE = {np.dtype(np.float32): MS_F32, np.dtype(np.float64): MS_F64, np.dtype(np.uint8): MS_U8,

@@ -23,18 +23,18 @@ namespace ms {
 constexpr unsigned long long KEY_NONE = ~0ull;
 
 // ---- K0 -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_minmax(const float *z, int64_t n, uint32_t *keys) {
+__global__ void __launch_bounds__(256) k_minmax(const float *z, int64_t n, uint32_t *keys, int vec) {
     uint32_t lo = 0xffffffffu, hi = 0u;
     int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
     for (; i < n; i += stride) {
-        if (i + 4 <= n) {
+        if (vec && i + 4 <= n) {
             float4 v = *reinterpret_cast<const float4 *>(z + i);
             uint32_t a = okey32(v.x), b = okey32(v.y), c = okey32(v.z), d = okey32(v.w);
             lo = min(lo, min(min(a, b), min(c, d)));
             hi = max(hi, max(max(a, b), max(c, d)));
         } else {
-            for (int64_t j = i; j < n; j++) {
+            for (int64_t j = i; j < n && j < i + 4; j++) {
                 uint32_t a = okey32(z[j]);
                 lo = min(lo, a);
                 hi = max(hi, a);
@@ -71,7 +71,8 @@ int minmax_dev(const float *z, int64_t n, float *out2, cudaStream_t s) {
     MS_CUDA(cudaMemcpyAsync(keys.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
     int64_t want = (n / 4 + 255) / 256;
     int blocks = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
-    MS_LAUNCH(k_minmax, blocks, 256, 0, s, z, n, keys.p);
+    // 128-bit loads need a 16-byte aligned base (a band's first own row need not be)
+    MS_LAUNCH(k_minmax, blocks, 256, 0, s, z, n, keys.p, (int)(((uintptr_t)z & 15) == 0));
     MS_LAUNCH(k_minmax_finish, 1, 1, 0, s, keys.p, out2);
     return MS_OK;
 }
@@ -128,44 +129,72 @@ __global__ void __launch_bounds__(256) k_boruvka_init(int *comp, uint32_t *E, in
 // sorts it behind every local edge of the same weight; a component whose lowest edge is foreign freezes (k_hook).
 constexpr unsigned FOREIGN_BIT = 0x80000000u;
 
+// LIST = false: one thread per raster cell (round 1).  LIST = true: one thread per entry of list_in.  Either way
+// the cells that still have a neighbour in another component are appended to list_out: a cell inside its component
+// never has an outgoing edge again, and components grow every round, so the later rounds touch ever fewer cells
+// (8192^2 fractal: 67 M -> 41 M -> 27 M -> ... instead of 67 M every round).
+template <bool LIST>
 __global__ void __launch_bounds__(256) k_minedge(const float *__restrict__ z, const int *__restrict__ lab,
                                                  const int *__restrict__ comp, const uint8_t *__restrict__ frozen,
-                                                 unsigned long long *best, int rows, int cols) {
-    int c = blockIdx.x * 64 + (threadIdx.x & 63);
-    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (r >= rows || c >= cols) return;
-    int i = r * cols + c;
-    int l = lab[i];
-    if (l == 0) return;
-    int cc = comp[l];
-    if (cc == 0) return;
-    if (frozen && frozen[cc]) return;
-    float zc = z[i];
-    unsigned long long bk = KEY_NONE;
-    // interior cell (label != 0 implies not on the border): all 8 neighbours are in the raster, or in a halo row
-#pragma unroll
-    for (int dr = -1; dr <= 1; dr++)
-#pragma unroll
-        for (int dc = -1; dc <= 1; dc++) {
-            if (dr == 0 && dc == 0) continue;
-            int j = i + dr * cols + dc;
-            if (r + dr < 0 || r + dr >= rows) {
-                float w = fmaxf(zc, __ldg(z + j));
-                unsigned long long key = ((unsigned long long)okey32(w) << 32) | FOREIGN_BIT | (unsigned)c;
-                bk = key < bk ? key : bk;
-                continue;
-            }
-            int lj = __ldg(lab + j);
-            if (lj == l) continue;
-            if (__ldg(comp + lj) == cc) continue;
-            float w = fmaxf(zc, __ldg(z + j));
-            // symmetric edge id: lower cell index and the direction to the higher one (E, SW, S, SE)
-            int lo = j < i ? j : i;
-            int code = (dr == 0) ? 0 : ((dr * dc == -1) ? 1 : (dc == 0 ? 2 : 3));
-            unsigned long long key = ((unsigned long long)okey32(w) << 32) | (unsigned)(((unsigned)lo << 2) | code);
-            bk = key < bk ? key : bk;
+                                                 unsigned long long *best, int rows, int cols,
+                                                 const int *__restrict__ list_in, int n_in, int *list_out, int *n_out) {
+    int i = -1, r = 0, c = 0;
+    if (LIST) {
+        int k = blockIdx.x * blockDim.x + threadIdx.x;
+        if (k < n_in) {
+            i = list_in[k];
+            r = i / cols;
+            c = i - r * cols;
         }
-    if (bk != KEY_NONE && bk < best[cc]) atomicMin(&best[cc], bk);
+    } else {
+        c = blockIdx.x * 64 + (threadIdx.x & 63);
+        r = blockIdx.y * 4 + (threadIdx.x >> 6);
+        if (r < rows && c < cols) i = r * cols + c;
+    }
+    bool keep = false;
+    if (i >= 0) {
+        int l = lab[i];
+        int cc = l ? comp[l] : 0;
+        if (cc != 0 && !(frozen && frozen[cc])) {
+            float zc = z[i];
+            unsigned long long bk = KEY_NONE;
+            // interior cell (label != 0 implies not on the border): all 8 neighbours are in the raster, or in a halo row
+#pragma unroll
+            for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+                for (int dc = -1; dc <= 1; dc++) {
+                    if (dr == 0 && dc == 0) continue;
+                    int j = i + dr * cols + dc;
+                    if (r + dr < 0 || r + dr >= rows) {
+                        float w = fmaxf(zc, __ldg(z + j));
+                        unsigned long long key = ((unsigned long long)okey32(w) << 32) | FOREIGN_BIT | (unsigned)c;
+                        bk = key < bk ? key : bk;
+                        continue;
+                    }
+                    int lj = __ldg(lab + j);
+                    if (lj == l) continue;
+                    if (__ldg(comp + lj) == cc) continue;
+                    float w = fmaxf(zc, __ldg(z + j));
+                    // symmetric edge id: lower cell index and the direction to the higher one (E, SW, S, SE)
+                    int lo = j < i ? j : i;
+                    int code = (dr == 0) ? 0 : ((dr * dc == -1) ? 1 : (dc == 0 ? 2 : 3));
+                    unsigned long long key = ((unsigned long long)okey32(w) << 32) | (unsigned)(((unsigned)lo << 2) | code);
+                    bk = key < bk ? key : bk;
+                }
+            if (bk != KEY_NONE) {
+                keep = true;
+                if (bk < best[cc]) atomicMin(&best[cc], bk);
+            }
+        }
+    }
+    // warp-aggregated append of the survivors
+    unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+        int lane = threadIdx.x & 31, base = 0;
+        if (lane == 0) base = atomicAdd(n_out, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) list_out[base + __popc(m & ((1u << lane) - 1))] = i;
+    }
 }
 
 __device__ inline int edge_other(int lo, int code, int cols) {
@@ -242,6 +271,65 @@ __global__ void __launch_bounds__(256) k_fill_final(const float *__restrict__ z,
     if (depths) depths[i] = __fsub_rn(w, zc);
 }
 
+// The Boruvka rounds shared by the single-GPU and the row-band fill.  comp / E initialised by k_boruvka_init;
+// `frozen` (row bands only, may be NULL) zeroed.  Returns the number of rounds.
+static int boruvka_rounds(const float *dem, const int *lab, int *comp, uint32_t *E, uint8_t *frozen, int nC,
+                          int64_t rows, int64_t cols, int *rounds_out, const char *what, cudaStream_t s) {
+    int64_t n = rows * cols;
+    DevBuf<int> parent, counters, listA, listB;
+    DevBuf<uint32_t> wk;
+    DevBuf<unsigned long long> best;
+    MS_TRY(parent.alloc(nC, s));
+    MS_TRY(wk.alloc(nC, s));
+    MS_TRY(best.alloc(nC, s));
+    MS_TRY(counters.alloc(2, s));
+    MS_TRY(listA.alloc((size_t)n, s));
+    dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
+    unsigned gc = cdiv(nC, 256);
+    int64_t *h = host_flags().h;
+    MS_CUDA(cudaMemsetAsync(best.p, 0xff, (size_t)nC * sizeof(unsigned long long), s));
+    int rounds = 0;
+    int64_t live = nC - 1;       // live components; each round every one of them merges with another (or freezes)
+    int n_list = 0;
+    int *lin = nullptr, *lout = listA.p;
+    while (live > 0) {
+        MS_CUDA(cudaMemsetAsync(counters.p, 0, 2 * sizeof(int), s));
+        if (rounds == 0) {
+            prof_units(n);
+            MS_LAUNCH(k_minedge<false>, g2, 256, 0, s, dem, lab, (const int *)comp, (const uint8_t *)frozen, best.p,
+                      (int)rows, (int)cols, (const int *)nullptr, 0, lout, counters.p + 1);
+        } else {
+            prof_units(n_list);
+            MS_LAUNCH(k_minedge<true>, cdiv(n_list, 256), 256, 0, s, dem, lab, (const int *)comp, (const uint8_t *)frozen,
+                      best.p, (int)rows, (int)cols, (const int *)lin, n_list, lout, counters.p + 1);
+        }
+        MS_LAUNCH(k_hook, gc, 256, 0, s, best.p, comp, lab, parent.p, wk.p, frozen, nC, (int)cols);
+        MS_LAUNCH(k_boruvka_update, gc, 256, 0, s, comp, E, parent.p, wk.p, (const uint8_t *)frozen, nC, best.p,
+                  counters.p);
+        MS_CUDA(cudaMemcpyAsync(h, counters.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        MS_TRY(ms::stream_sync(s));
+        int64_t now = ((int *)h)[0];
+        n_list = ((int *)h)[1];
+        rounds++;
+        if (now >= live || rounds > 64) {
+            set_error("%s: Boruvka contraction stalled (%lld -> %lld live components, round %d)", what,
+                      (long long)live, (long long)now, rounds);
+            return MS_ERR_NOCONV;
+        }
+        live = now;
+        if (live > 0 && n_list == 0) {
+            set_error("%s: live components without an outgoing edge", what);
+            return MS_ERR_NOCONV;
+        }
+        // the survivors of this round are the next round's work; the second list is sized by the first's count
+        if (rounds == 1 && live > 0) MS_TRY(listB.alloc((size_t)n_list, s));
+        lin = lout;
+        lout = (lout == listA.p) ? listB.p : listA.p;
+    }
+    if (rounds_out) *rounds_out = rounds;
+    return MS_OK;
+}
+
 int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_t rows, int64_t cols,
                           int64_t *stats, cudaStream_t s) {
     if (!dtm || !filled) { set_error("fill_terrain: null pointer"); return MS_ERR_ARG; }
@@ -270,37 +358,13 @@ int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_
     int nC = (int)h[0];
     tmp.release();
 
-    DevBuf<int> comp, parent, remaining;
-    DevBuf<uint32_t> E, wk;
-    DevBuf<unsigned long long> best;
+    DevBuf<int> comp;
+    DevBuf<uint32_t> E;
     MS_TRY(comp.alloc(nC, s));
-    MS_TRY(parent.alloc(nC, s));
     MS_TRY(E.alloc(nC, s));
-    MS_TRY(wk.alloc(nC, s));
-    MS_TRY(best.alloc(nC, s));
-    MS_TRY(remaining.alloc(1, s));
-    unsigned gc = cdiv(nC, 256);
-    MS_LAUNCH(k_boruvka_init, gc, 256, 0, s, comp.p, E.p, nC);
-    MS_CUDA(cudaMemsetAsync(best.p, 0xff, (size_t)nC * sizeof(unsigned long long), s));
+    MS_LAUNCH(k_boruvka_init, cdiv(nC, 256), 256, 0, s, comp.p, E.p, nC);
     int rounds = 0;
-    int64_t live = nC - 1;       // live components; each round every one of them merges with another
-    while (live > 0) {
-        MS_LAUNCH(k_minedge, g2, 256, 0, s, dtm, lab.p, comp.p, (const uint8_t *)nullptr, best.p, (int)rows, (int)cols);
-        MS_LAUNCH(k_hook, gc, 256, 0, s, best.p, comp.p, lab.p, parent.p, wk.p, (uint8_t *)nullptr, nC, (int)cols);
-        MS_CUDA(cudaMemsetAsync(remaining.p, 0, sizeof(int), s));
-        MS_LAUNCH(k_boruvka_update, gc, 256, 0, s, comp.p, E.p, parent.p, wk.p, (const uint8_t *)nullptr, nC, best.p,
-                  remaining.p);
-        MS_CUDA(cudaMemcpyAsync(h, remaining.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-        MS_TRY(ms::stream_sync(s));
-        int64_t now = *(int *)h;
-        rounds++;
-        if (now >= live || rounds > 64) {
-            set_error("fill_terrain: Boruvka contraction stalled (%lld -> %lld live components, round %d)",
-                      (long long)live, (long long)now, rounds);
-            return MS_ERR_NOCONV;
-        }
-        live = now;
-    }
+    MS_TRY(boruvka_rounds(dtm, lab.p, comp.p, E.p, nullptr, nC, rows, cols, &rounds, "fill_terrain", s));
     MS_LAUNCH(k_fill_final, g1, 256, 0, s, dtm, lab.p, E.p, filled, depths, n);
     if (stats) { stats[0] = rounds; stats[1] = nC; stats[5] = jump_rounds; }
     return MS_OK;
@@ -474,36 +538,10 @@ int fill_band_local(ms_band *B, const float *dem, int64_t *n_frozen, cudaStream_
     uint8_t *frozen = (uint8_t *)band_buf(B, BB_FROZEN, (size_t)nC);
     int *frank = (int *)band_buf(B, BB_FRANK, (size_t)nC * sizeof(int));
     if (!comp || !E || !frozen || !frank) return MS_ERR_CUDA;
-    DevBuf<int> parent, remaining;
-    DevBuf<uint32_t> wk;
-    DevBuf<unsigned long long> best;
-    MS_TRY(parent.alloc(nC, s));
-    MS_TRY(wk.alloc(nC, s));
-    MS_TRY(best.alloc(nC, s));
-    MS_TRY(remaining.alloc(1, s));
     unsigned gc = cdiv(nC, 256);
     MS_LAUNCH(k_boruvka_init, gc, 256, 0, s, comp, E, nC);
-    MS_CUDA(cudaMemsetAsync(best.p, 0xff, (size_t)nC * sizeof(unsigned long long), s));
     MS_CUDA(cudaMemsetAsync(frozen, 0, (size_t)nC, s));
-    int rounds = 0;
-    int64_t live = nC - 1;
-    while (live > 0) {
-        MS_LAUNCH(k_minedge, g2, 256, 0, s, dem, lab, comp, (const uint8_t *)frozen, best.p, (int)rows, (int)cols);
-        MS_LAUNCH(k_hook, gc, 256, 0, s, best.p, comp, lab, parent.p, wk.p, frozen, nC, (int)cols);
-        MS_CUDA(cudaMemsetAsync(remaining.p, 0, sizeof(int), s));
-        MS_LAUNCH(k_boruvka_update, gc, 256, 0, s, comp, E, parent.p, wk.p, (const uint8_t *)frozen, nC, best.p,
-                  remaining.p);
-        MS_CUDA(cudaMemcpyAsync(h, remaining.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-        MS_TRY(ms::stream_sync(s));
-        int64_t now = *(int *)h;
-        rounds++;
-        if (now >= live || rounds > 64) {
-            set_error("band fill: Boruvka contraction stalled (%lld -> %lld live components, round %d)",
-                      (long long)live, (long long)now, rounds);
-            return MS_ERR_NOCONV;
-        }
-        live = now;
-    }
+    MS_TRY(boruvka_rounds(dem, lab, comp, E, frozen, nC, rows, cols, nullptr, "band fill", s));
     // dense ranks of the frozen component roots
     MS_LAUNCH(k_frozen_flags, gc, 256, 0, s, comp, frozen, frank, nC);
     MS_TRY(exclusive_scan_i32(frank, frank, nC, total.p, s));

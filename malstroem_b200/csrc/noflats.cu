@@ -46,9 +46,21 @@ constexpr int NF_T = 64;             // tile edge
 constexpr int NF_LD = NF_T + 3;      // shared row stride in doubles (odd: spreads the rows of a block over banks)
 constexpr int NF_SMEM = (NF_T + 2) * NF_LD * 8 + NF_T * NF_T * 4;
 constexpr int NF_BLOCK_ITERS = 64;   // in-block iteration guard (a block that hits it stays dirty)
+// Forwarding a tile's ring to its neighbours before the tile has settled (after iterations 1, 2, 4, ... or after
+// every iteration) was measured at 8192^2: the kernel is throughput-bound for two thirds of its run (every CTA slot
+// busy, profiles/r01_nf_timeline.txt), so the extra visits cost more than the shorter chains save (11.1 ms -> 12.9 /
+// 13.8 ms).  Kept behind these switches, off.
+#ifndef NF_FLUSH_ALWAYS
+#define NF_FLUSH_ALWAYS 0
+#endif
+#ifndef NF_MIDFLUSH
+#define NF_MIDFLUSH 0
+#endif
 
 #ifdef NF_STATS
-__device__ unsigned long long g_nf_dbg[16];   // [0] tile iterations [1] block visits [2] block iterations [3] -, then per round (n, ns)
+__device__ unsigned long long g_nf_dbg[16];
+__device__ unsigned long long g_nf_log[4 * 262144];     // per visit: t_pop, t_loaded, t_end, tile | iters << 32
+__device__ unsigned int g_nf_nlog;   // [0] tile iterations [1] block visits [2] block iterations [3] -, then per round (n, ns)
 __device__ inline unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #endif
 
@@ -236,6 +248,7 @@ struct NfTileShared {
     unsigned long long dirty[3];
     unsigned long long chgmask;
     int ring;          // bit 0/1/2/3: the tile's top / bottom / left / right ring changed
+    int nb;            // neighbour tiles to queue: bit (dy+1)*3 + (dx+1)
     int k;             // ticket
     int flags;         // side bits this tile was queued with
     int e, elo;        // largest / smallest binade exponent of the tile's lake cells (integer form needs e == elo)
@@ -256,8 +269,11 @@ __device__ inline unsigned long long nf_region(int flags) {
 
 // Runs the dirty-block iteration of one tile to quiescence.  On entry S.dirty[0] holds the initial mask,
 // S.dirty[1] = S.dirty[2] = S.chgmask = 0, S.ring = 0, all visible (a __syncthreads() has passed).
-template <class R>
-__device__ inline int nf_tile_iterate(const R &rx, NfTileShared &S) {
+// `flush()` (called by all threads right after a __syncthreads) writes the blocks in S.chgmask back, queues the
+// neighbours that can gain from the changed ring, and clears S.chgmask / S.ring.  It is called at the end (and,
+// with NF_MIDFLUSH, while the tile is still settling).
+template <class R, class F>
+__device__ inline int nf_tile_iterate(const R &rx, NfTileShared &S, F &flush) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int it = 0;
     for (;; it++) {
@@ -295,7 +311,9 @@ __device__ inline int nf_tile_iterate(const R &rx, NfTileShared &S) {
             if (rings) atomicOr(&S.ring, rings);
         }
         __syncthreads();
+        if (NF_MIDFLUSH && S.ring && (NF_FLUSH_ALWAYS || ((it + 1) & it) == 0)) flush();
     }
+    if (S.chgmask) flush();
     return it;
 }
 
@@ -380,6 +398,7 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
                 S.dirty[2] = 0;
                 S.chgmask = 0;
                 S.ring = 0;
+                S.nb = 0;
                 S.e = INT_MIN;
                 S.elo = INT_MAX;
                 S.bad = 0;
@@ -393,9 +412,28 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
         if (t < 0) break;
 #ifdef NF_STATS
         long long tc0 = clock64(), tc1 = 0, tc2 = 0; int nit = 0;
+        unsigned long long tg0 = gtimer(), tg1 = 0;
 #endif
         const int ty = t / tiles_x, tx = t - ty * tiles_x;
         const int r0 = ty * NF_T, c0 = tx * NF_T;
+        // queue the neighbour tiles named by S.nb (tid 0, after the tile's writes were fenced)
+        auto push_neighbours = [&]() {
+            int nbm = S.nb;
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    if (!dy && !dx) continue;
+                    if (!(nbm & (1 << ((dy + 1) * 3 + (dx + 1))))) continue;
+                    int y = ty + dy, x = tx + dx;
+                    if (y < 0 || y >= tiles_y || x < 0 || x >= tiles_x) continue;
+                    int nb = y * tiles_x + x;
+                    // which side of the neighbour looks at us
+                    int bits = (dy < 0 ? 2 : 0) | (dy > 0 ? 1 : 0) | (dx < 0 ? 8 : 0) | (dx > 0 ? 4 : 0);
+                    if (dy && dx) bits = dy < 0 ? 2 : 1;      // a corner: one block of that side is enough
+                    if (!(__ldg(tilesides + nb) & bits)) continue;      // nothing there that could change
+                    // an idle tile (no side bits yet, not running) is queued by whoever sets its first side bit
+                    if (atomicOr(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb);
+                }
+        };
         bool solved = false;
         if (CAP && use_int) {
             // ---- integer form: load tile + apron (all loads of a batch in flight together), convert on the fly
@@ -470,35 +508,74 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
                 if (tid == 0) S.dirty[0] = nf_region(S.flags);
                 __syncthreads();
                 RelaxI32 rx{sdi, (int)sqd, (int)dqd, &S.bad};
+                auto flush = [&]() {
+                    if (S.bad) return;              // the tile will be redone in float64: write nothing
+                    // the blocks that changed: W = F + D * ulp (exact)
+                    unsigned long long mm = S.chgmask;
+                    for (int idx = 0; mm; idx++) {
+                        int b = __ffsll((long long)mm) - 1;
+                        mm &= mm - 1;
+                        if ((idx & 7) != warp) continue;
+                        int lr = (b >> 3) * 8 + (lane >> 2), lc = (b & 7) * 8 + (lane & 3) * 2;
+                        int r = r0 + lr, c = c0 + lc;
+                        const int *p = sdi + (lr + 1) * NF_ILD + (lc + 1);
+                        if (r < rows) {
+#pragma unroll
+                            for (int q = 0; q < 2; q++) {
+                                int d = p[q];
+                                if (c + q < cols && d < D_INF) {
+                                    size_t i = (size_t)r * cols + c + q;
+                                    W[i] = __dadd_rn((double)__ldg(zsrc + i), __dmul_rn((double)d, ulp));
+                                }
+                            }
+                        }
+                    }
+                    // Which neighbours can actually gain from the new ring?  A ring cell with distance d improves an
+                    // adjacent lake cell of the neighbour (held in the apron, possibly stale = too high, which only
+                    // errs towards queueing) iff d + weight is below it.  Waves mostly run one way, so this drops
+                    // the visit that would only bounce back to the tile the wave came from.
+                    int side = tid >> 6, k = tid & 63;          // 0 top, 1 bottom, 2 left, 3 right
+                    if (S.ring & (1 << side)) {
+                        int lr = side == 0 ? 0 : (side == 1 ? NF_T - 1 : k);
+                        int lc = side == 2 ? 0 : (side == 3 ? NF_T - 1 : k);
+                        int d = sdi[(lr + 1) * NF_ILD + (lc + 1)];
+                        int nbm = 0;
+                        if (d < D_INF) {
+#pragma unroll
+                            for (int o = -1; o <= 1; o++) {
+                                // apron cell across this side, offset o along it
+                                int ar = side == 0 ? -1 : (side == 1 ? NF_T : lr + o);
+                                int ac = side == 2 ? -1 : (side == 3 ? NF_T : lc + o);
+                                int da = sdi[(ar + 1) * NF_ILD + (ac + 1)];
+                                int w = (o == 0) ? rx.sq : rx.dq;
+                                if (da <= D_INF && d + w < da) {
+                                    int dy = ar < 0 ? -1 : (ar >= NF_T ? 1 : 0), dx = ac < 0 ? -1 : (ac >= NF_T ? 1 : 0);
+                                    nbm |= 1 << ((dy + 1) * 3 + (dx + 1));
+                                }
+                            }
+                        }
+                        nbm = __reduce_or_sync(0xffffffffu, nbm);
+                        if (lane == 0 && nbm) atomicOr(&S.nb, nbm);
+                    }
+                    __threadfence();
+                    __syncthreads();
+                    if (tid == 0) {
+                        push_neighbours();
+                        S.nb = 0;
+                        S.ring = 0;
+                        S.chgmask = 0;
+                    }
+                    __syncthreads();
+                };
 #ifdef NF_STATS
-                tc1 = clock64();
+                tc1 = clock64(); tg1 = gtimer();
 #endif
-                int its = nf_tile_iterate(rx, S);
+                int its = nf_tile_iterate(rx, S, flush);
 #ifdef NF_STATS
                 nit = its;
 #endif
                 (void)its;
                 solved = !S.bad;                    // a distance left the trusted range: redo the tile in float64
-                // write back the blocks that changed: W = F + D * ulp (exact)
-                unsigned long long mm = solved ? S.chgmask : 0ull;
-                for (int idx = 0; mm; idx++) {
-                    int b = __ffsll((long long)mm) - 1;
-                    mm &= mm - 1;
-                    if ((idx & 7) != warp) continue;
-                    int lr = (b >> 3) * 8 + (lane >> 2), lc = (b & 7) * 8 + (lane & 3) * 2;
-                    int r = r0 + lr, c = c0 + lc;
-                    const int *p = sdi + (lr + 1) * NF_ILD + (lc + 1);
-                    if (r < rows) {
-#pragma unroll
-                        for (int q = 0; q < 2; q++) {
-                            int d = p[q];
-                            if (c + q < cols && d < D_INF) {
-                                size_t i = (size_t)r * cols + c + q;
-                                W[i] = __dadd_rn((double)__ldg(zsrc + i), __dmul_rn((double)d, ulp));
-                            }
-                        }
-                    }
-                }
             }
             if (!solved) __syncthreads();          // everybody is done with the integer tile before it is overwritten
         }
@@ -510,6 +587,7 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
                 S.dirty[2] = 0;
                 S.chgmask = 0;
                 S.ring = 0;
+                S.nb = 0;
             }
             for (int q = tid; q < (NF_T + 2) * (NF_T + 2); q += 256) {
                 int lr = q / (NF_T + 2), lc = q - lr * (NF_T + 2);
@@ -528,25 +606,47 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
             tc1 = clock64();
 #endif
             RelaxF64<CAP> rx{sw, sz, sh, dg, capB};
-            int its = nf_tile_iterate(rx, S);
+            auto flush = [&]() {
+                // the blocks that changed: a warp writes 8 rows of 8 doubles (lane: row l/4, 2 columns)
+                unsigned long long mm = S.chgmask;
+                for (int idx = 0; mm; idx++) {
+                    int b = __ffsll((long long)mm) - 1;
+                    mm &= mm - 1;
+                    if ((idx & 7) != warp) continue;
+                    int lr = (b >> 3) * 8 + (lane >> 2), lc = (b & 7) * 8 + (lane & 3) * 2;
+                    int r = r0 + lr, c = c0 + lc;
+                    const double *p = sw + (lr + 1) * NF_LD + (lc + 1);
+                    if (r < rows) {
+                        if (c < cols) W[(size_t)r * cols + c] = p[0];
+                        if (c + 1 < cols) W[(size_t)r * cols + c + 1] = p[1];
+                    }
+                }
+                __threadfence();
+                __syncthreads();
+                if (tid == 0) {
+                    // every neighbour that sees a changed side (a diagonal one sees the corner cell, which belongs
+                    // to both adjoining sides)
+                    int rg = S.ring, nbm = 0;
+                    for (int dy = -1; dy <= 1; dy++)
+                        for (int dx = -1; dx <= 1; dx++) {
+                            if (!dy && !dx) continue;
+                            bool hit = (dy < 0 && (rg & 1)) || (dy > 0 && (rg & 2)) || (dx < 0 && (rg & 4)) ||
+                                       (dx > 0 && (rg & 8));
+                            if (hit) nbm |= 1 << ((dy + 1) * 3 + (dx + 1));
+                        }
+                    S.nb = nbm;
+                    push_neighbours();
+                    S.nb = 0;
+                    S.ring = 0;
+                    S.chgmask = 0;
+                }
+                __syncthreads();
+            };
+            int its = nf_tile_iterate(rx, S, flush);
 #ifdef NF_STATS
             nit = its;
 #endif
             (void)its;
-            // write back the blocks that changed: a warp writes 8 rows of 8 doubles (lane: row l/4, 2 columns)
-            unsigned long long mm = S.chgmask;
-            for (int idx = 0; mm; idx++) {
-                int b = __ffsll((long long)mm) - 1;
-                mm &= mm - 1;
-                if ((idx & 7) != warp) continue;
-                int lr = (b >> 3) * 8 + (lane >> 2), lc = (b & 7) * 8 + (lane & 3) * 2;
-                int r = r0 + lr, c = c0 + lc;
-                const double *p = sw + (lr + 1) * NF_LD + (lc + 1);
-                if (r < rows) {
-                    if (c < cols) W[(size_t)r * cols + c] = p[0];
-                    if (c + 1 < cols) W[(size_t)r * cols + c + 1] = p[1];
-                }
-            }
         }
 #ifdef NF_STATS
         tc2 = clock64();
@@ -555,29 +655,15 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
             atomicAdd(&g_nf_dbg[2], (unsigned long long)(tc1 ? tc2 - tc1 : 0));
             atomicAdd(&g_nf_dbg[3], (unsigned long long)nit);
             atomicMax(&g_nf_dbg[4], (unsigned long long)(tc1 ? tc2 - tc1 : 0));
+            unsigned k = atomicAdd(&g_nf_nlog, 1u);
+            if (k < 262144u) {
+                g_nf_log[4 * k] = tg0; g_nf_log[4 * k + 1] = tg1; g_nf_log[4 * k + 2] = gtimer();
+                g_nf_log[4 * k + 3] = (unsigned long long)t | ((unsigned long long)nit << 32);
+            }
         }
 #endif
-        __threadfence();
         __syncthreads();
         if (tid == 0) {
-            int ringbits = S.chgmask ? S.ring : 0;
-            bool top = ringbits & 1, bot = ringbits & 2, lef = ringbits & 4, rig = ringbits & 8;
-            for (int dy = -1; dy <= 1; dy++)
-                for (int dx = -1; dx <= 1; dx++) {
-                    if (!dy && !dx) continue;
-                    // a diagonal neighbour only sees our corner cell: it is covered by either adjoining side
-                    bool hit = (dy < 0 && top) || (dy > 0 && bot) || (dx < 0 && lef) || (dx > 0 && rig);
-                    if (!hit) continue;
-                    int y = ty + dy, x = tx + dx;
-                    if (y < 0 || y >= tiles_y || x < 0 || x >= tiles_x) continue;
-                    int nb = y * tiles_x + x;
-                    // which side of the neighbour looks at us
-                    int bits = (dy < 0 ? 2 : 0) | (dy > 0 ? 1 : 0) | (dx < 0 ? 8 : 0) | (dx > 0 ? 4 : 0);
-                    if (dy && dx) bits = dy < 0 ? 2 : 1;      // a corner: one block of that side is enough
-                    if (!(__ldg(tilesides + nb) & bits)) continue;      // nothing there that could change
-                    // an idle tile (no side bits yet, not running) is queued by whoever sets its first side bit
-                    if (atomicOr(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb);
-                }
             // this tile: side bits that arrived while it ran mean it has to run again
             if (atomicAnd(tileflag + t, ~NF_RUNNING) & NF_SIDES) nf_push(ring, cap, ctl, t);
             __threadfence();
@@ -902,6 +988,13 @@ int ms_fill_terrain_no_flats(const float *dtm, double short_eps, double diag_eps
 }
 
 #ifdef NF_STATS
+int ms_nf_log(unsigned long long *out, unsigned *n, int reset) {
+    if (n) cudaMemcpyFromSymbol(n, ms::g_nf_nlog, sizeof(unsigned));
+    if (out) cudaMemcpyFromSymbol(out, ms::g_nf_log, sizeof(unsigned long long) * 4 * 262144);
+    if (reset) { unsigned z = 0; cudaMemcpyToSymbol(ms::g_nf_nlog, &z, sizeof(z)); }
+    return 0;
+}
+
 int ms_nf_debug(unsigned long long *out, int n, int reset) {
     if (out) cudaMemcpyFromSymbol(out, ms::g_nf_dbg, sizeof(unsigned long long) * n);
     if (reset) { static unsigned long long z[16]; cudaMemcpyToSymbol(ms::g_nf_dbg, z, sizeof(z)); }

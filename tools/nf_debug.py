@@ -19,8 +19,11 @@ out = (ctypes.c_ulonglong * 16)()
 dbg = raw.ms_nf_debug
 dbg.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
 import time
+nflog = raw.ms_nf_log
+nflog.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 for rep in range(3):
     dbg(None, 0, 1)
+    nflog(None, None, 1)
     st = (ctypes.c_int64 * 8)()
     torch.cuda.synchronize(); t0 = time.perf_counter()
     rc = L.ms_fill_terrain_no_flats_dev(dem.data_ptr(), filled.data_ptr(), sh, dg, fnf.data_ptr(), S, S, st, sp)
@@ -31,3 +34,12 @@ for rep in range(3):
     v = max(st[1], 1)
     print("wall %.2f ms  visits %d  mean load %d cyc  mean solve %d cyc  mean iters %.2f  max solve %d cyc" %
           ((t1 - t0) * 1e3, st[1], out[1] // v, out[2] // v, out[3] / v, out[4]))
+
+log = np.zeros(4 * 262144, dtype=np.uint64)
+nl = ctypes.c_uint(0)
+nflog(log.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nl), 0)
+k = min(nl.value, 262144)
+log = log[: 4 * k].reshape(k, 4)
+os.makedirs("gpurun_out", exist_ok=True)
+np.save("gpurun_out/nf_log_%d.npy" % S, log)
+print("logged", k, "visits")
