@@ -129,72 +129,95 @@ __global__ void __launch_bounds__(256) k_boruvka_init(int *comp, uint32_t *E, in
 // sorts it behind every local edge of the same weight; a component whose lowest edge is foreign freezes (k_hook).
 constexpr unsigned FOREIGN_BIT = 0x80000000u;
 
-// LIST = false: one thread per raster cell (round 1).  LIST = true: one thread per entry of list_in.  Either way
-// the cells that still have a neighbour in another component are appended to list_out: a cell inside its component
-// never has an outgoing edge again, and components grow every round, so the later rounds touch ever fewer cells
-// (8192^2 fractal: 67 M -> 41 M -> 27 M -> ... instead of 67 M every round).
+constexpr int ME_PER_THREAD = 4;      // cells per thread: one list append (atomic) per 1024 cells
+
+__device__ inline bool minedge_cell(const float *__restrict__ z, const int *__restrict__ lab,
+                                    const int *__restrict__ comp, const uint8_t *__restrict__ frozen,
+                                    unsigned long long *best, int rows, int cols, int i, int r, int c) {
+    int l = lab[i];
+    int cc = l ? comp[l] : 0;
+    if (cc == 0 || (frozen && frozen[cc])) return false;
+    float zc = z[i];
+    unsigned long long bk = KEY_NONE;
+    // interior cell (label != 0 implies not on the border): all 8 neighbours are in the raster, or in a halo row
+#pragma unroll
+    for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+        for (int dc = -1; dc <= 1; dc++) {
+            if (dr == 0 && dc == 0) continue;
+            int j = i + dr * cols + dc;
+            if (r + dr < 0 || r + dr >= rows) {
+                float w = fmaxf(zc, __ldg(z + j));
+                unsigned long long key = ((unsigned long long)okey32(w) << 32) | FOREIGN_BIT | (unsigned)c;
+                bk = key < bk ? key : bk;
+                continue;
+            }
+            int lj = __ldg(lab + j);
+            if (lj == l) continue;
+            if (__ldg(comp + lj) == cc) continue;
+            float w = fmaxf(zc, __ldg(z + j));
+            // symmetric edge id: lower cell index and the direction to the higher one (E, SW, S, SE)
+            int lo = j < i ? j : i;
+            int code = (dr == 0) ? 0 : ((dr * dc == -1) ? 1 : (dc == 0 ? 2 : 3));
+            unsigned long long key = ((unsigned long long)okey32(w) << 32) | (unsigned)(((unsigned)lo << 2) | code);
+            bk = key < bk ? key : bk;
+        }
+    if (bk == KEY_NONE) return false;
+    if (bk < best[cc]) atomicMin(&best[cc], bk);
+    return true;
+}
+
+// LIST = false: a CTA covers 16 rows x 64 columns of the raster (round 1).  LIST = true: 1024 entries of list_in.
+// Either way the cells that still have a neighbour in another component are appended to list_out: a cell inside its
+// component never has an outgoing edge again, and components grow every round, so the later rounds touch ever
+// fewer cells.
 template <bool LIST>
 __global__ void __launch_bounds__(256) k_minedge(const float *__restrict__ z, const int *__restrict__ lab,
                                                  const int *__restrict__ comp, const uint8_t *__restrict__ frozen,
                                                  unsigned long long *best, int rows, int cols,
                                                  const int *__restrict__ list_in, int n_in, int *list_out, int *n_out) {
-    int i = -1, r = 0, c = 0;
-    if (LIST) {
-        int k = blockIdx.x * blockDim.x + threadIdx.x;
-        if (k < n_in) {
-            i = list_in[k];
-            r = i / cols;
-            c = i - r * cols;
-        }
-    } else {
-        c = blockIdx.x * 64 + (threadIdx.x & 63);
-        r = blockIdx.y * 4 + (threadIdx.x >> 6);
-        if (r < rows && c < cols) i = r * cols + c;
-    }
-    bool keep = false;
-    if (i >= 0) {
-        int l = lab[i];
-        int cc = l ? comp[l] : 0;
-        if (cc != 0 && !(frozen && frozen[cc])) {
-            float zc = z[i];
-            unsigned long long bk = KEY_NONE;
-            // interior cell (label != 0 implies not on the border): all 8 neighbours are in the raster, or in a halo row
+    int cell[ME_PER_THREAD];
+    unsigned keepbits = 0;
 #pragma unroll
-            for (int dr = -1; dr <= 1; dr++)
-#pragma unroll
-                for (int dc = -1; dc <= 1; dc++) {
-                    if (dr == 0 && dc == 0) continue;
-                    int j = i + dr * cols + dc;
-                    if (r + dr < 0 || r + dr >= rows) {
-                        float w = fmaxf(zc, __ldg(z + j));
-                        unsigned long long key = ((unsigned long long)okey32(w) << 32) | FOREIGN_BIT | (unsigned)c;
-                        bk = key < bk ? key : bk;
-                        continue;
-                    }
-                    int lj = __ldg(lab + j);
-                    if (lj == l) continue;
-                    if (__ldg(comp + lj) == cc) continue;
-                    float w = fmaxf(zc, __ldg(z + j));
-                    // symmetric edge id: lower cell index and the direction to the higher one (E, SW, S, SE)
-                    int lo = j < i ? j : i;
-                    int code = (dr == 0) ? 0 : ((dr * dc == -1) ? 1 : (dc == 0 ? 2 : 3));
-                    unsigned long long key = ((unsigned long long)okey32(w) << 32) | (unsigned)(((unsigned)lo << 2) | code);
-                    bk = key < bk ? key : bk;
-                }
-            if (bk != KEY_NONE) {
-                keep = true;
-                if (bk < best[cc]) atomicMin(&best[cc], bk);
+    for (int u = 0; u < ME_PER_THREAD; u++) {
+        int i = -1, r = 0, c = 0;
+        if (LIST) {
+            int k = (blockIdx.x * ME_PER_THREAD + u) * 256 + threadIdx.x;
+            if (k < n_in) {
+                i = list_in[k];
+                r = i / cols;
+                c = i - r * cols;
             }
+        } else {
+            c = blockIdx.x * 64 + (threadIdx.x & 63);
+            r = (blockIdx.y * ME_PER_THREAD + u) * 4 + (threadIdx.x >> 6);
+            if (r < rows && c < cols) i = r * cols + c;
         }
+        cell[u] = i;
+        if (i >= 0 && minedge_cell(z, lab, comp, frozen, best, rows, cols, i, r, c)) keepbits |= 1u << u;
     }
-    // warp-aggregated append of the survivors
-    unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (m) {
-        int lane = threadIdx.x & 31, base = 0;
-        if (lane == 0) base = atomicAdd(n_out, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (keep) list_out[base + __popc(m & ((1u << lane) - 1))] = i;
+    // append the survivors: block-wide exclusive scan of the per-thread counts, one atomic per CTA
+    __shared__ int wsum[8];
+    __shared__ int base_s;
+    int cnt = __popc(keepbits), lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
     }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < 8; k++) { int t = wsum[k]; wsum[k] = tot; tot += t; }
+        base_s = tot ? atomicAdd(n_out, tot) : 0;
+    }
+    __syncthreads();
+    int pos = base_s + wsum[w] + inc - cnt;
+#pragma unroll
+    for (int u = 0; u < ME_PER_THREAD; u++)
+        if (keepbits & (1u << u)) list_out[pos++] = cell[u];
 }
 
 __device__ inline int edge_other(int lo, int code, int cols) {
@@ -296,11 +319,12 @@ static int boruvka_rounds(const float *dem, const int *lab, int *comp, uint32_t 
         MS_CUDA(cudaMemsetAsync(counters.p, 0, 2 * sizeof(int), s));
         if (rounds == 0) {
             prof_units(n);
-            MS_LAUNCH(k_minedge<false>, g2, 256, 0, s, dem, lab, (const int *)comp, (const uint8_t *)frozen, best.p,
+            dim3 g2m(cdiv(cols, 64), cdiv(rows, 4 * ME_PER_THREAD));
+            MS_LAUNCH(k_minedge<false>, g2m, 256, 0, s, dem, lab, (const int *)comp, (const uint8_t *)frozen, best.p,
                       (int)rows, (int)cols, (const int *)nullptr, 0, lout, counters.p + 1);
         } else {
             prof_units(n_list);
-            MS_LAUNCH(k_minedge<true>, cdiv(n_list, 256), 256, 0, s, dem, lab, (const int *)comp, (const uint8_t *)frozen,
+            MS_LAUNCH(k_minedge<true>, cdiv(n_list, 256 * ME_PER_THREAD), 256, 0, s, dem, lab, (const int *)comp, (const uint8_t *)frozen,
                       best.p, (int)rows, (int)cols, (const int *)lin, n_list, lout, counters.p + 1);
         }
         MS_LAUNCH(k_hook, gc, 256, 0, s, best.p, comp, lab, parent.p, wk.p, frozen, nC, (int)cols);

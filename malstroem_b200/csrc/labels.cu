@@ -62,6 +62,108 @@ __global__ void __launch_bounds__(256) k_cc_merge(int *parent, int rows, int col
     }
 }
 
+// Tile-local phase: one CTA labels a 64x64 tile in shared memory with the same union-find (row runs pre-linked,
+// atomicMin hooking, smaller index wins), then writes each cell's tile-local root as a GLOBAL cell index.  Only the
+// cells on tile edges are merged through global memory afterwards (k_cc_border): 3 % of the raster instead of all.
+constexpr int CT = 64;
+
+__device__ inline int cc_find_s(const int *p, int x) {
+    int q = p[x];
+    while (q != x) { x = q; q = p[x]; }
+    return x;
+}
+
+__device__ inline void cc_union_s(int *p, int a, int b) {
+    for (;;) {
+        a = cc_find_s(p, a);
+        b = cc_find_s(p, b);
+        if (a == b) return;
+        if (a > b) { int t = a; a = b; b = t; }
+        int old = atomicMin(p + b, a);
+        if (old == b) return;
+        b = old;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_cc_tile(const T *__restrict__ data, int *__restrict__ parent, int rows, int cols,
+                                                 int tiles_x) {
+    __shared__ int sp[CT * CT];
+    int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    int r0 = ty * CT, c0 = tx * CT, tid = threadIdx.x;
+    // a thread owns 16 consecutive cells of one row: runs are linked while loading
+    int lr = tid >> 2, cb = (tid & 3) * 16;
+    int r = r0 + lr;
+    unsigned fg = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        int c = c0 + cb + k;
+        if (r < rows && c < cols && is_fg(data[(size_t)r * cols + c])) fg |= 1u << k;
+    }
+    {
+        int run = -1;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            int idx = lr * CT + cb + k;
+            if (fg & (1u << k)) { if (run < 0) run = idx; sp[idx] = run; }
+            else { sp[idx] = -1; run = -1; }
+        }
+    }
+    __syncthreads();
+    // join the 16-cell segments of a row, then the rows
+    if (cb > 0 && (fg & 1u) && sp[lr * CT + cb - 1] >= 0) cc_union_s(sp, lr * CT + cb, lr * CT + cb - 1);
+    __syncthreads();
+    if (lr > 0) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            if (!(fg & (1u << k))) continue;
+            int lc = cb + k, i = lr * CT + lc, up = i - CT;
+            if (sp[up] >= 0) {
+                // N is foreground: NW and NE (if foreground) are row-linked to N already; only the first cell of a
+                // run, or a cell whose NW is background, adds information
+                if (lc == 0 || sp[i - 1] < 0 || sp[up - 1] < 0) cc_union_s(sp, i, up);
+            } else {
+                if (lc > 0 && sp[up - 1] >= 0) cc_union_s(sp, i, up - 1);
+                if (lc < CT - 1 && sp[up + 1] >= 0) cc_union_s(sp, i, up + 1);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        int c = c0 + cb + k;
+        if (r >= rows || c >= cols) continue;
+        int v = -1;
+        if (fg & (1u << k)) {
+            int root = cc_find_s(sp, lr * CT + cb + k);
+            v = (r0 + (root >> 6)) * cols + c0 + (root & 63);
+        }
+        parent[(size_t)r * cols + c] = v;
+    }
+}
+
+// merges across tile edges: cells of a tile's first row look up (3 neighbours), cells of its first column look left
+__global__ void __launch_bounds__(256) k_cc_border(int *parent, int rows, int cols) {
+    int c = blockIdx.x * 64 + (threadIdx.x & 63);
+    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (r >= rows || c >= cols) return;
+    bool toprow = (r % CT) == 0 && r > 0, leftcol = (c % CT) == 0 && c > 0;
+    if (!toprow && !leftcol) return;
+    int i = r * cols + c;
+    if (parent[i] < 0) return;
+    if (toprow) {
+        int up = i - cols;
+        if (c > 0 && parent[up - 1] >= 0) cc_union(parent, i, up - 1);
+        if (parent[up] >= 0) cc_union(parent, i, up);
+        if (c < cols - 1 && parent[up + 1] >= 0) cc_union(parent, i, up + 1);
+    }
+    if (leftcol) {
+        if (r > 0 && parent[i - cols - 1] >= 0) cc_union(parent, i, i - cols - 1);
+        if (parent[i - 1] >= 0) cc_union(parent, i, i - 1);
+        if (r < rows - 1 && parent[i + cols - 1] >= 0) cc_union(parent, i, i + cols - 1);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_cc_flatten(int *parent, int *flag, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -91,8 +193,10 @@ int cc_dev_t(const T *data, int32_t *labels, int64_t rows, int64_t cols, int64_t
     MS_TRY(flag.alloc((size_t)n, s));
     dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
     unsigned g1 = cdiv(n, 256);
-    MS_LAUNCH(k_cc_init<T>, g2, 256, 0, s, data, parent.p, (int)rows, (int)cols);
-    MS_LAUNCH(k_cc_merge, g2, 256, 0, s, parent.p, (int)rows, (int)cols);
+    int tiles_x = (int)cdiv(cols, CT), tiles_y = (int)cdiv(rows, CT);
+    prof_units(n);
+    MS_LAUNCH(k_cc_tile<T>, tiles_x * tiles_y, 256, 0, s, data, parent.p, (int)rows, (int)cols, tiles_x);
+    MS_LAUNCH(k_cc_border, g2, 256, 0, s, parent.p, (int)rows, (int)cols);
     MS_LAUNCH(k_cc_flatten, g1, 256, 0, s, parent.p, flag.p, n);
     MS_TRY(exclusive_scan_i32(flag.p, flag.p, n, nlabels_dev, s));
     MS_LAUNCH(k_cc_number, g1, 256, 0, s, parent.p, flag.p, labels, n);
@@ -165,8 +269,9 @@ int cc_band_local_t(ms_band *B, const T *data, int64_t cell_offset, int64_t *roo
     int *rank = (int *)band_buf(B, BB_CC_RANK, (size_t)n * sizeof(int));
     if (!parent || !rank) return MS_ERR_CUDA;
     dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
-    MS_LAUNCH(k_cc_init<T>, g2, 256, 0, s, data, parent, (int)rows, (int)cols);
-    MS_LAUNCH(k_cc_merge, g2, 256, 0, s, parent, (int)rows, (int)cols);
+    int tiles_x = (int)cdiv(cols, CT), tiles_y = (int)cdiv(rows, CT);
+    MS_LAUNCH(k_cc_tile<T>, tiles_x * tiles_y, 256, 0, s, data, parent, (int)rows, (int)cols, tiles_x);
+    MS_LAUNCH(k_cc_border, g2, 256, 0, s, parent, (int)rows, (int)cols);
     MS_LAUNCH(k_cc_flatten, cdiv(n, 256), 256, 0, s, parent, rank, n);
     MS_LAUNCH(k_cc_edge_roots, cdiv(cols, 256), 256, 0, s, parent, cell_offset, (int)rows, (int)cols, root_top, root_bot);
     return MS_OK;
