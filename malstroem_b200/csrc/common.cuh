@@ -169,6 +169,50 @@ struct ms_band {
 namespace ms {
 void *band_buf(ms_band *b, int slot, size_t bytes);      // grow-only cudaMalloc'ed buffer of the context
 
+// pointer jumping restricted to the cells in `list` (device, n_list entries): every other cell already points at its
+// root or at a listed cell.  Used after a tile-local compression (k_descent_tile, k_ws_tile).
+int forest_resolve_list(int *ptr, const int *list, int n_list, int64_t *rounds_out, cudaStream_t s);
+
+#ifdef __CUDACC__
+// ---- tile-local pointer compression (64x64 tiles, 256 threads, 16 cells per thread) -----------------------------
+// sp[k] = tile-local parent of cell k (roots point at themselves).  Asynchronous pointer doubling in shared memory:
+// a reader sees the old or the new parent, both are ancestors.
+constexpr int FT = 64;
+__device__ inline void tile_pointer_double(unsigned short *sp) {
+    for (;;) {
+        int changed = 0;
+#pragma unroll 4
+        for (int u = 0; u < 16; u++) {
+            int k = threadIdx.x + 256 * u;
+            unsigned short p = sp[k], pp = sp[p];
+            if (pp != p) { sp[k] = pp; changed = 1; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+}
+
+// block-aggregated append: `cnt` entries of this thread (in order) go to list_out at the returned position
+__device__ inline int block_append_pos(int cnt, int *n_out) {
+    __shared__ int wsum_[8];
+    __shared__ int base_;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) wsum_[w] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < 8; k++) { int t = wsum_[k]; wsum_[k] = tot; tot += t; }
+        base_ = tot ? atomicAdd(n_out, tot) : 0;
+    }
+    __syncthreads();
+    return base_ + wsum_[w] + inc - cnt;
+}
+#endif
+
 // internal device-pointer stage entry points used by the pipeline (pipeline.cu)
 int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_t rows, int64_t cols,
                           int64_t *stats, cudaStream_t s);

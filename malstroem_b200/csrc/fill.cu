@@ -105,6 +105,79 @@ __global__ void __launch_bounds__(256) k_descent(const float *__restrict__ z, in
     ptr[i] = bi;
 }
 
+// Tile form of k_descent + most of the pointer jumping: a CTA holds a 64x64 tile of z (+ apron) in shared memory,
+// finds every cell's pointer, compresses the in-tile paths by pointer doubling, and writes for every cell the
+// GLOBAL index its tile-local root stands for: itself (a local minimum), 0 (raster border = "outside"), or - when
+// the root's lowest neighbour lies in another tile - that neighbour.  Only cells of the last kind still need global
+// pointer jumping; they are appended to `list` (catchments are ~50 cells, so that is a small fraction).
+__global__ void __launch_bounds__(256) k_descent_tile(const float *__restrict__ z, int *__restrict__ ptr, int rows,
+                                                      int cols, int tiles_x, int open, int *list, int *n_list) {
+    __shared__ float sz[(FT + 2) * (FT + 2)];
+    __shared__ unsigned short sp[FT * FT];
+    __shared__ int tgt[FT * FT];          // per tile-local root: >= 0 final global index, < 0: -(1 + cell in another tile)
+    int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    int r0 = ty * FT, c0 = tx * FT, tid = threadIdx.x;
+    for (int k = tid; k < (FT + 2) * (FT + 2); k += 256) {
+        int lr = k / (FT + 2), lc = k - lr * (FT + 2);
+        int r = r0 + lr - 1, c = c0 + lc - 1;
+        sz[k] = (r >= 0 && r < rows && c >= 0 && c < cols) ? z[(size_t)r * cols + c] : INFINITY;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int u = 0; u < 16; u++) {
+        int k = tid + 256 * u;
+        int lr = k >> 6, lc = k & 63;
+        int r = r0 + lr, c = c0 + lc;
+        unsigned short p = (unsigned short)k;
+        int t = 0;
+        if (r < rows && c < cols) {
+            int i = r * cols + c;
+            if ((r == 0 && !(open & 1)) || c == 0 || (r == rows - 1 && !(open & 2)) || c == cols - 1) {
+                t = 0;                                   // raster border: points at "outside" (cell 0)
+            } else {
+                float bz = sz[(lr + 1) * (FT + 2) + lc + 1];
+                int bi = i, bdr = 0, bdc = 0;
+#pragma unroll
+                for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+                    for (int dc = -1; dc <= 1; dc++) {
+                        if (dr == 0 && dc == 0) continue;
+                        if (r + dr < 0 || r + dr >= rows) continue;
+                        int j = i + dr * cols + dc;
+                        float zj = sz[(lr + 1 + dr) * (FT + 2) + lc + 1 + dc];
+                        if (zj < bz || (zj == bz && j < bi)) { bz = zj; bi = j; bdr = dr; bdc = dc; }
+                    }
+                int tr = lr + bdr, tc = lc + bdc;
+                if (bi == i) t = i;                                           // local minimum
+                else if (tr >= 0 && tr < FT && tc >= 0 && tc < FT) p = (unsigned short)(tr * FT + tc);
+                else t = -(1 + bi);                                           // lowest neighbour is in another tile
+            }
+        }
+        sp[k] = p;
+        tgt[k] = t;
+    }
+    __syncthreads();
+    tile_pointer_double(sp);
+    int mine[16], cnt = 0;
+#pragma unroll 4
+    for (int u = 0; u < 16; u++) {
+        int k = tid + 256 * u;
+        int lr = k >> 6, lc = k & 63;
+        int r = r0 + lr, c = c0 + lc;
+        mine[u] = -1;
+        if (r < rows && c < cols) {
+            int t = tgt[sp[k]];
+            int i = r * cols + c;
+            if (t < 0) { t = -(t + 1); mine[u] = i; cnt++; }
+            ptr[i] = t;
+        }
+    }
+    int pos = block_append_pos(cnt, n_list);
+#pragma unroll 4
+    for (int u = 0; u < 16; u++)
+        if (mine[u] >= 0) list[pos++] = mine[u];
+}
+
 __global__ void __launch_bounds__(256) k_rootflag(const int *ptr, int *flag, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flag[i] = (ptr[i] == (int)i) ? 1 : 0;
@@ -294,6 +367,22 @@ __global__ void __launch_bounds__(256) k_fill_final(const float *__restrict__ z,
     if (depths) depths[i] = __fsub_rn(w, zc);
 }
 
+// every cell -> the local minimum ("catchment") it drains to: tile-local compression, then pointer jumping over the
+// cells whose path leaves their tile.  `scratch` (n ints) holds that list.
+static int descent_resolve(const float *dem, int *lab, int *scratch, int64_t rows, int64_t cols, int open,
+                           int64_t *rounds_out, cudaStream_t s) {
+    DevBuf<int> cnt;
+    MS_TRY(cnt.alloc(1, s));
+    MS_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int), s));
+    int tiles_x = (int)cdiv(cols, FT), tiles_y = (int)cdiv(rows, FT);
+    prof_units(rows * cols);
+    MS_LAUNCH(k_descent_tile, tiles_x * tiles_y, 256, 0, s, dem, lab, (int)rows, (int)cols, tiles_x, open, scratch, cnt.p);
+    int64_t *h = host_flags().h;
+    MS_CUDA(cudaMemcpyAsync(h, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    return forest_resolve_list(lab, scratch, *(int *)h, rounds_out, s);
+}
+
 // The Boruvka rounds shared by the single-GPU and the row-band fill.  comp / E initialised by k_boruvka_init;
 // `frozen` (row bands only, may be NULL) zeroed.  Returns the number of rounds.
 static int boruvka_rounds(const float *dem, const int *lab, int *comp, uint32_t *E, uint8_t *frozen, int nC,
@@ -371,9 +460,8 @@ int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_
     unsigned g1 = cdiv(n, 256);
     int64_t *h = host_flags().h;
 
-    MS_LAUNCH(k_descent, g2, 256, 0, s, dtm, lab.p, (int)rows, (int)cols, 0);
     int64_t jump_rounds = 0;
-    MS_TRY(forest_resolve(lab.p, n, &jump_rounds, s));
+    MS_TRY(descent_resolve(dtm, lab.p, tmp.p, rows, cols, 0, &jump_rounds, s));
     MS_LAUNCH(k_rootflag, g1, 256, 0, s, lab.p, tmp.p, n);
     MS_TRY(exclusive_scan_i32(tmp.p, tmp.p, n, total.p, s));
     MS_LAUNCH(k_catchment_ids, g1, 256, 0, s, lab.p, tmp.p, n);
@@ -547,8 +635,7 @@ int fill_band_local(ms_band *B, const float *dem, int64_t *n_frozen, cudaStream_
     dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
     unsigned g1 = cdiv(n, 256);
     int64_t *h = host_flags().h;
-    MS_LAUNCH(k_descent, g2, 256, 0, s, dem, lab, (int)rows, (int)cols, B->open);
-    MS_TRY(forest_resolve(lab, n, nullptr, s));
+    MS_TRY(descent_resolve(dem, lab, tmp.p, rows, cols, B->open, nullptr, s));
     MS_LAUNCH(k_rootflag, g1, 256, 0, s, lab, tmp.p, n);
     MS_TRY(exclusive_scan_i32(tmp.p, tmp.p, n, total.p, s));
     MS_LAUNCH(k_catchment_ids, g1, 256, 0, s, lab, tmp.p, n);

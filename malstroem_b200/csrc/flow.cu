@@ -97,6 +97,79 @@ __global__ void __launch_bounds__(256) k_ws_ptr(const uint8_t *__restrict__ fd, 
     if (interior_nodir && d > 7 && r > 0 && c > 0 && r < rows - 1 && c < cols - 1) *interior_nodir = 1;
 }
 
+// Tile form of k_ws_ptr + most of the pointer jumping (see k_descent_tile): in-tile paths are compressed in shared
+// memory; a cell whose path leaves its tile gets the cell it enters next and goes on `list` for the global jumps.
+template <typename L>
+__global__ void __launch_bounds__(256) k_ws_tile(const uint8_t *__restrict__ fd, const L *__restrict__ lab, int *ptr,
+                                                 int *interior_nodir, L unassigned, int rows, int cols, int tiles_x,
+                                                 int *list, int *n_list) {
+    __shared__ unsigned short sp[FT * FT];
+    __shared__ int tgt[FT * FT];          // per tile-local root: >= 0 final global index, < 0: -(1 + cell in another tile)
+    int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    int r0 = ty * FT, c0 = tx * FT, tid = threadIdx.x;
+#pragma unroll 4
+    for (int u = 0; u < 16; u++) {
+        int k = tid + 256 * u;
+        int lr = k >> 6, lc = k & 63;
+        int r = r0 + lr, c = c0 + lc;
+        unsigned short p = (unsigned short)k;
+        int t = 0;
+        if (r < rows && c < cols) {
+            int i = r * cols + c;
+            t = i;
+            int d = fd[i], nr, nc;
+            if (interior_nodir && d > 7 && r > 0 && c > 0 && r < rows - 1 && c < cols - 1) *interior_nodir = 1;
+            if (lab[i] == unassigned && d8_next(r, c, d, rows, cols, &nr, &nc)) {
+                int tr = nr - r0, tc = nc - c0;
+                if (tr >= 0 && tr < FT && tc >= 0 && tc < FT) p = (unsigned short)(tr * FT + tc);
+                else t = -(1 + nr * cols + nc);
+            }
+        }
+        sp[k] = p;
+        tgt[k] = t;
+    }
+    __syncthreads();
+    tile_pointer_double(sp);
+    int mine[16], cnt = 0;
+#pragma unroll 4
+    for (int u = 0; u < 16; u++) {
+        int k = tid + 256 * u;
+        int lr = k >> 6, lc = k & 63;
+        int r = r0 + lr, c = c0 + lc;
+        mine[u] = -1;
+        if (r < rows && c < cols) {
+            int t = tgt[sp[k]];
+            int i = r * cols + c;
+            if (t < 0) { t = -(t + 1); mine[u] = i; cnt++; }
+            ptr[i] = t;
+        }
+    }
+    int pos = block_append_pos(cnt, n_list);
+#pragma unroll 4
+    for (int u = 0; u < 16; u++)
+        if (mine[u] >= 0) list[pos++] = mine[u];
+}
+
+// ptr[i] = the first labelled / terminal cell on i's path.  `scratch_list`: n ints.
+template <typename L>
+static int ws_resolve(const uint8_t *fd, const L *lab, int *ptr, int *nodir_flag, L unassigned, int64_t rows,
+                      int64_t cols, int64_t *rounds_out, cudaStream_t s) {
+    int64_t n = rows * cols;
+    DevBuf<int> list, cnt;
+    MS_TRY(list.alloc((size_t)n, s));
+    MS_TRY(cnt.alloc(1, s));
+    MS_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int), s));
+    int tiles_x = (int)cdiv(cols, FT), tiles_y = (int)cdiv(rows, FT);
+    prof_units(n);
+    MS_LAUNCH(k_ws_tile<L>, tiles_x * tiles_y, 256, 0, s, fd, lab, ptr, nodir_flag, unassigned, (int)rows, (int)cols,
+              tiles_x, list.p, cnt.p);
+    int64_t *h = host_flags().h;
+    MS_CUDA(cudaMemcpyAsync(h, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (nodir_flag) MS_CUDA(cudaMemcpyAsync(h + 8, nodir_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    return forest_resolve_list(ptr, list.p, *(int *)h, rounds_out, s);
+}
+
 template <typename L>
 __global__ void __launch_bounds__(256) k_ws_assign(L *lab, const int *__restrict__ ptr,
                                                    const int *__restrict__ ptr_full, int64_t n, int rows, int cols) {
@@ -121,11 +194,9 @@ int watersheds_dev_t(const uint8_t *fd, L *lab, int64_t rows, int64_t cols, L un
     MS_TRY(flag.alloc(1, s));
     MS_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
     dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
-    MS_LAUNCH(k_ws_ptr<L>, g2, 256, 0, s, fd, lab, ptr.p, (int *)nullptr, flag.p, unassigned, (int)rows, (int)cols);
     int64_t *h = host_flags().h;
-    MS_CUDA(cudaMemcpyAsync(h + 8, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     int64_t rounds = 0;
-    MS_TRY(forest_resolve(ptr.p, n, &rounds, s));     // synchronises: h[8] is valid afterwards
+    MS_TRY(ws_resolve<L>(fd, lab, ptr.p, flag.p, unassigned, rows, cols, &rounds, s));     // synchronises: h[8] is valid
     bool general = *(int *)(h + 8) != 0;
     if (general) {
         MS_TRY(ptr_full.alloc((size_t)n, s));
@@ -234,11 +305,8 @@ int ms_band_ws_local_dev(ms_band *B, const uint8_t *fd, const int32_t *labelled,
     DevBuf<int> flag;
     MS_TRY(flag.alloc(1, s));
     MS_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
-    dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
-    MS_LAUNCH(k_ws_ptr<int32_t>, g2, 256, 0, s, fd, labelled, ptr, (int *)nullptr, flag.p, unassigned, (int)rows, (int)cols);
     int64_t *h = host_flags().h;
-    MS_CUDA(cudaMemcpyAsync(h + 8, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    MS_TRY(forest_resolve(ptr, n, nullptr, s));
+    MS_TRY(ws_resolve<int32_t>(fd, labelled, ptr, flag.p, unassigned, rows, cols, nullptr, s));
     if (*(int *)(h + 8)) {
         set_error("band watersheds: an interior cell without flow direction (band mode needs every path to end on "
                   "the raster border)");

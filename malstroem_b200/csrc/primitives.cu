@@ -166,6 +166,49 @@ __global__ void __launch_bounds__(256) k_forest_jump(int *ptr, int64_t n, int *c
     if (more) *changed = 1;
 }
 
+__global__ void __launch_bounds__(256) k_forest_jump_list(int *ptr, const int *__restrict__ list, int n, int *changed) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int i = list[k];
+    int p = ptr[i];
+    if (p == i) return;
+    int q = ptr[p];
+    if (q == p) return;
+    bool more = true;
+#pragma unroll 1
+    for (int h = 0; h < JUMP_HOPS; h++) {
+        p = q;
+        q = ptr[p];
+        if (q == p) { more = false; break; }
+    }
+    ptr[i] = q;
+    if (more) *changed = 1;
+}
+
+int forest_resolve_list(int *ptr, const int *list, int n_list, int64_t *rounds_out, cudaStream_t s) {
+    int rounds = 0;
+    if (n_list > 0) {
+        DevBuf<int> flag;
+        MS_TRY(flag.alloc(1, s));
+        int64_t *h = host_flags().h;
+        for (;;) {
+            MS_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
+            prof_units(n_list);
+            MS_LAUNCH(k_forest_jump_list, cdiv(n_list, 256), 256, 0, s, ptr, list, n_list, flag.p);
+            MS_CUDA(cudaMemcpyAsync(h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+            MS_TRY(ms::stream_sync(s));
+            rounds++;
+            if (*(int *)h == 0) break;
+            if (rounds >= 64) {
+                set_error("forest_resolve: no convergence after %d rounds (cyclic pointers)", rounds);
+                return MS_ERR_NOCONV;
+            }
+        }
+    }
+    if (rounds_out) *rounds_out = rounds;
+    return MS_OK;
+}
+
 int forest_resolve(int *ptr, int64_t n, int64_t *rounds_out, cudaStream_t s) {
     DevBuf<int> flag;
     MS_TRY(flag.alloc(1, s));
