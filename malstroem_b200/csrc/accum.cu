@@ -3,17 +3,22 @@
 // flow.accumulated_flow (flow.py:344-364; speedups/_flow.pyx:225-273): accum(c) = 1 + sum of accum over the
 // cells flowing into c = size of c's upstream tree, exact float64 integers.
 //
-//   pass A  k_acc_tile<false>   one CTA per 64x64 tile: D8 codes + 1-cell apron in shared memory, in-tile
-//           downstream index and in-degree per cell, then every in-tile leaf walks downstream with shared-memory
-//           atomics (add the carried count to the next cell, decrement its in-degree, continue only as the last
-//           missing input — the reference's tracer rule run from all leaves at once).  Result: the count each
-//           cell collects from inside its own tile.  For every perimeter cell the tile-local end of its path is
-//           chased; cells that leave the tile ("exits") publish their local count.
+//   pass A  k_acc_tile_a   one CTA per 64x64 tile: D8 codes + 1-cell apron in shared memory, in-tile downstream index
+//           and in-degree per cell, then every in-tile leaf walks downstream — the reference's tracer rule ("stop at a
+//           cell that still waits for another input") run from all leaves at once.  A cell's state is ONE 32-bit word,
+//           count in the low 24 bits (<= 4096 inside a tile) and the number of inputs still missing above them, so a
+//           step is a single native shared-memory atomic: add (carried count - one missing input); whoever takes the
+//           last missing input away reads the complete count from the value the atomic returns and carries it on.
+//           (64-bit shared atomics are CAS loops on sm_100a; the packed word is 3x faster per step.)  Result: the
+//           count each cell collects from inside its own tile (kept as uint16 per cell), and per perimeter cell where
+//           its in-tile path ends; cells that leave the tile ("exits") publish their local count.
 //   links   k_acc_links / k_acc_node_trace: exits form a forest (exit -> entry cell in the next tile -> the exit
 //           that entry's in-tile path ends at).  Same tracer on that forest (~1.5 % of the cells) in global memory
 //           gives every exit its full count.
-//   pass C  k_acc_tile<true>    the tile pass again with the full counts of the neighbouring exits injected at the
-//           entry cells; writes accum.
+//   pass C  k_acc_tile_c   what enters a tile from the neighbouring exits is added along the in-tile paths below the
+//           entry cells (walkers from the <= 252 perimeter cells; the 30-bit inflow is split into two 16-bit halves
+//           accumulated in separate 32-bit words, so plain native atomics cannot overflow), and
+//           accum = local count + that.
 // Codes > 7 and steps off the raster end a path (the reference leaves accumulation over such cells undefined).
 #include "common.cuh"
 
@@ -23,6 +28,8 @@ constexpr int AT = 64;                    // tile edge
 constexpr int AH = AT + 2;                // apron row length
 constexpr unsigned short A_OUT = 0xffffu; // "leaves the tile or ends"
 constexpr int A_SLOTS = 256;              // perimeter slots per tile (252 used)
+constexpr unsigned A_CNT = 0x00ffffffu;   // packed word: count
+constexpr int A_SHIFT = 24;               // packed word: missing inputs
 
 __device__ inline int perim_slot(int lr, int lc) {
     if (lr == 0) return lc;
@@ -37,98 +44,84 @@ __device__ inline void perim_cell(int p, int *lr, int *lc) {
     else { *lr = p - (2 * AT + AT - 2) + 1; *lc = AT - 1; }
 }
 
-struct AccSmem {
-    unsigned long long acc[AT * AT];
-    int indeg[AT * AT];
-    unsigned short dn[AT * AT];
-    unsigned char dir[AH * AH];
-};
+// loads the tile's D8 codes + apron (255 outside the domain) and the in-tile downstream index of every cell
+__device__ inline void acc_load_tile(const uint8_t *__restrict__ fd, int rows, int cols, int r0, int c0, int rlo, int rhi,
+                                     unsigned char *sdir, unsigned short *sdn) {
+    int tid = threadIdx.x;
+    for (int k = tid; k < AH * AH; k += 256) {
+        int lr = k / AH, lc = k - lr * AH;
+        int r = r0 + lr - 1, c = c0 + lc - 1;
+        sdir[k] = (r >= rlo && r < rhi && c >= 0 && c < cols) ? fd[(long long)r * cols + c] : (unsigned char)255;
+    }
+    __syncthreads();
+    for (int k = tid; k < AT * AT; k += 256) {
+        int lr = k >> 6, lc = k & 63;
+        int d = sdir[(lr + 1) * AH + (lc + 1)];
+        unsigned short dn = A_OUT;
+        if (r0 + lr < rows && c0 + lc < cols && d <= 7) {
+            int tr = lr + kDR[d], tc = lc + kDC[d];
+            if (tr >= 0 && tr < AT && tc >= 0 && tc < AT && r0 + tr < rows && c0 + tc < cols)
+                dn = (unsigned short)(tr * AT + tc);
+        }
+        sdn[k] = dn;
+    }
+}
 
 // Row bands: `open` bit 0 / 1 = a halo row of flow directions lies above the first / below the last row; a path
-// stepping into it leaves the band through an "exit" like any other tile exit, and (FINAL) a halo cell flowing
-// into the band brings halo_top / halo_bot[its column] = its full count.
-template <bool FINAL>
-__global__ void __launch_bounds__(256) k_acc_tile(const uint8_t *__restrict__ fd, int rows, int cols, int tiles_x,
-                                                  double *__restrict__ nodeX, int *__restrict__ entry_next,
-                                                  uint8_t *__restrict__ is_exit, double *__restrict__ accum, int open,
-                                                  const double *__restrict__ halo_top,
-                                                  const double *__restrict__ halo_bot) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    AccSmem &S = *reinterpret_cast<AccSmem *>(smem_raw);
+// stepping into it leaves the band through an "exit" like any other tile exit.
+__global__ void __launch_bounds__(256) k_acc_tile_a(const uint8_t *__restrict__ fd, int rows, int cols, int tiles_x,
+                                                    double *__restrict__ nodeX, int *__restrict__ entry_next,
+                                                    uint8_t *__restrict__ is_exit, unsigned short *__restrict__ loc16,
+                                                    int open) {
+    __shared__ unsigned int word[AT * AT];
+    __shared__ unsigned short sdn[AT * AT];
+    __shared__ unsigned char sdir[AH * AH];
     int tile = blockIdx.x;
     int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     int r0 = ty * AT, c0 = tx * AT, tid = threadIdx.x;
     const int rlo = (open & 1) ? -1 : 0, rhi = rows + ((open & 2) ? 1 : 0);
-    for (int k = tid; k < AH * AH; k += 256) {
-        int lr = k / AH, lc = k - lr * AH;
-        int r = r0 + lr - 1, c = c0 + lc - 1;
-        S.dir[k] = (r >= rlo && r < rhi && c >= 0 && c < cols) ? fd[(long long)r * cols + c] : (unsigned char)255;
+    acc_load_tile(fd, rows, cols, r0, c0, rlo, rhi, sdir, sdn);
+    unsigned leaves = 0;                                            // bit u: cell tid + 256 u has no in-tile input
+#pragma unroll 4
+    for (int u = 0; u < 16; u++) {
+        int k = tid + 256 * u;
+        int lr = k >> 6, lc = k & 63;
+        const unsigned char *ctr = sdir + (lr + 1) * AH + (lc + 1);
+        unsigned n = 15;                                            // outside the raster: never a leaf, never reached
+        if (r0 + lr < rows && c0 + lc < cols) {
+            n = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                int nr = lr + kDR[q], nc = lc + kDC[q];
+                if (ctr[kDR[q] * AH + kDC[q]] != ((q + 4) & 7)) continue;      // apron value 255 never matches
+                if (nr >= 0 && nr < AT && nc >= 0 && nc < AT) n++;
+            }
+            if (n == 0) leaves |= 1u << u;
+        }
+        word[k] = 1u | (n << A_SHIFT);
+    }
+    __syncthreads();
+    for (int u = 0; u < 16; u++) {
+        if (!(leaves & (1u << u))) continue;
+        int k = tid + 256 * u;
+        unsigned carried = 1;
+        int cur = k;
+        for (;;) {
+            unsigned short d = sdn[cur];
+            if (d == A_OUT) break;
+            unsigned old = atomicAdd(&word[d], carried - (1u << A_SHIFT));
+            if ((old >> A_SHIFT) != 1u) break;                      // somebody else will bring the last input
+            carried += old & A_CNT;
+            cur = d;
+        }
     }
     __syncthreads();
     for (int k = tid; k < AT * AT; k += 256) {
         int lr = k >> 6, lc = k & 63;
         int r = r0 + lr, c = c0 + lc;
-        const unsigned char *ctr = S.dir + (lr + 1) * AH + (lc + 1);
-        int d = *ctr;
-        unsigned short dn = A_OUT;
-        int n = 0;
-        unsigned long long start = 1;
-        if (r < rows && c < cols) {
-            if (d <= 7) {
-                int tr = lr + kDR[d], tc = lc + kDC[d];
-                if (tr >= 0 && tr < AT && tc >= 0 && tc < AT && r0 + tr < rows && c0 + tc < cols)
-                    dn = (unsigned short)(tr * AT + tc);
-            }
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                int nr = lr + kDR[q], nc = lc + kDC[q];
-                if (ctr[kDR[q] * AH + kDC[q]] != ((q + 4) & 7)) continue;      // apron value 255 never matches
-                if (nr >= 0 && nr < AT && nc >= 0 && nc < AT) {
-                    n++;
-                } else if (FINAL) {
-                    // upstream neighbour in another tile: it is an exit there; add its full count
-                    int gr = r0 + nr, gc = c0 + nc;
-                    if (gr < 0) start += (unsigned long long)halo_top[gc];
-                    else if (gr >= rows) start += (unsigned long long)halo_bot[gc];
-                    else {
-                        int nt = (gr / AT) * tiles_x + (gc / AT);
-                        start += (unsigned long long)nodeX[(size_t)nt * A_SLOTS + perim_slot(gr % AT, gc % AT)];
-                    }
-                }
-            }
-        } else {
-            n = 1 << 20;      // outside the raster: never a leaf, never reached
-        }
-        S.dn[k] = dn;
-        S.indeg[k] = n ? n : -1;
-        S.acc[k] = start;
+        if (r < rows && c < cols) loc16[(size_t)r * cols + c] = (unsigned short)(word[k] & A_CNT);
     }
-    __syncthreads();
-    for (int k = tid; k < AT * AT; k += 256) {
-        if (S.indeg[k] != -1) continue;
-        int cur = k;
-        unsigned long long carried = S.acc[k];
-        for (;;) {
-            unsigned short d = S.dn[cur];
-            if (d == A_OUT) break;
-            atomicAdd(&S.acc[d], carried);
-            __threadfence_block();
-            if (atomicSub(&S.indeg[d], 1) != 1) break;
-            __threadfence_block();
-            carried = *(volatile unsigned long long *)&S.acc[d];
-            cur = d;
-        }
-    }
-    __syncthreads();
-    if (FINAL) {
-        for (int k = tid; k < AT * AT; k += 256) {
-            int lr = k >> 6, lc = k & 63;
-            int r = r0 + lr, c = c0 + lc;
-            if (r < rows && c < cols) accum[(size_t)r * cols + c] = (double)S.acc[k];
-        }
-        return;
-    }
-    // pass A epilogue: per perimeter cell, where its in-tile path ends and (for exits) the local count
+    // per perimeter cell, where its in-tile path ends and (for exits) the local count
     if (tid >= 4 * AT - 4) {          // the four unused slots of the tile
         entry_next[(size_t)tile * A_SLOTS + tid] = -1;
         is_exit[(size_t)tile * A_SLOTS + tid] = 0;
@@ -141,26 +134,90 @@ __global__ void __launch_bounds__(256) k_acc_tile(const uint8_t *__restrict__ fd
         uint8_t ex = 0;
         if (r < rows && c < cols) {
             int cur = lr * AT + lc;
-            for (int guard = 0; guard < AT * AT && S.dn[cur] != A_OUT; guard++) cur = S.dn[cur];
-            // does the end cell step into another in-raster tile?
+            for (int guard = 0; guard < AT * AT && sdn[cur] != A_OUT; guard++) cur = sdn[cur];
+            // does the end cell step into another tile of the domain?
             int er = cur >> 6, ec = cur & 63;
-            int d = S.dir[(er + 1) * AH + (ec + 1)];
-            if (d <= 7 && S.dn[cur] == A_OUT) {
+            int d = sdir[(er + 1) * AH + (ec + 1)];
+            if (d <= 7 && sdn[cur] == A_OUT) {
                 int gr = r0 + er + kDR[d], gc = c0 + ec + kDC[d];
                 if (gr >= rlo && gr < rhi && gc >= 0 && gc < cols) nxt = tile * A_SLOTS + perim_slot(er, ec);
             }
             // is this perimeter cell itself an exit?
-            int d0 = S.dir[(lr + 1) * AH + (lc + 1)];
-            if (d0 <= 7 && S.dn[lr * AT + lc] == A_OUT) {
+            int d0 = sdir[(lr + 1) * AH + (lc + 1)];
+            if (d0 <= 7 && sdn[lr * AT + lc] == A_OUT) {
                 int gr = r + kDR[d0], gc = c + kDC[d0];
                 if (gr >= rlo && gr < rhi && gc >= 0 && gc < cols) {
                     ex = 1;
-                    nodeX[slot] = (double)S.acc[lr * AT + lc];
+                    nodeX[slot] = (double)(word[lr * AT + lc] & A_CNT);
                 }
             }
         }
         entry_next[slot] = nxt;
         is_exit[slot] = ex;
+    }
+}
+
+// (FINAL) halo_top / halo_bot[column] = full count of the neighbouring band's edge-row cell, used where that cell
+// flows into this band.
+__global__ void __launch_bounds__(256) k_acc_tile_c(const uint8_t *__restrict__ fd, int rows, int cols, int tiles_x,
+                                                    const double *__restrict__ nodeX,
+                                                    const unsigned short *__restrict__ loc16,
+                                                    double *__restrict__ accum, int open,
+                                                    const double *__restrict__ halo_top,
+                                                    const double *__restrict__ halo_bot) {
+    __shared__ unsigned int lo[AT * AT], hi[AT * AT];
+    __shared__ unsigned short sdn[AT * AT];
+    __shared__ unsigned char sdir[AH * AH];
+    int tile = blockIdx.x;
+    int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    int r0 = ty * AT, c0 = tx * AT, tid = threadIdx.x;
+    const int rlo = (open & 1) ? -1 : 0, rhi = rows + ((open & 2) ? 1 : 0);
+    for (int k = tid; k < AT * AT; k += 256) { lo[k] = 0; hi[k] = 0; }
+    acc_load_tile(fd, rows, cols, r0, c0, rlo, rhi, sdir, sdn);
+    __syncthreads();
+    if (tid < 4 * AT - 4) {
+        int lr, lc;
+        perim_cell(tid, &lr, &lc);
+        int r = r0 + lr, c = c0 + lc;
+        if (r < rows && c < cols) {
+            // what the exits of the neighbouring tiles (or of the neighbouring band) bring into this cell
+            const unsigned char *ctr = sdir + (lr + 1) * AH + (lc + 1);
+            unsigned long long inflow = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                int nr = lr + kDR[q], nc = lc + kDC[q];
+                if (nr >= 0 && nr < AT && nc >= 0 && nc < AT) continue;
+                if (ctr[kDR[q] * AH + kDC[q]] != ((q + 4) & 7)) continue;      // apron value 255 never matches
+                int gr = r0 + nr, gc = c0 + nc;
+                if (gr < 0) inflow += (unsigned long long)halo_top[gc];
+                else if (gr >= rows) inflow += (unsigned long long)halo_bot[gc];
+                else {
+                    int nt = (gr / AT) * tiles_x + (gc / AT);
+                    inflow += (unsigned long long)nodeX[(size_t)nt * A_SLOTS + perim_slot(gr % AT, gc % AT)];
+                }
+            }
+            if (inflow) {
+                unsigned a = (unsigned)(inflow & 0xffffu), b = (unsigned)(inflow >> 16);
+                int cur = lr * AT + lc;
+                for (int guard = 0; guard < AT * AT; guard++) {
+                    atomicAdd(&lo[cur], a);
+                    if (b) atomicAdd(&hi[cur], b);
+                    unsigned short d = sdn[cur];
+                    if (d == A_OUT) break;
+                    cur = d;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < AT * AT; k += 256) {
+        int lr = k >> 6, lc = k & 63;
+        int r = r0 + lr, c = c0 + lc;
+        if (r < rows && c < cols) {
+            size_t i = (size_t)r * cols + c;
+            unsigned long long v = (unsigned long long)loc16[i] + lo[k] + ((unsigned long long)hi[k] << 16);
+            accum[i] = (double)v;
+        }
     }
 }
 
@@ -214,12 +271,6 @@ int accum_dev_impl(const uint8_t *fd, double *acc, int64_t rows, int64_t cols, c
         set_error("accumulated_flow: unsupported shape %lld x %lld", (long long)rows, (long long)cols);
         return MS_ERR_SHAPE;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        MS_CUDA(cudaFuncSetAttribute(k_acc_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccSmem)));
-        MS_CUDA(cudaFuncSetAttribute(k_acc_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccSmem)));
-        attr_done = true;
-    }
     int tiles_x = (int)cdiv(cols, AT), tiles_y = (int)cdiv(rows, AT);
     int ntiles = tiles_x * tiles_y;
     int64_t nslots64 = (int64_t)ntiles * A_SLOTS;
@@ -227,26 +278,27 @@ int accum_dev_impl(const uint8_t *fd, double *acc, int64_t rows, int64_t cols, c
     DevBuf<double> X;
     DevBuf<int> entry_next, next, indeg, indeg0;
     DevBuf<uint8_t> is_exit;
+    DevBuf<unsigned short> loc16;
     MS_TRY(X.alloc((size_t)nslots, s));
     MS_TRY(entry_next.alloc((size_t)nslots, s));
     MS_TRY(next.alloc((size_t)nslots, s));
     MS_TRY(indeg.alloc((size_t)nslots, s));
     MS_TRY(indeg0.alloc((size_t)nslots, s));
     MS_TRY(is_exit.alloc((size_t)nslots, s));
+    MS_TRY(loc16.alloc((size_t)(rows * cols), s));
     MS_CUDA(cudaMemsetAsync(indeg.p, 0, (size_t)nslots * sizeof(int), s));
+    MS_CUDA(cudaMemsetAsync(X.p, 0, (size_t)nslots * sizeof(double), s));
     prof_units(rows * cols);
-    MS_LAUNCH(k_acc_tile<false>, ntiles, 256, sizeof(AccSmem), s, fd, (int)rows, (int)cols, tiles_x, X.p, entry_next.p,
-              is_exit.p, (double *)nullptr, 0, (const double *)nullptr, (const double *)nullptr);
+    MS_LAUNCH(k_acc_tile_a, ntiles, 256, 0, s, fd, (int)rows, (int)cols, tiles_x, X.p, entry_next.p, is_exit.p, loc16.p, 0);
     MS_LAUNCH(k_acc_links, cdiv(nslots, 256), 256, 0, s, fd, is_exit.p, entry_next.p, next.p, indeg.p, (int)rows,
               (int)cols, tiles_x, nslots);
     MS_CUDA(cudaMemcpyAsync(indeg0.p, indeg.p, (size_t)nslots * sizeof(int), cudaMemcpyDeviceToDevice, s));
     MS_LAUNCH(k_acc_node_trace, cdiv(nslots, 256), 256, 0, s, is_exit.p, next.p, indeg0.p, indeg.p, X.p, nslots);
     prof_units(rows * cols);
-    MS_LAUNCH(k_acc_tile<true>, ntiles, 256, sizeof(AccSmem), s, fd, (int)rows, (int)cols, tiles_x, X.p, entry_next.p,
-              is_exit.p, acc, 0, (const double *)nullptr, (const double *)nullptr);
+    MS_LAUNCH(k_acc_tile_c, ntiles, 256, 0, s, fd, (int)rows, (int)cols, tiles_x, (const double *)X.p,
+              (const unsigned short *)loc16.p, acc, 0, (const double *)nullptr, (const double *)nullptr);
     return MS_OK;
 }
-
 
 // =====================================================================================================
 // Row-band accumulation.  Phase 1 (accum_band_local): the tile pass and the band's own link
@@ -347,20 +399,11 @@ static int acc_band_bufs(ms_band *B, int *ntiles_out, int *nslots_out) {
     if (!band_buf(B, BB_ACC_X, (size_t)nslots * 8) || !band_buf(B, BB_ACC_X0, (size_t)nslots * 8) ||
         !band_buf(B, BB_ACC_ENTRY_NEXT, (size_t)nslots * 4) || !band_buf(B, BB_ACC_NEXT, (size_t)nslots * 4) ||
         !band_buf(B, BB_ACC_INDEG, (size_t)nslots * 4) || !band_buf(B, BB_ACC_INDEG0, (size_t)nslots * 4) ||
-        !band_buf(B, BB_ACC_ISEXIT, (size_t)nslots))
+        !band_buf(B, BB_ACC_ISEXIT, (size_t)nslots) || !band_buf(B, BB_ACC_LOC16, (size_t)(B->rows * B->cols) * 2))
         return MS_ERR_CUDA;
     return MS_OK;
 }
 
-static int acc_attr() {
-    static bool attr_done = false;
-    if (!attr_done) {
-        MS_CUDA(cudaFuncSetAttribute(k_acc_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccSmem)));
-        MS_CUDA(cudaFuncSetAttribute(k_acc_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccSmem)));
-        attr_done = true;
-    }
-    return MS_OK;
-}
 
 }  // namespace ms
 
@@ -372,7 +415,6 @@ int ms_band_accum_local_dev(ms_band *B, const uint8_t *fd, int32_t *exit_to, dou
     MS_TRY(ensure_init());
     if (!B || !fd || !exit_to || !exit_val || !entry_root) { set_error("band accumulation: null pointer"); return MS_ERR_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
-    MS_TRY(acc_attr());
     int ntiles, nslots;
     MS_TRY(acc_band_bufs(B, &ntiles, &nslots));
     int rows = (int)B->rows, cols = (int)B->cols, tiles_x = (int)cdiv(cols, AT);
@@ -383,8 +425,8 @@ int ms_band_accum_local_dev(ms_band *B, const uint8_t *fd, int32_t *exit_to, dou
     MS_CUDA(cudaMemsetAsync(indeg, 0, (size_t)nslots * sizeof(int), s));
     MS_CUDA(cudaMemsetAsync(X, 0, (size_t)nslots * sizeof(double), s));
     prof_units(B->rows * B->cols);
-    MS_LAUNCH(k_acc_tile<false>, ntiles, 256, sizeof(AccSmem), s, fd, rows, cols, tiles_x, X, entry_next, is_exit,
-              (double *)nullptr, B->open, (const double *)nullptr, (const double *)nullptr);
+    MS_LAUNCH(k_acc_tile_a, ntiles, 256, 0, s, fd, rows, cols, tiles_x, X, entry_next, is_exit,
+              (unsigned short *)B->buf[BB_ACC_LOC16], B->open);
     MS_LAUNCH(k_acc_links, cdiv(nslots, 256), 256, 0, s, fd, is_exit, entry_next, next, indeg, rows, cols, tiles_x, nslots);
     MS_CUDA(cudaMemcpyAsync(indeg0, indeg, (size_t)nslots * sizeof(int), cudaMemcpyDeviceToDevice, s));
     MS_CUDA(cudaMemcpyAsync(X0, X, (size_t)nslots * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -435,8 +477,8 @@ int ms_band_accum_finish_dev(ms_band *B, const uint8_t *fd, const double *halo_t
                   halo_total_top, halo_total_bot);
     MS_LAUNCH(k_acc_node_trace, cdiv(nslots, 256), 256, 0, s, is_exit, next, indeg0, indeg, X, nslots);
     prof_units(B->rows * B->cols);
-    MS_LAUNCH(k_acc_tile<true>, ntiles, 256, sizeof(AccSmem), s, fd, rows, cols, tiles_x, X, entry_next, is_exit, accum,
-              B->open, halo_total_top, halo_total_bot);
+    MS_LAUNCH(k_acc_tile_c, ntiles, 256, 0, s, fd, rows, cols, tiles_x, (const double *)X,
+              (const unsigned short *)B->buf[BB_ACC_LOC16], accum, B->open, halo_total_top, halo_total_bot);
     return MS_OK;
 }
 
