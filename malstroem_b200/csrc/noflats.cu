@@ -249,6 +249,7 @@ struct NfTileShared {
     unsigned long long chgmask;
     int ring;          // bit 0/1/2/3: the tile's top / bottom / left / right ring changed
     int nb;            // neighbour tiles to queue: bit (dy+1)*3 + (dx+1)
+    int grab[3];       // next dirty block to hand out (per iteration, rotating like `dirty`)
     int k;             // ticket
     int flags;         // side bits this tile was queued with
     int e, elo;        // largest / smallest binade exponent of the tile's lake cells (integer form needs e == elo)
@@ -274,18 +275,23 @@ __device__ inline unsigned long long nf_region(int flags) {
 // with NF_MIDFLUSH, while the tile is still settling).
 template <class R, class F>
 __device__ inline int nf_tile_iterate(const R &rx, NfTileShared &S, F &flush) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
     int it = 0;
     for (;; it++) {
         const unsigned long long m = S.dirty[it % 3];
         if (m == 0) break;
-        if (tid == 0) S.dirty[(it + 2) % 3] = 0;
-        unsigned long long mm = m, mark = 0, mine = 0;
+        if (tid == 0) { S.dirty[(it + 2) % 3] = 0; S.grab[(it + 2) % 3] = 0; }
+        unsigned long long mark = 0, mine = 0;
         int rings = 0;
-        for (int idx = 0; mm; idx++) {
-            int b = __ffsll((long long)mm) - 1;
-            mm &= mm - 1;
-            if ((idx & 7) != warp) continue;
+        // the warps take the dirty blocks off a counter: blocks differ a lot in how long they take to settle
+        const unsigned mlo = (unsigned)m, mhi = (unsigned)(m >> 32);
+        const int clo = __popc(mlo), cnt = clo + __popc(mhi);
+        for (;;) {
+            int j = 0;
+            if (lane == 0) j = atomicAdd(&S.grab[it % 3], 1);
+            j = __shfl_sync(0xffffffffu, j, 0);
+            if (j >= cnt) break;
+            int b = j < clo ? (int)__fns(mlo, 0, j + 1) : 32 + (int)__fns(mhi, 0, j - clo + 1);
             unsigned sd;
             if (!rx.block(b, &sd)) continue;
             int by = b >> 3, bx = b & 7;
@@ -399,6 +405,7 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
                 S.chgmask = 0;
                 S.ring = 0;
                 S.nb = 0;
+                S.grab[0] = S.grab[1] = S.grab[2] = 0;
                 S.e = INT_MIN;
                 S.elo = INT_MAX;
                 S.bad = 0;
@@ -585,6 +592,7 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
                 S.dirty[0] = nf_region(S.flags);
                 S.dirty[1] = 0;
                 S.dirty[2] = 0;
+                S.grab[0] = S.grab[1] = S.grab[2] = 0;
                 S.chgmask = 0;
                 S.ring = 0;
                 S.nb = 0;
