@@ -169,6 +169,7 @@ int ms_band_fill_finish_dev(ms_band *band, const float *dem, const float *graph_
 /* fill.fill_terrain_no_flats (fill.py:174-232) on a band: init (needs the halo rows of `filled`; returns the
  * band's count of lake / flat cells), solve (mode 0: first solve, after the halo rows of fnf were exchanged; mode 1:
  * again after the halo rows named by `edges` changed), verify (the fixed-point stencil incl. halo rows). */
+double ms_nf_cap_bound(int64_t rows, int64_t cols, double diag_eps);   /* rows = of the WHOLE raster */
 int ms_band_nf_init_dev(ms_band *band, const float *dem, const float *filled, double *fnf, int64_t *nonseed,
                         void *stream);
 int ms_band_nf_solve_dev(ms_band *band, const float *dem, const float *filled, double *fnf, double short_eps,

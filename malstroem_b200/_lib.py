@@ -67,6 +67,7 @@ SIGNATURES = {
     "ms_band_fill_edges_dev": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p]),
     "ms_graph_minimax_dev": (c_int, [c_i64, c_p, c_p, c_p, c_i64, c_p, c_p]),
     "ms_band_fill_finish_dev": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p]),
+    "ms_nf_cap_bound": (c_dbl, [c_i64, c_i64, c_dbl]),
     "ms_band_nf_init_dev": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p]),
     "ms_band_nf_solve_dev": (c_int, [c_p, c_p, c_p, c_p, c_dbl, c_dbl, c_dbl, c_int, c_int, c_int, c_p, c_p]),
     "ms_band_nf_verify_dev": (c_int, [c_p, c_p, c_p, c_dbl, c_dbl, c_p, c_p]),

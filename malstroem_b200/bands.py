@@ -320,8 +320,7 @@ class BandPipeline(object):
             ns = i64(0)
             self._call("ms_band_nf_init_dev", self.h, _p(self.dem), _p(self.out["filled"]), _p(self.out["fnf"]),
                        ctypes.byref(ns), st)
-            tot = comm.all_reduce(torch.tensor([ns.value], dtype=torch.float64, device=dev), "sum")
-            cap_bound = (float(tot.item()) + 16.0) * self.diag * 1.001
+            cap_bound = float(_lib.lib().ms_nf_cap_bound(self.R, self.cols, self.diag))
             self._halo(fnf)
             visits = i64(0)
             self._call("ms_band_nf_solve_dev", self.h, _p(self.dem), _p(self.out["filled"]), _p(self.out["fnf"]),

@@ -202,10 +202,17 @@ constexpr int D_LIMIT = 0x20000000;       // a tile whose distances get this lar
 
 __device__ inline int imin4(int a, int b, int c, int d) { return min(min(a, b), min(c, d)); }
 
+constexpr int NF_NBIN = 8;               // binades a tile may span in the integer form
+
 struct RelaxI32 {
     int *sd;
-    int sq, dq;
-    int *overflow;     // set when a distance leaves the range the integer form is trusted for
+    const unsigned char *se;   // per interior cell: low byte of the binade exponent of its F
+    const int2 *wtab;          // (short, diag) in ulps for binade elo + k
+    int elo8;                  // low byte of the tile's lowest binade exponent
+    int *overflow;             // set when a distance leaves the range the integer form is trusted for
+    __device__ inline int2 weights(int lr, int lc) const {
+        return wtab[(se[lr * NF_T + lc] - elo8) & (NF_NBIN - 1)];
+    }
     __device__ inline bool block(int b, unsigned *sides) const {
         const unsigned full = 0xffffffffu;
         int lane = threadIdx.x & 31;
@@ -215,6 +222,12 @@ struct RelaxI32 {
         bool live = (w0 <= D_INF) || (w1 <= D_INF);
         *sides = 0;
         if (!__any_sync(full, live)) return false;
+        // neighbouring lake cells share their F, hence their binade: a cell's own weights apply to all its inputs
+        int sq = 0, dq = 0, sq1 = 0, dq1 = 0;
+        if (live) {
+            int2 wa = weights(lr, lc), wb = weights(lr, lc + 1);
+            sq = wa.x; dq = wa.y; sq1 = wb.x; dq1 = wb.y;
+        }
         unsigned sds = 0;
         bool any = false;
         for (int it = 0;; it++) {
@@ -228,7 +241,7 @@ struct RelaxI32 {
                     if (m < w0) { w0 = m; p[0] = m; ch = true; if (m >= D_LIMIT) *overflow = 1; }
                 }
                 if (w1 <= D_INF) {
-                    int m = min(imin4(a1, a3, c1, c3) + dq, imin4(a2, w0, r, c2) + sq);
+                    int m = min(imin4(a1, a3, c1, c3) + dq1, imin4(a2, w0, r, c2) + sq1);
                     if (m < w1) { w1 = m; p[1] = m; ch = true; if (m >= D_LIMIT) *overflow = 1; }
                 }
             }
@@ -250,6 +263,8 @@ struct NfTileShared {
     int ring;          // bit 0/1/2/3: the tile's top / bottom / left / right ring changed
     int nb;            // neighbour tiles to queue: bit (dy+1)*3 + (dx+1)
     int grab[3];       // next dirty block to hand out (per iteration, rotating like `dirty`)
+    unsigned char blist[64];   // the dirty blocks of the current iteration
+    int2 wtab[NF_NBIN];
     int k;             // ticket
     int flags;         // side bits this tile was queued with
     int e, elo;        // largest / smallest binade exponent of the tile's lake cells (integer form needs e == elo)
@@ -284,14 +299,15 @@ __device__ inline int nf_tile_iterate(const R &rx, NfTileShared &S, F &flush) {
         unsigned long long mark = 0, mine = 0;
         int rings = 0;
         // the warps take the dirty blocks off a counter: blocks differ a lot in how long they take to settle
-        const unsigned mlo = (unsigned)m, mhi = (unsigned)(m >> 32);
-        const int clo = __popc(mlo), cnt = clo + __popc(mhi);
+        const int cnt = __popcll(m);
+        if (tid < 64 && (m >> tid) & 1ull) S.blist[__popcll(m & ((1ull << tid) - 1ull))] = (unsigned char)tid;
+        __syncthreads();
         for (;;) {
             int j = 0;
             if (lane == 0) j = atomicAdd(&S.grab[it % 3], 1);
             j = __shfl_sync(0xffffffffu, j, 0);
             if (j >= cnt) break;
-            int b = j < clo ? (int)__fns(mlo, 0, j + 1) : 32 + (int)__fns(mhi, 0, j - clo + 1);
+            int b = S.blist[j];
             unsigned sd;
             if (!rx.block(b, &sd)) continue;
             int by = b >> 3, bx = b & 7;
@@ -324,22 +340,38 @@ __device__ inline int nf_tile_iterate(const R &rx, NfTileShared &S, F &flush) {
 }
 
 // lake cell (w > f) -> integer distance; anything else -> wall.  Tracks the range of binades seen (elo..ehi).
-__device__ inline int nf_to_int(double w, float f, int &bad, int &elo, int &ehi, int &dmax) {
-    double fd = (double)f;
-    if (!(w > fd)) return D_WALL;
+__device__ inline int nf_binade(double fd) {
     int hi = __double2hiint(fd);
     int e = ((hi >> 20) & 0x7ff) - 1023;
     // values just above a negative power of two have the smaller magnitude: they live one binade lower
     if (fd < 0 && (hi & 0xfffff) == 0 && __double2loint(fd) == 0) e -= 1;
-    if (fd == 0.0 || e < -900) { bad = 1; return D_WALL; }
+    return e;
+}
+
+__device__ inline int nf_to_int(double w, float f, int &bad, int &elo, int &ehi, int &dmax, unsigned char *e8) {
+    double fd = (double)f;
+    *e8 = 0;
+    if (!(w > fd)) return D_WALL;
+    int e = nf_binade(fd);
+    if (fd == 0.0 || e < -900) { bad |= 1; return D_WALL; }
+    *e8 = (unsigned char)(e & 0xff);
     elo = min(elo, e);
     ehi = max(ehi, e);
     if (w == INFINITY) return D_INF;
     int ew = ((__double2hiint(w) >> 20) & 0x7ff) - 1023;
-    if (ew != e) { bad = 1; return D_WALL; }
+    if (ew != e) { bad |= 2; return D_WALL; }
     double inv_ulp = __hiloint2double((1023 - (e - 52)) << 20, 0);
     double d = (w - fd) * inv_ulp;              // exact: same binade, both multiples of its ulp
-    if (!(d < (double)D_LIMIT)) { bad = 1; return D_WALL; }
+    if (!(d < (double)D_LIMIT)) {
+#ifdef NF_STATS
+        if (atomicAdd(&g_nf_dbg[12], 1ull) == 1000ull) {
+            g_nf_dbg[13] = (unsigned long long)__double_as_longlong(w);
+            g_nf_dbg[14] = (unsigned long long)__double_as_longlong(fd);
+        }
+#endif
+        bad |= 4;
+        return D_WALL;
+    }
     int di = (int)d;
     dmax = max(dmax, di);
     return di;
@@ -366,7 +398,7 @@ struct NfRowRegs {
 };
 
 template <bool CAP>
-__global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc, double *W, int *ring, int cap,
+__global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ zsrc, double *W, int *ring, int cap,
                                                   int *tileflag, const int *__restrict__ tilesides, NfCtl *ctl, int rows, int cols, int tiles_x,
                                                   int tiles_y, double sh, double dg, int use_int, double capB_in,
                                                   int open) {
@@ -374,6 +406,7 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
     double *sw = reinterpret_cast<double *>(smem_raw);
     float *sz = reinterpret_cast<float *>(smem_raw + (NF_T + 2) * NF_LD * 8);
     int *sdi = reinterpret_cast<int *>(smem_raw);
+    unsigned char *se = smem_raw + (NF_T + 2) * NF_ILD * 4;          // integer form: binade byte per interior cell
     __shared__ NfTileShared S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double capB = CAP ? (capB_in >= 0 ? capB_in : ((double)ctl->nonseed + 16.0) * dg * 1.001) : 0.0;
@@ -478,43 +511,63 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
                     int lr = warp + 8 * (half * 5 + j);
                     if (lr < NF_T + 2) {
                         int *row = sdi + lr * NF_ILD;
-                        row[1 + 2 * lane] = nf_to_int(rg[j].w0, rg[j].f0, bad, elo, ehi, dmax);
-                        row[2 + 2 * lane] = nf_to_int(rg[j].w1, rg[j].f1, bad, elo, ehi, dmax);
-                        if (lane < 2) row[lane ? NF_T + 1 : 0] = nf_to_int(rg[j].wa, rg[j].fa, bad, elo, ehi, dmax);
+                        unsigned char e0, e1, ea;
+                        row[1 + 2 * lane] = nf_to_int(rg[j].w0, rg[j].f0, bad, elo, ehi, dmax, &e0);
+                        row[2 + 2 * lane] = nf_to_int(rg[j].w1, rg[j].f1, bad, elo, ehi, dmax, &e1);
+                        if (lane < 2) row[lane ? NF_T + 1 : 0] = nf_to_int(rg[j].wa, rg[j].fa, bad, elo, ehi, dmax, &ea);
+                        if (lr >= 1 && lr <= NF_T) {
+                            se[(lr - 1) * NF_T + 2 * lane] = e0;
+                            se[(lr - 1) * NF_T + 2 * lane + 1] = e1;
+                        }
                     }
                 }
             }
             dmax = __reduce_max_sync(0xffffffffu, dmax);
             elo = __reduce_min_sync(0xffffffffu, elo);
             ehi = __reduce_max_sync(0xffffffffu, ehi);
-            bad = __any_sync(0xffffffffu, bad);
+            bad = __reduce_or_sync(0xffffffffu, bad);
+#ifdef NF_STATS
+            if (lane == 0 && bad) { if (bad & 1) atomicAdd(&g_nf_dbg[6], 1ull); if (bad & 2) atomicAdd(&g_nf_dbg[7], 1ull); if (bad & 4) atomicAdd(&g_nf_dbg[8], 1ull); }
+#endif
             if (lane == 0) {
                 if (dmax) atomicMax(&S.dmax, dmax);
                 if (ehi != INT_MIN) { atomicMin(&S.elo, elo); atomicMax(&S.e, ehi); }
                 if (bad) S.bad = 1;
             }
             __syncthreads();
-            double ulp = 0, sqd = 0, dqd = 0;
-            bool ok = !S.bad && (S.e == INT_MIN || S.e == S.elo);
+            bool ok = !S.bad && (S.e == INT_MIN || S.e - S.elo < NF_NBIN) && S.dmax < D_LIMIT;
+#ifdef NF_STATS
+            if (tid == 0 && !S.bad && !ok) atomicAdd(&g_nf_dbg[9], 1ull);
+#endif
             if (ok && S.e != INT_MIN) {
-                int e = S.e;
-                ulp = __longlong_as_double((long long)(e - 52 + 1023) << 52);
-                double inv_ulp = __longlong_as_double((long long)(1023 - (e - 52)) << 52);
-                sqd = sh * inv_ulp;
-                double dqx = dg * inv_ulp;
-                dqd = rint(dqx);
-                double fr2 = fabs(dqx - floor(dqx) - 0.5);
-                // short must be a whole number of ulps, diag must not sit on a rounding tie, and the distances
-                // must stay inside the range the integer form is trusted for
-                ok = sqd >= 1.0 && sqd == rint(sqd) && dqd >= 1.0 && fr2 > 1e-9 && dqd < (double)(1 << 27) &&
-                     sqd < (double)(1 << 27) && S.dmax < D_LIMIT;
+                // weights per binade of the tile: short must be a whole number of ulps, diag must not sit on a
+                // rounding tie, and both must leave room in the integer range
+                if (tid < NF_NBIN) {
+                    int e = S.elo + tid;
+                    int2 wt = make_int2(0, 0);
+                    if (e <= S.e) {
+                        double inv_ulp = __longlong_as_double((long long)(1023 - (e - 52)) << 52);
+                        double sqd = sh * inv_ulp, dqx = dg * inv_ulp, dqd = rint(dqx);
+                        double fr2 = fabs(dqx - floor(dqx) - 0.5);
+                        bool good = sqd >= 1.0 && sqd == rint(sqd) && dqd >= 1.0 && fr2 > 1e-9 &&
+                                    dqd < (double)(1 << 27) && sqd < (double)(1 << 27);
+                        if (good) wt = make_int2((int)sqd, (int)dqd);
+                        else S.bad = 1;
+                    }
+                    S.wtab[tid] = wt;
+                }
+                __syncthreads();
+                ok = !S.bad;
+#ifdef NF_STATS
+                if (tid == 0 && !ok) atomicAdd(&g_nf_dbg[10], 1ull);
+#endif
             }
             if (ok && S.e == INT_MIN) {
                 solved = true;                      // no lake cell in the tile or its apron: nothing to do
             } else if (ok) {
                 if (tid == 0) S.dirty[0] = nf_region(S.flags);
                 __syncthreads();
-                RelaxI32 rx{sdi, (int)sqd, (int)dqd, &S.bad};
+                RelaxI32 rx{sdi, se, S.wtab, S.elo & 0xff, &S.bad};
                 auto flush = [&]() {
                     if (S.bad) return;              // the tile will be redone in float64: write nothing
                     // the blocks that changed: W = F + D * ulp (exact)
@@ -532,7 +585,9 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
                                 int d = p[q];
                                 if (c + q < cols && d < D_INF) {
                                     size_t i = (size_t)r * cols + c + q;
-                                    W[i] = __dadd_rn((double)__ldg(zsrc + i), __dmul_rn((double)d, ulp));
+                                    double fd = (double)__ldg(zsrc + i);
+                                    double ulp = __longlong_as_double((long long)(nf_binade(fd) - 52 + 1023) << 52);
+                                    W[i] = __dadd_rn(fd, __dmul_rn((double)d, ulp));
                                 }
                             }
                         }
@@ -547,6 +602,7 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
                         int lc = side == 2 ? 0 : (side == 3 ? NF_T - 1 : k);
                         int d = sdi[(lr + 1) * NF_ILD + (lc + 1)];
                         int nbm = 0;
+                        int2 wt = rx.weights(lr, lc);
                         if (d < D_INF) {
 #pragma unroll
                             for (int o = -1; o <= 1; o++) {
@@ -554,7 +610,7 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
                                 int ar = side == 0 ? -1 : (side == 1 ? NF_T : lr + o);
                                 int ac = side == 2 ? -1 : (side == 3 ? NF_T : lc + o);
                                 int da = sdi[(ar + 1) * NF_ILD + (ac + 1)];
-                                int w = (o == 0) ? rx.sq : rx.dq;
+                                int w = (o == 0) ? wt.x : wt.y;
                                 if (da <= D_INF && d + w < da) {
                                     int dy = ar < 0 ? -1 : (ar >= NF_T ? 1 : 0), dx = ac < 0 ? -1 : (ac >= NF_T ? 1 : 0);
                                     nbm |= 1 << ((dy + 1) * 3 + (dx + 1));
@@ -583,11 +639,17 @@ __global__ void __launch_bounds__(256) k_nf_solve(const float *__restrict__ zsrc
 #endif
                 (void)its;
                 solved = !S.bad;                    // a distance left the trusted range: redo the tile in float64
+#ifdef NF_STATS
+                if (tid == 0 && !solved) atomicAdd(&g_nf_dbg[11], 1ull);
+#endif
             }
             if (!solved) __syncthreads();          // everybody is done with the integer tile before it is overwritten
         }
         if (!solved) {
             // ---- float64 form
+#ifdef NF_STATS
+            if (tid == 0) atomicAdd(&g_nf_dbg[5], 1ull);
+#endif
             if (tid == 0) {
                 S.dirty[0] = nf_region(S.flags);
                 S.dirty[1] = 0;
@@ -731,6 +793,19 @@ __global__ void __launch_bounds__(256) k_nf_verify(const float *__restrict__ z, 
     if (threadIdx.x == 0 && cnt) atomicAdd(&ctl->nviol, cnt);
 }
 
+}  // namespace ms
+
+/* The cap of the fast path: candidates more than this above the plain fill are ignored.  The solution exceeds the
+ * plain fill by (geodesic steps to the lake's outlet) * diag at most; 4 * (rows + cols) steps covers every lake that
+ * does not wind back and forth across the whole raster, and is far below the millimetre-scale gaps to shore cells
+ * that the cap is there to keep out (a bound derived from the number of lake cells reaches a millimetre at 8192^2
+ * and stops filtering).  A lake that needs more is caught by the verification and solved by the uncapped path. */
+extern "C" double ms_nf_cap_bound(int64_t rows, int64_t cols, double diag_eps) {
+    return 4.0 * (double)(rows + cols) * diag_eps;
+}
+
+namespace ms {
+
 int g_nf_use_int = 1;      // MS_NF_INT=0 in the environment keeps every tile in the float64 form (debugging)
 
 template <bool CAP>
@@ -798,6 +873,7 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
     MS_TRY(ring.alloc((size_t)cap_ring, s));
     MS_TRY(ctl.alloc(1, s));
     bool cap = sh > 0 && dg > 0;      // capped fast path first; a verification failure falls back to the generic one
+    const double cap_bound = ms_nf_cap_bound(rows, cols, dg);
     dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
     int64_t visits = 0, tries = 0;
@@ -811,9 +887,9 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
                   tiles_x, 0);
         MS_LAUNCH(k_nf_compact, cdiv(ntiles, 256), 256, 0, s, tileflag.p, ring.p, ctl.p, ntiles);
         if (cap) {
-            MS_LAUNCH(k_nf_seedcand, g2, 256, 0, s, filled, out, ctl.p, (int)rows, (int)cols, sh, dg, -1.0, 0);
+            MS_LAUNCH(k_nf_seedcand, g2, 256, 0, s, filled, out, ctl.p, (int)rows, (int)cols, sh, dg, cap_bound, 0);
             MS_TRY(nf_launch_solve<true>(filled, out, ring.p, cap_ring, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols, tiles_x,
-                                         tiles_y, ntiles, sh, dg, g_nf_use_int, -1.0, 0, n, s));
+                                         tiles_y, ntiles, sh, dg, g_nf_use_int, cap_bound, 0, n, s));
         } else {
             MS_TRY(nf_launch_solve<false>(dtm, out, ring.p, cap_ring, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols, tiles_x,
                                           tiles_y, ntiles, sh, dg, 0, -1.0, 0, n, s));

@@ -33,7 +33,7 @@ for rep in range(3):
     dbg(out, 16, 0)
     v = max(st[1], 1)
     print("wall %.2f ms  visits %d  mean load %d cyc  mean solve %d cyc  mean iters %.2f  max solve %d cyc" %
-          ((t1 - t0) * 1e3, st[1], out[1] // v, out[2] // v, out[3] / v, out[4]))
+          ((t1 - t0) * 1e3, st[1], out[1] // v, out[2] // v, out[3] / v, out[4]), " fp64-form visits", out[5], "reasons(warps F0/subnormal, W other binade, D range; tile range, weights, overflow)", list(out[6:12]))
 
 log = np.zeros(4 * 262144, dtype=np.uint64)
 nl = ctypes.c_uint(0)
@@ -43,3 +43,4 @@ log = log[: 4 * k].reshape(k, 4)
 os.makedirs("gpurun_out", exist_ok=True)
 np.save("gpurun_out/nf_log_%d.npy" % S, log)
 print("logged", k, "visits")
+print("sample out-of-range cell: W=%r F=%r count=%d" % (np.array([out[13]], dtype=np.uint64).view(np.float64)[0], np.array([out[14]], dtype=np.uint64).view(np.float64)[0], out[12]))
