@@ -257,6 +257,20 @@ typedef struct ms_rasters {
  * convergence flags and counts. */
 int ms_pipeline_dev(ms_rasters *io, void *stream);
 
+/* The same with the finished rasters shipped to (pinned) host buffers while the later stages run: every non-NULL
+ * pointer of `host` receives its raster through a second stream as soon as the stage that produces it is done.
+ * The copies are complete after ms_copies_wait().  (The host-buffer front end of malstroem_b200.pipeline uses this;
+ * what the reference's tool layer writes to GeoTIFFs — dem.py:67-93, bluespots.py:159-216 — is exactly this set.) */
+typedef struct ms_host_out {
+    float *filled, *depths;
+    double *fnf;
+    uint8_t *flowdir;
+    double *accum;
+    int32_t *labels, *wsheds;
+} ms_host_out;
+int ms_pipeline_host_dev(ms_rasters *io, const ms_host_out *host, void *stream);
+int ms_copies_wait(void);
+
 /* synthetic fractal DEM (malstroem_b200/synth.py, bit-identical), generated in place on the device */
 int ms_synth_fractal_dev(float *dem, int64_t rows, int64_t cols, int64_t row0, int64_t col0, int seed,
                          void *stream);

@@ -86,6 +86,8 @@ SIGNATURES = {
     "ms_band_extreme_value_dev": (c_int, [c_p, c_p, c_i64, c_i64, c_int, c_p, c_p]),
     "ms_band_extreme_index_dev": (c_int, [c_p, c_p, c_i64, c_i64, c_p, c_i64, c_p, c_p]),
     "ms_pipeline_dev": (c_int, [c_p, c_p]),
+    "ms_pipeline_host_dev": (c_int, [c_p, c_p, c_p]),
+    "ms_copies_wait": (c_int, []),
     "ms_synth_fractal_dev": (c_int, [c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_p]),
 }
 
@@ -100,6 +102,12 @@ class MsRasters(ctypes.Structure):
                 ("ppmin_value", c_p), ("ppmin_row", c_p), ("ppmin_col", c_p),
                 ("ppmax_value", c_p), ("ppmax_row", c_p), ("ppmax_col", c_p),
                 ("nlabels", c_i64), ("short_eps", c_dbl), ("diag_eps", c_dbl), ("stats", c_i64 * 8)]
+
+
+class MsHostOut(ctypes.Structure):
+    """struct ms_host_out of include/malstroem_b200.h"""
+    _fields_ = [("filled", c_p), ("depths", c_p), ("fnf", c_p), ("flowdir", c_p), ("accum", c_p), ("labels", c_p),
+                ("wsheds", c_p)]
 
 
 _lib = None

@@ -24,10 +24,39 @@ int label_extreme_dev_impl(const double *data, const int32_t *lab, int64_t rows,
 int label_count_dev_impl(const int32_t *lab, int64_t n, int64_t nbins, int64_t *cnt, int *err_dev, cudaStream_t s);
 }  // namespace ms
 
-extern "C" int ms_pipeline_dev(ms_rasters *io, void *stream) {
+namespace {
+// device -> host copies of finished rasters on a second stream, so that they overlap the stages that follow
+cudaStream_t g_copy_stream = nullptr;
+cudaEvent_t g_copy_ev[8];
+int g_copy_n = 0;
+
+int ship(void *dst, const void *src, size_t bytes, cudaStream_t s) {
+    if (!dst) return MS_OK;
+    if (!g_copy_stream) {
+        MS_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 8; k++) MS_CUDA(cudaEventCreateWithFlags(&g_copy_ev[k], cudaEventDisableTiming));
+    }
+    cudaEvent_t ev = g_copy_ev[g_copy_n++ & 7];
+    MS_CUDA(cudaEventRecord(ev, s));
+    MS_CUDA(cudaStreamWaitEvent(g_copy_stream, ev, 0));
+    MS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_copy_stream));
+    return MS_OK;
+}
+}  // namespace
+
+extern "C" int ms_copies_wait(void) {
+    if (g_copy_stream) MS_CUDA(cudaStreamSynchronize(g_copy_stream));
+    return MS_OK;
+}
+
+extern "C" int ms_pipeline_dev(ms_rasters *io, void *stream) { return ms_pipeline_host_dev(io, nullptr, stream); }
+
+extern "C" int ms_pipeline_host_dev(ms_rasters *io, const ms_host_out *host, void *stream) {
     using namespace ms;
     MS_TRY(ensure_init());
     cudaStream_t s = (cudaStream_t)stream;
+    static const ms_host_out no_host = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (!host) host = &no_host;
     if (!io || !io->dem || !io->filled || !io->depths || !io->fnf || !io->flowdir || !io->labels || !io->wsheds) {
         set_error("pipeline: null raster pointer");
         return MS_ERR_ARG;
@@ -38,6 +67,8 @@ extern "C" int ms_pipeline_dev(ms_rasters *io, void *stream) {
 
     // dem.py:67-72
     MS_TRY(fill_terrain_dev_impl(io->dem, io->filled, io->depths, rows, cols, io->stats, s));
+    MS_TRY(ship(host->filled, io->filled, (size_t)n * sizeof(float), s));
+    MS_TRY(ship(host->depths, io->depths, (size_t)n * sizeof(float), s));
     // dem.py:79 (fill.py:235-250)
     DevBuf<float> mm;
     MS_TRY(mm.alloc(2, s));
@@ -52,9 +83,14 @@ extern "C" int ms_pipeline_dev(ms_rasters *io, void *stream) {
     int64_t nfstats[3] = {0, 0, 0};
     MS_TRY(fill_no_flats_dev_impl(io->dem, io->filled, io->short_eps, io->diag_eps, io->fnf, rows, cols, nfstats, s));
     io->stats[2] = nfstats[0]; io->stats[3] = nfstats[1]; io->stats[4] = nfstats[2];
+    MS_TRY(ship(host->fnf, io->fnf, (size_t)n * sizeof(double), s));
     MS_TRY(flowdir_dev_impl(io->fnf, io->flowdir, rows, cols, 1, s, 0));
+    MS_TRY(ship(host->flowdir, io->flowdir, (size_t)n, s));
     // dem.py:87-91
-    if (io->accum) MS_TRY(accum_dev_impl(io->flowdir, io->accum, rows, cols, s));
+    if (io->accum) {
+        MS_TRY(accum_dev_impl(io->flowdir, io->accum, rows, cols, s));
+        MS_TRY(ship(host->accum, io->accum, (size_t)n * sizeof(double), s));
+    }
     // bluespots.py:158-160
     DevBuf<int64_t> tot;
     DevBuf<int> err;
@@ -65,6 +101,7 @@ extern "C" int ms_pipeline_dev(ms_rasters *io, void *stream) {
     MS_CUDA(cudaMemcpyAsync(h, tot.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
     io->nlabels = h[0];
+    MS_TRY(ship(host->labels, io->labels, (size_t)n * sizeof(int32_t), s));
     if (io->nlabels + 1 > io->table_capacity) {
         set_error("pipeline: %lld labels do not fit table_capacity %lld", (long long)io->nlabels,
                   (long long)io->table_capacity);
@@ -76,6 +113,7 @@ extern "C" int ms_pipeline_dev(ms_rasters *io, void *stream) {
     // bluespots.py:183-186
     MS_CUDA(cudaMemcpyAsync(io->wsheds, io->labels, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
     MS_TRY(watersheds_dev_impl(io->flowdir, io->wsheds, 4, rows, cols, 0, io->stats, s));
+    MS_TRY(ship(host->wsheds, io->wsheds, (size_t)n * sizeof(int32_t), s));
     if (io->ws_count) MS_TRY(label_count_dev_impl(io->wsheds, n, io->nlabels + 1, io->ws_count, err.p, s));
     // bluespots.py:195-206 (both pour-point variants)
     if (io->ppmin_value)

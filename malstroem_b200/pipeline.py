@@ -60,13 +60,19 @@ class RasterPipeline(object):
         self._host = None
 
     # ---- device-resident run (bench `value`) ---------------------------------------------------------
-    def run(self, dem=None):
-        """dem: optional cuda float32 tensor of the pipeline's shape (else self.dem is used as is)."""
+    def run(self, dem=None, host_out=None):
+        """dem: optional cuda float32 tensor of the pipeline's shape (else self.dem is used as is).
+        host_out: optional _lib.MsHostOut of pinned host buffers the finished rasters are shipped to while the later
+        stages run (complete after ms_copies_wait)."""
         if dem is not None and dem.data_ptr() != self.dem.data_ptr():
             self.dem.copy_(dem)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with _lib.lock:
-            _lib.check(_lib.lib().ms_pipeline_dev(ctypes.byref(self.io), ctypes.c_void_p(stream)), "ms_pipeline_dev")
+            if host_out is None:
+                _lib.check(_lib.lib().ms_pipeline_dev(ctypes.byref(self.io), ctypes.c_void_p(stream)), "ms_pipeline_dev")
+            else:
+                _lib.check(_lib.lib().ms_pipeline_host_dev(ctypes.byref(self.io), ctypes.byref(host_out),
+                                                           ctypes.c_void_p(stream)), "ms_pipeline_host_dev")
         self.nlabels = int(self.io.nlabels)
         self.stats = dict(zip(STAT_NAMES, [int(v) for v in self.io.stats]))
         self.short, self.diag = float(self.io.short_eps), float(self.io.diag_eps)
@@ -95,13 +101,16 @@ class RasterPipeline(object):
             if src.data_ptr() != h["dem"].data_ptr():
                 h["dem"].copy_(src)
         self.dem.copy_(h["dem"], non_blocking=True)
-        self.run()
-        for name, t in self.out.items():
-            h[name].copy_(t, non_blocking=True)
+        ho = _lib.MsHostOut()
+        for name in self.out:
+            setattr(ho, name, h[name].data_ptr())
+        self.run(host_out=ho)          # rasters leave through the copy stream while the later stages run
         m = self.nlabels + 1
         for name, t in self.tables.items():
             h[name][:m].copy_(t[:m], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        with _lib.lock:
+            _lib.check(_lib.lib().ms_copies_wait(), "ms_copies_wait")
         return h
 
     def bytes_h2d(self):
