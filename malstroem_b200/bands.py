@@ -253,10 +253,27 @@ class BandPipeline(object):
             ext[self.rows + 1].copy_(b)
 
     # ---- the staged run (order and operands: DemTool.process dem.py:53-93, BluespotTool.process bluespots.py:138-216)
+    def _tick(self, name):
+        """MS_BAND_TIMING=1: wall time per stage (with a device synchronisation at every stage boundary)."""
+        if not self._timing:
+            return
+        import time
+        torch.cuda.synchronize(self.device)
+        now = time.perf_counter()
+        self.timing[name] = self.timing.get(name, 0.0) + (now - self._t_last) * 1e3
+        self._t_last = now
+
     def run(self):
+        import os
+        import time
         L, comm, dev, cols, rows, n = _lib.lib(), self.comm, self.device, self.cols, self.rows, self.rows * self.cols
         st = self._stream()
         i64 = ctypes.c_int64
+        self._timing = os.environ.get("MS_BAND_TIMING") == "1"
+        if self._timing:
+            self.timing = getattr(self, "timing", {})
+            torch.cuda.synchronize(self.device)
+            self._t_last = time.perf_counter()
         # K1 fill (+ depths)
         self._halo(self.dem_ext)
         nF = i64(0)
@@ -277,9 +294,10 @@ class BandPipeline(object):
             self._call("ms_band_fill_edges_dev", self.h, _p(self.dem), _p(h_top), _p(h_bot), _p(ea), _p(eb), _p(ew), cap,
                        ctypes.byref(ne), st)
             k = ne.value
-            ea = torch.cat(comm.all_gather_var(ea[:k])).contiguous()
-            eb = torch.cat(comm.all_gather_var(eb[:k])).contiguous()
-            ew = torch.cat(comm.all_gather_var(ew[:k])).contiguous()
+            packed = torch.stack([ea[:k], eb[:k], ew[:k].view(torch.int32)], dim=1)      # one gather for the graph
+            packed = torch.cat(comm.all_gather_var(packed))
+            ea, eb = packed[:, 0].contiguous(), packed[:, 1].contiguous()
+            ew = packed[:, 2].contiguous().view(torch.float32)
             graph_x = torch.empty(total_f + 1, dtype=torch.float32, device=dev)
             self._call("ms_graph_minimax_dev", total_f + 1, _p(ea), _p(eb), _p(ew), ea.numel(), _p(graph_x), st)
             self.stats["fill_graph_edges"] = int(ea.numel())
@@ -287,6 +305,7 @@ class BandPipeline(object):
         self._call("ms_band_fill_finish_dev", self.h, _p(self.dem), _p(graph_x), _p(self.out["filled"]),
                    _p(self.out["depths"]), st)
         self._halo(self.ext["filled"])
+        self._tick("fill")
         # short / diag (fill.py:235-250)
         mm = torch.empty(2, dtype=torch.float32, device=dev)
         self._call("ms_minmax_f32_dev", _p(self.dem), n, _p(mm), st)
@@ -296,20 +315,28 @@ class BandPipeline(object):
         maxval = np.float64(max(abs(np.float32(hi.item())), abs(np.float32(lo.item()))))
         self.short = float((np.nextafter(maxval, np.inf) - maxval) * 1024.0)
         self.diag = float(self.short * 2 ** 0.5)
+        self._tick("minmax")
         # K2 no-flats fill
         self._noflats(st)
+        self._tick("noflats")
         # K3 D8
         self._call("ms_band_flowdir_dev", self.h, _p(self.out["fnf"]), _p(self.out["flowdir"]), 1, st)
         self._halo(self.ext["flowdir"])
+        self._tick("flowdir")
         # K4 accumulation
         self._accum(st)
+        self._tick("accum")
         # K5/K6 bluespot labels, K8 stats
         self._labels(st)
+        self._tick("labels")
         self._stats(st)
+        self._tick("stats")
         # K7 watersheds, K10 counts
         self._watersheds(st)
+        self._tick("watersheds")
         # K8'/K8'' pour points
         self._pour_points(st)
+        self._tick("pour_points")
         return self
 
     def _noflats(self, st):
@@ -359,7 +386,8 @@ class BandPipeline(object):
         entry_root = torch.empty(2 * cols, dtype=torch.int32, device=dev)
         self._call("ms_band_accum_local_dev", self.h, _p(self.out["flowdir"]), _p(exit_to), _p(exit_val),
                    _p(entry_root), st)
-        all_to, all_val, all_root = comm.all_gather(exit_to), comm.all_gather(exit_val), comm.all_gather(entry_root)
+        packed = comm.all_gather(torch.stack([exit_to.double(), exit_val, entry_root.double()]))     # [G, 3, 2*cols]
+        all_to, all_val, all_root = packed[:, 0].to(torch.int32), packed[:, 1].contiguous(), packed[:, 2].to(torch.int32)
         parent = accum_forest(all_to, all_root, cols).contiguous()
         totals = all_val.reshape(-1).clone()
         self._call("ms_forest_accumulate_dev", totals.numel(), _p(parent), _p(totals), st)
@@ -421,10 +449,15 @@ class BandPipeline(object):
         tcnt = self._table("st_count", torch.int64)
         self._call("ms_label_stats_dev", _p(self.out["depths"]), _lib.MS_F32, _p(self.out["labels"]), n, self.nlabels,
                    _p(tmin), _p(tmax), _p(tsum), _p(tcnt), st)
-        comm.all_reduce(tmin, "min")
-        comm.all_reduce(tmax, "max")
-        comm.all_reduce(tsum, "sum")
-        comm.all_reduce(tcnt, "sum")
+        m = self.nlabels + 1
+        lohi = torch.cat([tmin, -tmax])                      # max(x) = -min(-x): one reduction for both
+        comm.all_reduce(lohi, "min")
+        tmin.copy_(lohi[:m])
+        tmax.copy_(-lohi[m:])
+        sums = torch.cat([tsum, tcnt.double()])              # counts < 2^53: exact in float64
+        comm.all_reduce(sums, "sum")
+        tsum.copy_(sums[:m])
+        tcnt.copy_(sums[m:].round().long())
 
     def _watersheds(self, st):
         comm, dev, cols = self.comm, self.device, self.cols
@@ -434,7 +467,8 @@ class BandPipeline(object):
         edge_res = torch.empty(2 * cols, dtype=torch.int32, device=dev)
         exit_to = torch.empty(2 * cols, dtype=torch.int32, device=dev)
         self._call("ms_band_ws_local_dev", self.h, _p(self.out["flowdir"]), _p(ws), 0, _p(edge_res), _p(exit_to), st)
-        all_res, all_to = comm.all_gather(edge_res), comm.all_gather(exit_to)
+        packed = comm.all_gather(torch.stack([edge_res, exit_to]))                                   # [G, 2, 2*cols]
+        all_res, all_to = packed[:, 0].contiguous(), packed[:, 1].contiguous()
         arr = watershed_chain(all_res, all_to, cols).contiguous()
         final = torch.empty_like(arr)
         self._call("ms_chain_resolve_dev", arr.numel(), _p(arr), _p(final), st)
@@ -446,20 +480,26 @@ class BandPipeline(object):
         comm.all_reduce(cnt, "sum")
 
     def _pour_points(self, st):
-        comm, n, cols = self.comm, self.rows * self.cols, self.cols
-        for key, data, want_max in (("ppmin", self.out["fnf"], 0), ("ppmax", self.out["accum"], 1)):
-            val = self._table(key + "_value", torch.float64)
-            self._call("ms_band_extreme_value_dev", _p(data), _p(self.out["labels"]), n, self.nlabels, want_max, _p(val),
-                       st)
-            comm.all_reduce(val, "max" if want_max else "min")
-            idx = torch.empty(self.nlabels + 1, dtype=torch.int64, device=self.device)
-            self._call("ms_band_extreme_index_dev", _p(data), _p(self.out["labels"]), n, self.nlabels, _p(val),
-                       self.cell_offset, _p(idx), st)
-            comm.all_reduce(idx, "min")
-            none = idx == torch.iinfo(torch.int64).max
-            self.tables[key + "_row"] = torch.where(none, torch.full_like(idx, -1), idx // cols)
-            self.tables[key + "_col"] = torch.where(none, torch.full_like(idx, -1), idx % cols)
-
+        comm, n, cols, m = self.comm, self.rows * self.cols, self.cols, self.nlabels + 1
+        keys = (("ppmin", self.out["fnf"], 0), ("ppmax", self.out["accum"], 1))
+        vals = torch.empty(2 * m, dtype=torch.float64, device=self.device)
+        for k, (key, data, want_max) in enumerate(keys):
+            self._call("ms_band_extreme_value_dev", _p(data), _p(self.out["labels"]), n, self.nlabels, want_max,
+                       _p(vals[k * m:]), st)
+        vals[m:].neg_()                                      # max(x) = -min(-x): one reduction for both tables
+        comm.all_reduce(vals, "min")
+        vals[m:].neg_()
+        idx = torch.empty(2 * m, dtype=torch.int64, device=self.device)
+        for k, (key, data, want_max) in enumerate(keys):
+            self._call("ms_band_extreme_index_dev", _p(data), _p(self.out["labels"]), n, self.nlabels, _p(vals[k * m:]),
+                       self.cell_offset, _p(idx[k * m:]), st)
+        comm.all_reduce(idx, "min")
+        none = idx == torch.iinfo(torch.int64).max
+        rows_, cols_ = torch.where(none, torch.full_like(idx, -1), idx // cols), torch.where(none, torch.full_like(idx, -1), idx % cols)
+        for k, (key, data, want_max) in enumerate(keys):
+            self.tables[key + "_value"] = vals[k * m:(k + 1) * m]
+            self.tables[key + "_row"] = rows_[k * m:(k + 1) * m]
+            self.tables[key + "_col"] = cols_[k * m:(k + 1) * m]
 
     # ---- host-buffer front end (bench `e2e`): H2D of the band's DEM rows, the run, D2H of every raster + table
     def host_buffers(self):

@@ -1,0 +1,25 @@
+"""torchrun: per-stage wall time of the banded run (MS_BAND_TIMING=1), rank 0 prints."""
+import os, sys
+os.environ["MS_BAND_TIMING"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+from malstroem_b200 import bands
+from malstroem_b200.pipeline import synth_fractal
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+p = bands.BandPipeline(world * S, S, bands.DistComm(), device=local)
+synth_fractal(S, S, seed=1, row0=rank * S, col0=0, device=local, out=p.dem)
+for _ in range(3):
+    p.run()
+p.timing = {}
+reps = 3
+for _ in range(reps):
+    p.run()
+if rank == 0:
+    tot = 0
+    for k, v in p.timing.items():
+        print("%-12s %7.2f ms" % (k, v / reps)); tot += v / reps
+    print("total        %7.2f ms" % tot, p.stats)
+dist.destroy_process_group()
