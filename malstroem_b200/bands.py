@@ -349,29 +349,35 @@ class BandPipeline(object):
                        ctypes.byref(ns), st)
             cap_bound = float(_lib.lib().ms_nf_cap_bound(self.R, self.cols, self.diag))
             self._halo(fnf)
+            self._tick("nf_init")
             visits = i64(0)
             self._call("ms_band_nf_solve_dev", self.h, _p(self.dem), _p(self.out["filled"]), _p(self.out["fnf"]),
                        self.short, self.diag, cap_bound, cap, 0, 0, ctypes.byref(visits), st)
             total_visits, sweeps = visits.value, 0
+            self._tick("nf_first_solve")
             for sweeps in range(1, 100000):
                 old_top, old_bot = fnf[0].clone(), fnf[self.rows + 1].clone()
                 self._halo(fnf)
-                ch = 0
-                if self.open & OPEN_TOP and not torch.equal(old_top, fnf[0]):
-                    ch |= 1
-                if self.open & OPEN_BOTTOM and not torch.equal(old_bot, fnf[self.rows + 1]):
-                    ch |= 2
-                anyc = comm.all_reduce(torch.tensor([ch], dtype=torch.int32, device=dev), "max")
-                if int(anyc.item()) == 0:
+                # which of my halo rows changed — decided on the device, one small gather tells every rank everything
+                flags = torch.zeros(2, dtype=torch.int32, device=dev)
+                if self.open & OPEN_TOP:
+                    flags[0] = (old_top != fnf[0]).any()
+                if self.open & OPEN_BOTTOM:
+                    flags[1] = (old_bot != fnf[self.rows + 1]).any()
+                allf = comm.all_gather(flags).cpu().numpy()
+                if not allf.any():
                     break
+                ch = int(allf[comm.rank, 0]) | (int(allf[comm.rank, 1]) << 1)
                 if ch:
                     self._call("ms_band_nf_solve_dev", self.h, _p(self.dem), _p(self.out["filled"]), _p(self.out["fnf"]),
                                self.short, self.diag, cap_bound, cap, 1, ch, ctypes.byref(visits), st)
                     total_visits += visits.value
+            self._tick("nf_exchange_loop")
             nv = i64(0)
             self._call("ms_band_nf_verify_dev", self.h, _p(self.dem), _p(self.out["fnf"]), self.short, self.diag,
                        ctypes.byref(nv), st)
             bad = comm.all_reduce(torch.tensor([nv.value], dtype=torch.int64, device=dev), "sum")
+            self._tick("nf_verify")
             self.stats.update(noflat_exchanges=sweeps, noflat_tile_visits=total_visits, noflat_capped=cap)
             if int(bad.item()) == 0:
                 return
