@@ -259,3 +259,26 @@ def test_pipeline_matches_functions():
     assert np.array_equal(h["ppmin_row"].numpy()[:m], mi["row"]) and np.array_equal(h["ppmin_col"].numpy()[:m], mi["col"])
     ma = port.label_max_index(acc, lab, n)
     assert np.array_equal(h["ppmax_row"].numpy()[:m], ma["row"]) and np.array_equal(h["ppmax_col"].numpy()[:m], ma["col"])
+
+
+# ---------------------------------------------------------------- sizes beyond the CPU oracle: certificates
+def test_certificates_4096():
+    """at sizes where the CPU oracle is impractical the results are certified by size-independent
+    properties (tools/big_check.py): fixed point from above (fill), the library's verification stencil (no-flats),
+    acc == 1 + sum of inflows with terminal sums == N, ws == label or ws(downstream).  The same tool certifies
+    32768 x 32768 (BASELINE config 3) in profiles/."""
+    import importlib.util
+    import os
+    import torch
+    from malstroem_b200.pipeline import RasterPipeline, synth_fractal
+    spec = importlib.util.spec_from_file_location(
+        "big_check", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "big_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    p = RasterPipeline(4096, 3072)
+    synth_fractal(4096, 3072, seed=7, out=p.dem)
+    p.run()
+    torch.cuda.synchronize()
+    bad_fill, bad_acc, bad_ws, root_sum = mod.certify(p, CH=1024)
+    assert (bad_fill, bad_acc, bad_ws) == (0, 0, 0) and root_sum == 4096 * 3072
+    assert p.stats["noflat_reverify"] == 0
