@@ -93,3 +93,49 @@ def pathological_dem(rows, cols, seed=1):
         mm = np.where(inside, level, mm)
     mm[rows // 3: rows // 3 + max(2, rows // 16), :] = 100000  # raster-wide flat strip
     return mm.astype(np.float32) * np.float32(0.001)
+
+
+def pathological_dem(rows, cols, seed=3):
+    """BASELINE config 5 in small: stepped plateaus (large exact flats), concentric nested craters (depressions inside
+    depressions, 6 levels) centred on rows k*rows/4 so that they straddle band edges, a spiral channel at one exact
+    elevation (the longest geodesic one can fold into a square: stresses the no-flats wave and makes the capped fast
+    path fail over to the generic one), and a flat running the whole width of the raster.  Integer millimetres ->
+    float32, like fractal_dem."""
+    y, x = np.mgrid[0:rows, 0:cols].astype(np.int64)
+    mm = 60000 + 25 * (x + 2 * y)                         # a gentle plane, 25 mm per cell
+    mm += (fractal_mm(rows, cols, seed=seed) - 100000) // 40
+    mm = (mm // 2000) * 2000 + np.minimum(mm % 2000, 300)  # plateaus: 300 mm of slope, then an exact flat
+    # nested craters
+    for k in (1, 2, 3):
+        cy, cx = k * rows // 4, (k * 2 - 1) * cols // 6
+        r = np.sqrt((y - cy) ** 2 + (x - cx) ** 2)
+        rad = min(rows, cols) // 7
+        inside = r < rad
+        ring = (r / max(rad / 12.0, 1.0)).astype(np.int64)           # 12 rings
+        depth = np.where(ring % 2 == 0, 6000 + 700 * (11 - ring), 2500 + 300 * (11 - ring))   # moats and rims alternate
+        mm = np.where(inside, mm[cy, cx] - depth, mm)
+    # a flat across the whole raster
+    band = (y >= rows * 5 // 8) & (y < rows * 5 // 8 + 6)
+    mm = np.where(band, 30000, mm)
+    # spiral channel, one cell wide, pitch 3, at one exact elevation; its outer end opens to the raster border
+    s0 = min(rows, cols) // 3
+    cy, cx = rows // 8 + s0 // 2, cols - s0 // 2 - 4
+    lo = mm.min() - 5000
+    yy, xx, step, d = cy, cx, 1, 0
+    path = [(yy, xx)]
+    moves = ((0, 1), (1, 0), (0, -1), (-1, 0))
+    while step * 3 < s0:
+        for _ in range(2):
+            dy, dx = moves[d % 4]
+            for _ in range(step * 3):
+                yy += dy
+                xx += dx
+                path.append((yy, xx))
+            d += 1
+        step += 1
+    py = np.clip(np.array([q[0] for q in path]), 1, rows - 2)
+    px = np.clip(np.array([q[1] for q in path]), 1, cols - 2)
+    mm[py, px] = lo
+    # the outer end drains off the right border
+    mm[py[-1], px[-1]:] = lo - 1000
+    return (mm.astype(np.float32) * np.float32(0.001)).astype(np.float32)

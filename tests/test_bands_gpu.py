@@ -77,3 +77,49 @@ def test_bands_lake_across_every_edge():
         finally:
             for p in pipes:
                 p.close()
+
+
+def test_pathological_single_and_banded():
+    """BASELINE config 5 in small (synth.pathological_dem): exact plateaus (79 % of the cells are lake / flat),
+    nested craters on the band edges, a raster-wide flat and a spiral channel with a 9500-step geodesic, on one GPU
+    and in bands."""
+    from malstroem_b200.pipeline import RasterPipeline
+    dem = synth.pathological_dem(768, 512)
+    want = oracle_all(dem)
+    p = RasterPipeline(768, 512)
+    h = p.run_host(dem)
+    for name in ("filled", "depths", "fnf", "flowdir", "accum", "labels", "wsheds"):
+        assert np.array_equal(h[name].numpy(), want[name]), name
+    assert p.nlabels == want["n"]
+    for nb in (2, 3):
+        pipes = bands.run_threaded(torch.from_numpy(dem).cuda(), nb)
+        try:
+            check(pipes, want)
+        finally:
+            for q in pipes:
+                q.close()
+
+
+def test_pathological_float64_form_falls_back():
+    """With the integer tile form switched off (MS_NF_INT=0, read once per process, hence the subprocess) the capped
+    float64 form cannot carry the spiral's wave past the cap: the verification stencil must reject it and the
+    generic solve must deliver the reference's bits."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import numpy as np\n"
+        "from malstroem_b200 import synth\n"
+        "from malstroem_b200.pipeline import RasterPipeline\n"
+        "from oracle import port\n"
+        "dem = synth.pathological_dem(768, 512)\n"
+        "p = RasterPipeline(768, 512)\n"
+        "h = p.run_host(dem)\n"
+        "short, diag = port.minimum_safe_short_and_diag(dem)\n"
+        "assert np.array_equal(h['fnf'].numpy(), port.fill_terrain_no_flats(dem, short, diag))\n"
+        "assert p.stats['noflat_reverify'] >= 1, p.stats\n"
+        "print('fallback ok', p.stats)\n")
+    env = dict(os.environ, MS_NF_INT="0", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "fallback ok" in r.stdout, r.stdout + r.stderr
