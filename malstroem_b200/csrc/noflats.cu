@@ -195,7 +195,7 @@ struct RelaxF64 {
 // to exactly dq ulps more, so the relaxation is an integer chamfer distance transform.  Cells that
 // cannot change (seeds, the raster border, cells outside the raster) are walls; they were taken into account as
 // sources once, by k_nf_seedcand.
-constexpr int NF_ILD = NF_T + 3;          // shared row stride in ints
+constexpr int NF_ILD = NF_T + 8;          // shared row stride in ints: even (64-bit pair loads), 8 banks per row
 constexpr int D_INF = 0x3fffffff;         // lake cell not reached yet
 constexpr int D_WALL = 0x40000000;        // not updatable, not a source
 constexpr int D_LIMIT = 0x20000000;       // a tile whose distances get this large is left to the float64 form
@@ -233,9 +233,12 @@ struct RelaxI32 {
         for (int it = 0;; it++) {
             bool ch = false;
             if (live) {
-                int a0 = p[-NF_ILD - 1], a1 = p[-NF_ILD], a2 = p[-NF_ILD + 1], a3 = p[-NF_ILD + 2];
-                int l = p[-1], r = p[2];
-                int c0 = p[NF_ILD - 1], c1 = p[NF_ILD], c2 = p[NF_ILD + 1], c3 = p[NF_ILD + 2];
+                // the 3 x 4 window as six aligned pairs (the own cells are re-read with their neighbours)
+                const int2 ua = *reinterpret_cast<const int2 *>(p - NF_ILD - 1), ub = *reinterpret_cast<const int2 *>(p - NF_ILD + 1);
+                const int2 ma = *reinterpret_cast<const int2 *>(p - 1), mb = *reinterpret_cast<const int2 *>(p + 1);
+                const int2 da = *reinterpret_cast<const int2 *>(p + NF_ILD - 1), db = *reinterpret_cast<const int2 *>(p + NF_ILD + 1);
+                const int a0 = ua.x, a1 = ua.y, a2 = ub.x, a3 = ub.y, l = ma.x, r = mb.y;
+                const int c0 = da.x, c1 = da.y, c2 = db.x, c3 = db.y;
                 if (w0 <= D_INF) {
                     int m = min(imin4(a0, a2, c0, c2) + dq, imin4(a1, l, w1, c1) + sq);
                     if (m < w0) { w0 = m; p[0] = m; ch = true; if (m >= D_LIMIT) *overflow = 1; }
@@ -263,6 +266,7 @@ struct NfTileShared {
     int ring;          // bit 0/1/2/3: the tile's top / bottom / left / right ring changed
     int nb;            // neighbour tiles to queue: bit (dy+1)*3 + (dx+1)
     int grab[3];       // next dirty block to hand out (per iteration, rotating like `dirty`)
+    int midflush;      // forward ring changes before the tile has settled (only while CTAs are idle)
     unsigned char blist[64];   // the dirty blocks of the current iteration
     int2 wtab[NF_NBIN];
     int k;             // ticket
@@ -333,7 +337,7 @@ __device__ inline int nf_tile_iterate(const R &rx, NfTileShared &S, F &flush) {
             if (rings) atomicOr(&S.ring, rings);
         }
         __syncthreads();
-        if (NF_MIDFLUSH && S.ring && (NF_FLUSH_ALWAYS || ((it + 1) & it) == 0)) flush();
+        if (NF_MIDFLUSH && S.midflush && S.ring && (NF_FLUSH_ALWAYS || ((it + 1) & it) == 0)) flush();
     }
     if (S.chgmask) flush();
     return it;
@@ -439,6 +443,8 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                 S.ring = 0;
                 S.nb = 0;
                 S.grab[0] = S.grab[1] = S.grab[2] = 0;
+                // NF_MIDFLUSH 1: always; 2: only while fewer tiles are queued or running than there are CTAs
+                S.midflush = NF_MIDFLUSH == 1 || (NF_MIDFLUSH == 2 && *(volatile int *)&ctl->pending < (int)gridDim.x);
                 S.e = INT_MIN;
                 S.elo = INT_MAX;
                 S.bad = 0;
