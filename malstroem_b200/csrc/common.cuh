@@ -142,6 +142,8 @@ __device__ __constant__ const int kDC[8] = {0, 1, 1, 1, 0, -1, -1, -1};
 // ---- shared device primitives (scan.cu, forest.cu) ----------------------------------------------
 // exclusive scan of int32 flags; out may alias flags; *total_dev receives the sum (int64 on device)
 int exclusive_scan_i32(const int *flags, int *out, int64_t n, int64_t *total_dev, cudaStream_t s);
+// the same over the flags "ptr[i] == i" (roots of a parent-pointer array); out must not alias ptr
+int exclusive_scan_selfptr(const int *ptr, int *out, int64_t n, int64_t *total_dev, cudaStream_t s);
 // pointer jumping on a forest given as parent indices (roots point to themselves); in place.
 // rounds_out (host, optional) receives the number of rounds.  MS_ERR_NOCONV after 64 rounds (cycles).
 int forest_resolve(int *ptr, int64_t n, int64_t *rounds_out, cudaStream_t s);

@@ -5,14 +5,17 @@
 // the raster border, i.e. W(c) = the lowest "highest cell" over all paths from c to the border.  Only
 // min/max of input values are involved, so any algorithm that reaches the fixed point is bit-exact.
 //
-//   1. k_descent      every interior cell points at the smallest cell of its 3x3 window in the strict
-//                     total order (z, flat index); border cells point at cell 0 ("outside")
-//   2. forest_resolve pointer jumping -> every cell knows the local minimum ("catchment") it drains to
-//   3. scan           dense catchment ids (0 = outside)
+//   1. k_descent_tile every interior cell points at the smallest cell of its 3x3 window in the strict
+//                     total order (z, flat index); border cells point at cell 0 ("outside"); in-tile paths are
+//                     compressed in shared memory
+//   2. forest_resolve_list  pointer jumping for the cells whose path leaves their tile -> every cell knows the
+//                     local minimum ("catchment") it drains to
+//   3. scan           dense catchment ids (0 = outside), straight from the root pointers
 //   4. Boruvka rounds on the catchment graph (edge weight = max(z_a, z_b) over adjacent cells of two
 //                     catchments): every component not yet merged with "outside" finds its lowest
-//                     outgoing edge (one raster pass, 64-bit atomicMin of (weight, edge id)), hooks to
-//                     the other side, and every catchment in it raises E = max(E, that weight).
+//                     outgoing edge (64-bit atomicMin of (weight, edge id); round 1 over the raster, later rounds
+//                     over the cells that still border another component), hooks to the other side, and every
+//                     catchment in it raises E = max(E, that weight).
 //                     Claim: when the component reaches "outside", E is the catchment's
 //                     spill elevation.
 //   5. k_fill_final   filled = max(z, E[catchment]), depths = filled - z
@@ -78,34 +81,9 @@ int minmax_dev(const float *z, int64_t n, float *out2, cudaStream_t s) {
 }
 
 // ---- K1 -------------------------------------------------------------------------------------------
-// `open` (row bands): bit 0 / 1 = the first / last row is not the raster border but continues in another band;
-// its cells are ordinary cells whose window is clipped to the band (a catchment never crosses a band edge).
-__global__ void __launch_bounds__(256) k_descent(const float *__restrict__ z, int *__restrict__ ptr, int rows,
-                                                 int cols, int open) {
-    int c = blockIdx.x * 64 + (threadIdx.x & 63);
-    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (r >= rows || c >= cols) return;
-    int i = r * cols + c;
-    if ((r == 0 && !(open & 1)) || c == 0 || (r == rows - 1 && !(open & 2)) || c == cols - 1) {
-        ptr[i] = 0;
-        return;
-    }
-    float bz = z[i];
-    int bi = i;
-#pragma unroll
-    for (int dr = -1; dr <= 1; dr++)
-#pragma unroll
-        for (int dc = -1; dc <= 1; dc++) {
-            if (dr == 0 && dc == 0) continue;
-            if (r + dr < 0 || r + dr >= rows) continue;
-            int j = i + dr * cols + dc;
-            float zj = __ldg(z + j);
-            if (zj < bz || (zj == bz && j < bi)) { bz = zj; bi = j; }
-        }
-    ptr[i] = bi;
-}
-
-// Tile form of k_descent + most of the pointer jumping: a CTA holds a 64x64 tile of z (+ apron) in shared memory,
+// `open` (row bands): bit 0 / 1 = the first / last row is not the raster border but continues in another band; its
+// cells are ordinary cells whose window is clipped to the band (a catchment never crosses a band edge).
+// Descent pointers + most of the pointer jumping: a CTA holds a 64x64 tile of z (+ apron) in shared memory,
 // finds every cell's pointer, compresses the in-tile paths by pointer doubling, and writes for every cell the
 // GLOBAL index its tile-local root stands for: itself (a local minimum), 0 (raster border = "outside"), or - when
 // the root's lowest neighbour lies in another tile - that neighbour.  Only cells of the last kind still need global
@@ -176,11 +154,6 @@ __global__ void __launch_bounds__(256) k_descent_tile(const float *__restrict__ 
 #pragma unroll 4
     for (int u = 0; u < 16; u++)
         if (mine[u] >= 0) list[pos++] = mine[u];
-}
-
-__global__ void __launch_bounds__(256) k_rootflag(const int *ptr, int *flag, int64_t n) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flag[i] = (ptr[i] == (int)i) ? 1 : 0;
 }
 
 // lab[i] = cid[ptr[i]], written over ptr (each thread only overwrites its own slot; cid is separate)
@@ -462,8 +435,7 @@ int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_
 
     int64_t jump_rounds = 0;
     MS_TRY(descent_resolve(dtm, lab.p, tmp.p, rows, cols, 0, &jump_rounds, s));
-    MS_LAUNCH(k_rootflag, g1, 256, 0, s, lab.p, tmp.p, n);
-    MS_TRY(exclusive_scan_i32(tmp.p, tmp.p, n, total.p, s));
+    MS_TRY(exclusive_scan_selfptr(lab.p, tmp.p, n, total.p, s));
     MS_LAUNCH(k_catchment_ids, g1, 256, 0, s, lab.p, tmp.p, n);
     MS_CUDA(cudaMemcpyAsync(h, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
@@ -636,8 +608,7 @@ int fill_band_local(ms_band *B, const float *dem, int64_t *n_frozen, cudaStream_
     unsigned g1 = cdiv(n, 256);
     int64_t *h = host_flags().h;
     MS_TRY(descent_resolve(dem, lab, tmp.p, rows, cols, B->open, nullptr, s));
-    MS_LAUNCH(k_rootflag, g1, 256, 0, s, lab, tmp.p, n);
-    MS_TRY(exclusive_scan_i32(tmp.p, tmp.p, n, total.p, s));
+    MS_TRY(exclusive_scan_selfptr(lab, tmp.p, n, total.p, s));
     MS_LAUNCH(k_catchment_ids, g1, 256, 0, s, lab, tmp.p, n);
     MS_CUDA(cudaMemcpyAsync(h, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));

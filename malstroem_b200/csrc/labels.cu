@@ -16,17 +16,6 @@ namespace ms {
 template <typename T>
 __device__ inline bool is_fg(T v) { return v != (T)0; }
 
-template <typename T>
-__global__ void __launch_bounds__(256) k_cc_init(const T *__restrict__ data, int *__restrict__ parent, int rows,
-                                                 int cols) {
-    int c = blockIdx.x * 64 + (threadIdx.x & 63);
-    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (r >= rows || c >= cols) return;
-    int i = r * cols + c;
-    if (!is_fg(data[i])) { parent[i] = -1; return; }
-    parent[i] = (c > 0 && is_fg(data[i - 1])) ? i - 1 : i;     // runs along a row are pre-linked
-}
-
 __device__ inline int cc_find(const int *parent, int x) {
     int p = __ldcg(parent + x);
     while (p != x) { x = p; p = __ldcg(parent + x); }
@@ -42,23 +31,6 @@ __device__ inline void cc_union(int *parent, int a, int b) {
         int old = atomicMin(parent + b, a);      // b was a root: hang it under the smaller root a
         if (old == b) return;
         b = old;                                  // somebody re-parented b meanwhile: retry from there
-    }
-}
-
-__global__ void __launch_bounds__(256) k_cc_merge(int *parent, int rows, int cols) {
-    int c = blockIdx.x * 64 + (threadIdx.x & 63);
-    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (r >= rows || c >= cols || r == 0) return;
-    int i = r * cols + c;
-    if (parent[i] < 0) return;
-    int up = i - cols;
-    if (parent[up] >= 0) {
-        // N is foreground: NW and NE (if foreground) are row-linked to N already
-        // only the first cell of a run, or a cell whose NW is background, adds information
-        if (c == 0 || parent[i - 1] < 0 || parent[up - 1] < 0) cc_union(parent, i, up);
-    } else {
-        if (c > 0 && parent[up - 1] >= 0) cc_union(parent, i, up - 1);
-        if (c < cols - 1 && parent[up + 1] >= 0) cc_union(parent, i, up + 1);
     }
 }
 
@@ -174,7 +146,7 @@ __global__ void __launch_bounds__(256) k_cc_flatten(int *parent, int *flag, int6
         if (root != p) parent[i] = root;
         f = (root == (int)i);
     }
-    flag[i] = f;
+    if (flag) flag[i] = f;
 }
 
 __global__ void __launch_bounds__(256) k_cc_number(const int *__restrict__ parent, const int *__restrict__ rank,
@@ -197,8 +169,8 @@ int cc_dev_t(const T *data, int32_t *labels, int64_t rows, int64_t cols, int64_t
     prof_units(n);
     MS_LAUNCH(k_cc_tile<T>, tiles_x * tiles_y, 256, 0, s, data, parent.p, (int)rows, (int)cols, tiles_x);
     MS_LAUNCH(k_cc_border, g2, 256, 0, s, parent.p, (int)rows, (int)cols);
-    MS_LAUNCH(k_cc_flatten, g1, 256, 0, s, parent.p, flag.p, n);
-    MS_TRY(exclusive_scan_i32(flag.p, flag.p, n, nlabels_dev, s));
+    MS_LAUNCH(k_cc_flatten, g1, 256, 0, s, parent.p, (int *)nullptr, n);
+    MS_TRY(exclusive_scan_selfptr(parent.p, flag.p, n, nlabels_dev, s));
     MS_LAUNCH(k_cc_number, g1, 256, 0, s, parent.p, flag.p, labels, n);
     return MS_OK;
 }
@@ -422,6 +394,11 @@ __device__ inline unsigned long long grp_max(unsigned m, unsigned long long v) {
 }
 
 __device__ inline double grp_sum(unsigned m, double v) {
+    if (m == 0xffffffffu) {              // the whole warp holds one label (inside a bluespot): butterfly
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
     double s = 0.0;
     unsigned rest = m;
     while (rest) {                       // lane order = raster order inside the group

@@ -528,6 +528,9 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                     }
                 }
             }
+#ifdef NF_STATS
+            long long tl1 = clock64();
+#endif
             dmax = __reduce_max_sync(0xffffffffu, dmax);
             elo = __reduce_min_sync(0xffffffffu, elo);
             ehi = __reduce_max_sync(0xffffffffu, ehi);
@@ -541,6 +544,9 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                 if (bad) S.bad = 1;
             }
             __syncthreads();
+#ifdef NF_STATS
+            if (tid == 0) { atomicAdd(&g_nf_dbg[13], (unsigned long long)(tl1 - tc0)); atomicAdd(&g_nf_dbg[14], (unsigned long long)(clock64() - tl1)); }
+#endif
             bool ok = !S.bad && (S.e == INT_MIN || S.e - S.elo < NF_NBIN) && S.dmax < D_LIMIT;
 #ifdef NF_STATS
             if (tid == 0 && !S.bad && !ok) atomicAdd(&g_nf_dbg[9], 1ull);
@@ -748,6 +754,86 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
     }
 }
 
+// k_nf_init + k_nf_seedcand in one pass (single-GPU capped path): a CTA holds z and F of a 64x64 tile with a 2-cell
+// apron, works out which cells of the tile and of its 1-cell ring are seeds, and writes W for the tile: z on the
+// raster border and for seeds; for a lake / flat cell the best candidate its fixed neighbours (seeds, border cells:
+// W = z there) offer, unless that lies above F + capB, else +inf.  (Row bands keep the two-kernel form: the seed
+// test of a halo-row cell would need a second halo row.)
+constexpr int NI_A = NF_T + 4;          // tile + 2-cell apron
+
+__global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ z, const float *__restrict__ F,
+                                                      double *__restrict__ W, int *tileflag, int *tilesides, NfCtl *ctl,
+                                                      int rows, int cols, int tiles_x, double sh, double dg, double capB) {
+    __shared__ float sz[NI_A * NI_A], sf[NI_A * NI_A];
+    __shared__ unsigned char fixedc[(NF_T + 2) * (NF_T + 2)];      // 1: W = z there for good (seed or raster border)
+    __shared__ int s_sides;
+    int tile = blockIdx.x;
+    int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    int r0 = ty * NF_T, c0 = tx * NF_T, tid = threadIdx.x;
+    if (tid == 0) s_sides = 0;
+    for (int k = tid; k < NI_A * NI_A; k += 256) {
+        int lr = k / NI_A, lc = k - lr * NI_A;
+        int r = r0 + lr - 2, c = c0 + lc - 2;
+        bool in = r >= 0 && r < rows && c >= 0 && c < cols;
+        sz[k] = in ? z[(size_t)r * cols + c] : INFINITY;
+        sf[k] = in ? F[(size_t)r * cols + c] : INFINITY;
+    }
+    __syncthreads();
+    for (int k = tid; k < (NF_T + 2) * (NF_T + 2); k += 256) {
+        int lr = k / (NF_T + 2), lc = k - lr * (NF_T + 2);          // ring coordinates: cell (r0 + lr - 1, c0 + lc - 1)
+        int r = r0 + lr - 1, c = c0 + lc - 1;
+        unsigned char fx = 0;
+        if (r >= 0 && r < rows && c >= 0 && c < cols) {
+            if (r == 0 || c == 0 || r == rows - 1 || c == cols - 1) fx = 1;
+            else {
+                const float *pf = sf + (lr + 1) * NI_A + (lc + 1);
+                float f = *pf;
+                float m = fminf(fminf(fminf(pf[-NI_A - 1], pf[-NI_A]), fminf(pf[-NI_A + 1], pf[-1])),
+                                fminf(fminf(pf[1], pf[NI_A - 1]), fminf(pf[NI_A], pf[NI_A + 1])));
+                fx = (f == sz[(lr + 1) * NI_A + (lc + 1)]) && (m < f);
+            }
+        }
+        fixedc[k] = fx;
+    }
+    __syncthreads();
+    int nonseed = 0, sides = 0;
+    for (int k = tid; k < NF_T * NF_T; k += 256) {
+        int lr = k >> 6, lc = k & 63;
+        int r = r0 + lr, c = c0 + lc;
+        if (r >= rows || c >= cols) continue;
+        const unsigned char *fx = fixedc + (lr + 1) * (NF_T + 2) + (lc + 1);
+        const float *pz = sz + (lr + 2) * NI_A + (lc + 2);
+        double w;
+        if (*fx) {
+            w = (double)*pz;
+        } else {
+            double best = INFINITY;
+#pragma unroll
+            for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+                for (int dc = -1; dc <= 1; dc++) {
+                    if (dr == 0 && dc == 0) continue;
+                    if (!fx[dr * (NF_T + 2) + dc]) continue;
+                    double cand = __dadd_rn((double)pz[dr * NI_A + dc], (dr != 0 && dc != 0) ? dg : sh);
+                    best = dmin2(best, cand);
+                }
+            w = (best <= (double)sf[(lr + 2) * NI_A + (lc + 2)] + capB) ? best : (double)INFINITY;
+            nonseed++;
+            sides |= (lr == 0 ? 1 : 0) | (lr == NF_T - 1 || r == rows - 2 ? 2 : 0) | (lc == 0 ? 4 : 0) |
+                     (lc == NF_T - 1 || c == cols - 2 ? 8 : 0);
+        }
+        W[(size_t)r * cols + c] = w;
+    }
+    if (sides) atomicOr(&s_sides, sides);
+    int cnt = __syncthreads_count(nonseed > 0);
+    nonseed = 0;
+    (void)nonseed;
+    if (tid == 0 && cnt) {
+        tileflag[tile] = 16;
+        tilesides[tile] = s_sides;
+    }
+}
+
 // CAP only: the one time seeds (and the raster border) act as sources.  A lake / flat cell (still +inf) takes the
 // best candidate its fixed neighbours offer, unless that lies above F + capB.  A neighbour is fixed iff W == F
 // there (seed: W = z = F; border: W = z = F); lake cells hold +inf or, once written by this kernel, a value > F.
@@ -889,11 +975,14 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
         MS_CUDA(cudaMemsetAsync(tilesides.p, 0, (size_t)ntiles * sizeof(int), s));
         MS_CUDA(cudaMemsetAsync(ring.p, 0xff, (size_t)cap_ring * sizeof(int), s));
         MS_CUDA(cudaMemsetAsync(ctl.p, 0, sizeof(NfCtl), s));
-        MS_LAUNCH(k_nf_init, g2, 256, 0, s, dtm, filled, out, banned.p, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols,
-                  tiles_x, 0);
+        if (cap)
+            MS_LAUNCH(k_nf_init_tile, ntiles, 256, 0, s, dtm, filled, out, tileflag.p, tilesides.p, ctl.p, (int)rows,
+                      (int)cols, tiles_x, sh, dg, cap_bound);
+        else
+            MS_LAUNCH(k_nf_init, g2, 256, 0, s, dtm, filled, out, banned.p, tileflag.p, tilesides.p, ctl.p, (int)rows,
+                      (int)cols, tiles_x, 0);
         MS_LAUNCH(k_nf_compact, cdiv(ntiles, 256), 256, 0, s, tileflag.p, ring.p, ctl.p, ntiles);
         if (cap) {
-            MS_LAUNCH(k_nf_seedcand, g2, 256, 0, s, filled, out, ctl.p, (int)rows, (int)cols, sh, dg, cap_bound, 0);
             MS_TRY(nf_launch_solve<true>(filled, out, ring.p, cap_ring, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols, tiles_x,
                                          tiles_y, ntiles, sh, dg, g_nf_use_int, cap_bound, 0, n, s));
         } else {

@@ -43,4 +43,5 @@ log = log[: 4 * k].reshape(k, 4)
 os.makedirs("gpurun_out", exist_ok=True)
 np.save("gpurun_out/nf_log_%d.npy" % S, log)
 print("logged", k, "visits")
+print("load phase: warp0 loads+convert %d cyc, reduce+sync %d cyc (means per visit)" % (out[13] // max(st[1], 1), out[14] // max(st[1], 1)))
 print("sample out-of-range cell: W=%r F=%r count=%d" % (np.array([out[13]], dtype=np.uint64).view(np.float64)[0], np.array([out[14]], dtype=np.uint64).view(np.float64)[0], out[12]))
