@@ -15,54 +15,57 @@ DR = (-1, -1, 0, 1, 1, 1, 0, -1)
 DC = (0, 1, 1, 1, 0, -1, -1, -1)
 
 
-def certify(p, CH=2048):
-  """Certificates on a finished RasterPipeline `p` (square or not): returns (fill, accum, watershed violations, terminal sum)."""
-  S_rows, S = p.rows, p.cols
-  dem, filled, acc, fd, lab, ws = p.dem, p.out["filled"], p.out["accum"], p.out["flowdir"], p.out["labels"], p.out["wsheds"]
-  bad_fill = bad_acc = bad_ws = 0
-  root_sum = 0.0
-  for r0 in range(0, S_rows, CH):
-      r1 = min(S_rows, r0 + CH)
-      a0, a1 = max(r0 - 1, 0), min(r1 + 1, S_rows)
-      F = filled[a0:a1]; Z = dem[a0:a1]; A = acc[a0:a1]; D = fd[a0:a1].long(); Wl = ws[a0:a1]; Lb = lab[a0:a1]
-      o0, o1 = r0 - a0, r0 - a0 + (r1 - r0)                   # own rows inside the padded chunk
-      Fo, Zo = F[o0:o1], Z[o0:o1]
-      bad_fill += int((Fo < Zo).sum())
-      inner = torch.zeros_like(Fo, dtype=torch.bool)
-      rr = torch.arange(r0, r1, device=F.device).view(-1, 1)
-      cc = torch.arange(S, device=F.device).view(1, -1)
-      interior = (rr > 0) & (rr < S_rows - 1) & (cc > 0) & (cc < S - 1)
-      bad_fill += int(((Fo != Zo) & ~interior).sum())
-      upstream = torch.ones_like(A[o0:o1])
-      wsdown = torch.zeros_like(Wl[o0:o1])
-      moves = torch.zeros_like(interior)
-      for q in range(8):
-          # neighbour in direction q of every own cell (where it exists)
-          rs, cs = DR[q], DC[q]
-          ro0, ro1 = o0 + rs, o1 + rs
-          src_r0, src_r1 = max(ro0, 0), min(ro1, F.shape[0])
-          dst_r0 = src_r0 - ro0
-          dst_r1 = dst_r0 + (src_r1 - src_r0)
-          c_src0, c_src1 = max(cs, 0), S + min(cs, 0)
-          c_dst0, c_dst1 = max(-cs, 0), S + min(-cs, 0)
-          if src_r1 <= src_r0:
-              continue
-          nbF = F[src_r0:src_r1, c_src0:c_src1]
-          own = (slice(dst_r0, dst_r1), slice(c_dst0, c_dst1))
-          raised = (Fo[own] > Zo[own]) & interior[own]
-          bad_fill += int((raised & (nbF < Fo[own])).sum())
-          # accumulation: neighbour q flows into me iff its code is (q + 4) % 8
-          into = D[src_r0:src_r1, c_src0:c_src1] == ((q + 4) & 7)
-          upstream[own] += torch.where(into, A[src_r0:src_r1, c_src0:c_src1], torch.zeros_like(upstream[own]))
-          # watersheds: my downstream cell is neighbour q iff my code is q
-          mine = D[o0:o1][own] == q
-          wsdown[own] = torch.where(mine, Wl[src_r0:src_r1, c_src0:c_src1], wsdown[own])
-          moves[own] |= mine
-      bad_acc += int((upstream != A[o0:o1]).sum())
-      root_sum += float(A[o0:o1][~moves].sum())
-      want = torch.where(Lb[o0:o1] != 0, Lb[o0:o1], torch.where(moves, wsdown, torch.zeros_like(wsdown)))
-      bad_ws += int((want != Wl[o0:o1]).sum())
-  return bad_fill, bad_acc, bad_ws, root_sum
+def certify(p, CH=2048, skip_top=0, skip_bottom=0):
+    """Certificates on a finished RasterPipeline (or on one band of a BandPipeline: then the first / last own row,
+    whose neighbours live in another band, is skipped with skip_top / skip_bottom = 1 and the terminal sum has no
+    meaning).  Returns (fill violations, accumulation violations, watershed violations, terminal sum)."""
+    R, C = p.rows, p.cols
+    dem, filled, acc, fd, lab, ws = p.dem, p.out["filled"], p.out["accum"], p.out["flowdir"], p.out["labels"], p.out["wsheds"]
+    dev = dem.device
+    bad_fill = bad_acc = bad_ws = 0
+    root_sum = 0.0
+    cc = torch.arange(C, device=dev).view(1, -1)
+    for r0 in range(0, R, CH):
+        r1 = min(R, r0 + CH)
+        a0, a1 = max(r0 - 1, 0), min(r1 + 1, R)
+        F, Z, A, D = filled[a0:a1], dem[a0:a1], acc[a0:a1], fd[a0:a1].long()
+        Wl, Lb = ws[a0:a1], lab[a0:a1]
+        o0, o1 = r0 - a0, r0 - a0 + (r1 - r0)                   # own rows inside the padded chunk
+        Fo, Zo, Ao, Do, Wo, Lo = F[o0:o1], Z[o0:o1], A[o0:o1], D[o0:o1], Wl[o0:o1], Lb[o0:o1]
+        rr = torch.arange(r0, r1, device=dev).view(-1, 1)
+        keep = ((rr >= skip_top) & (rr < R - skip_bottom)).expand(r1 - r0, C)
+        border = (rr == 0) | (rr == R - 1) | (cc == 0) | (cc == C - 1)
+        if skip_top:
+            border = border & ~((rr == 0) & (cc > 0) & (cc < C - 1))
+        if skip_bottom:
+            border = border & ~((rr == R - 1) & (cc > 0) & (cc < C - 1))
+        bad_fill += int(((Fo < Zo) & keep).sum())
+        bad_fill += int(((Fo != Zo) & border & keep).sum())
+        upstream = torch.ones_like(Ao)
+        wsdown = torch.zeros_like(Wo)
+        moves = torch.zeros_like(keep)
+        for q in range(8):
+            # the neighbour in direction q of every own cell, where it exists inside the padded chunk
+            rs, cs = DR[q], DC[q]
+            src_r0, src_r1 = max(o0 + rs, 0), min(o1 + rs, F.shape[0])
+            if src_r1 <= src_r0:
+                continue
+            dst_r0 = src_r0 - (o0 + rs)
+            dst_r1 = dst_r0 + (src_r1 - src_r0)
+            own = (slice(dst_r0, dst_r1), slice(max(-cs, 0), C + min(-cs, 0)))
+            nb = (slice(src_r0, src_r1), slice(max(cs, 0), C + min(cs, 0)))
+            raised = (Fo[own] > Zo[own]) & ~border[own] & keep[own]
+            bad_fill += int((raised & (F[nb] < Fo[own])).sum())
+            into = D[nb] == ((q + 4) & 7)                              # that neighbour flows into me
+            upstream[own] += torch.where(into, A[nb], torch.zeros_like(upstream[own]))
+            mine = Do[own] == q                                        # I flow into that neighbour
+            wsdown[own] = torch.where(mine, Wl[nb], wsdown[own])
+            moves[own] |= mine
+        bad_acc += int(((upstream != Ao) & keep).sum())
+        root_sum += float(Ao[~moves].sum())
+        want = torch.where(Lo != 0, Lo, torch.where(moves, wsdown, torch.zeros_like(wsdown)))
+        bad_ws += int(((want != Wo) & keep).sum())
+    return bad_fill, bad_acc, bad_ws, root_sum
 
 
 if __name__ == "__main__":
