@@ -9,12 +9,13 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-p = bands.BandPipeline(world * S, S, bands.DistComm(), device=local)
-synth_fractal(S, S, seed=1, row0=rank * S, col0=0, device=local, out=p.dem)
-for _ in range(3):
+C = int(sys.argv[2]) if len(sys.argv) > 2 else S
+p = bands.BandPipeline(world * S, C, bands.DistComm(), device=local)
+synth_fractal(S, C, seed=1, row0=rank * S, col0=0, device=local, out=p.dem)
+for _ in range(2):
     p.run()
 p.timing = {}
-reps = 3
+reps = 2
 for _ in range(reps):
     p.run()
 if rank == 0:
