@@ -177,6 +177,21 @@ int ms_band_nf_solve_dev(ms_band *band, const float *dem, const float *filled, d
                          void *stream);
 int ms_band_nf_verify_dev(ms_band *band, const float *dem, const double *fnf, double short_eps, double diag_eps,
                           int64_t *nviol, void *stream);
+/* The same solve fused over NVLink peer memory: every band's solver kernel runs at the same time and the bands feed
+ * each other's tile queues and halo rows directly (system-scope atomics and stores into blocks mapped through CUDA
+ * IPC), instead of one host-driven halo exchange per crossing of a band edge.  create: allocates the band's shared
+ * block, info80 (HOST, 80 bytes) describes it; open: maps every rank's block (infos: world x 80 bytes gathered from
+ * all ranks, rows_all: own rows of every band; HOST pointers).  Per solve: init, halo exchange, seedcand, halo
+ * exchange, prepare (returns queued tiles), all ranks synchronise, arm, all ranks synchronise, solve (skip when no
+ * rank has queued tiles), halo exchange, verify. */
+int ms_band_nf_shared_create(ms_band *band, void *info80);
+int ms_band_nf_shared_open(ms_band *band, int rank, int world, const void *infos, const int64_t *rows_all);
+int ms_band_nf_seedcand_dev(ms_band *band, const float *filled, double *fnf, double short_eps, double diag_eps,
+                            double cap_bound, void *stream);
+int ms_band_nf_p2p_prepare_dev(ms_band *band, const double *fnf, int64_t *queued, void *stream);
+int ms_band_nf_p2p_arm_dev(ms_band *band, void *stream);
+int ms_band_nf_p2p_solve_dev(ms_band *band, const float *filled, double *fnf, double short_eps, double diag_eps,
+                             double cap_bound, int64_t *tile_visits, void *stream);
 
 /* flow.terrain_flowdirection (flow.py:142-167) on a band (needs the halo rows of the terrain) */
 int ms_band_flowdir_dev(ms_band *band, const double *terrain, uint8_t *flowdir, int edges_flow_outward, void *stream);

@@ -229,6 +229,23 @@ class BandPipeline(object):
                 self.out[name] = torch.empty((self.rows, self.cols), dtype=dt, device=dev)
         self.dem = self.dem_ext[1:1 + self.rows]
         self.tables, self.nlabels, self.stats = {}, 0, {}
+        self.p2p = self._p2p_setup()
+
+    def _p2p_setup(self):
+        """Bands on different GPUs of one node (torch.distributed / NCCL): map every band's no-flats solver state
+        into every rank through CUDA IPC, so that the solver kernels can feed each other over NVLink."""
+        import os
+        comm = self.comm
+        if not isinstance(comm, DistComm) or comm.size < 2 or os.environ.get("MS_BAND_P2P", "1") == "0":
+            return False
+        if comm.dist.get_backend(comm.group) != "nccl":
+            return False
+        info = np.zeros(80, dtype=np.uint8)
+        self._call("ms_band_nf_shared_create", self.h, _lib.ptr(info))
+        infos = comm.all_gather(torch.from_numpy(info).to(self.device)).cpu().numpy().copy()
+        rows_all = np.array([b - a for a, b in band_rows(self.R, comm.size)], dtype=np.int64)
+        self._call("ms_band_nf_shared_open", self.h, comm.rank, comm.size, _lib.ptr(infos), _lib.ptr(rows_all))
+        return True
 
     def close(self):
         if self.h is not None:
@@ -343,6 +360,8 @@ class BandPipeline(object):
         comm, dev, cols = self.comm, self.device, self.cols
         fnf = self.ext["fnf"]
         i64 = ctypes.c_int64
+        if self.p2p and self._noflats_p2p(st):
+            return
         for cap in (1, 0):
             ns = i64(0)
             self._call("ms_band_nf_init_dev", self.h, _p(self.dem), _p(self.out["filled"]), _p(self.out["fnf"]),
@@ -383,6 +402,43 @@ class BandPipeline(object):
                 return
         raise RuntimeError("band no-flats fill: the fixed-point verification failed (seed repair is not available in "
                            "band mode)")
+
+    def _noflats_p2p(self, st):
+        """The capped solve with all bands' solver kernels running at once and exchanging over NVLink peer memory.
+        Returns False if the verification stencil rejects the result (the host-driven generic path takes over)."""
+        comm, dev = self.comm, self.device
+        fnf = self.ext["fnf"]
+        i64 = ctypes.c_int64
+        cap_bound = float(_lib.lib().ms_nf_cap_bound(self.R, self.cols, self.diag))
+        ns = i64(0)
+        self._call("ms_band_nf_init_dev", self.h, _p(self.dem), _p(self.out["filled"]), _p(self.out["fnf"]),
+                   ctypes.byref(ns), st)
+        self._halo(fnf)
+        self._call("ms_band_nf_seedcand_dev", self.h, _p(self.out["filled"]), _p(self.out["fnf"]), self.short, self.diag,
+                   cap_bound, st)
+        self._halo(fnf)
+        self._tick("nf_init")
+        q = i64(0)
+        self._call("ms_band_nf_p2p_prepare_dev", self.h, _p(self.out["fnf"]), ctypes.byref(q), st)
+        torch.cuda.synchronize(dev)
+        allq = comm.all_gather(torch.tensor([q.value], dtype=torch.int64, device=dev)).cpu()      # also a barrier
+        visits = i64(0)
+        if int(allq.sum()) > 0:
+            self._call("ms_band_nf_p2p_arm_dev", self.h, st)
+            comm.all_reduce(torch.zeros(1, dtype=torch.int32, device=dev), "sum").cpu()           # barrier
+            self._call("ms_band_nf_p2p_solve_dev", self.h, _p(self.out["filled"]), _p(self.out["fnf"]), self.short,
+                       self.diag, cap_bound, ctypes.byref(visits), st)
+        self._tick("nf_p2p_solve")
+        self._halo(fnf)
+        nv = i64(0)
+        self._call("ms_band_nf_verify_dev", self.h, _p(self.dem), _p(self.out["fnf"]), self.short, self.diag,
+                   ctypes.byref(nv), st)
+        bad = comm.all_reduce(torch.tensor([nv.value], dtype=torch.int64, device=dev), "sum")
+        self._tick("nf_verify")
+        nbad = int(bad.item())
+        self.stats.update(noflat_exchanges=0, noflat_tile_visits=visits.value, noflat_capped=1, noflat_p2p=1,
+                          noflat_p2p_violations=nbad, noflat_p2p_queued=allq.view(-1).tolist())
+        return nbad == 0
 
     def _accum(self, st):
         comm, dev, cols = self.comm, self.device, self.cols

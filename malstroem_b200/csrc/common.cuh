@@ -167,6 +167,13 @@ struct ms_band {
     int nC;            // catchments of the band (fill)
     int nF;            // frozen components (fill)
     int gid_base;      // global id of the band's first frozen component
+    // no-flats solver fused over NVLink peer memory (noflats.cu): this band's shared block, the other ranks' blocks
+    // as mapped here, and the device copy of the kernel's peer table
+    void *nf_shared;
+    void *nf_peer[16];
+    int nf_peer_ipc[16];   // 1: mapped with cudaIpcOpenMemHandle (must be closed)
+    int nf_rank, nf_world;
+    void *nf_pp_dev;
 };
 namespace ms {
 void *band_buf(ms_band *b, int slot, size_t bytes);      // grow-only cudaMalloc'ed buffer of the context

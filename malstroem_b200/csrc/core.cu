@@ -265,8 +265,12 @@ int ms_band_create(int64_t rows, int64_t cols, int open, ms_band **out) {
 int ms_band_destroy(ms_band *b) {
     if (!b) return MS_OK;
     cudaDeviceSynchronize();
+    for (int k = 0; k < 16; k++)
+        if (b->nf_peer[k] && b->nf_peer_ipc[k]) cudaIpcCloseMemHandle(b->nf_peer[k]);
     for (int k = 0; k < ms::BB_COUNT; k++)
-        if (b->buf[k]) cudaFree(b->buf[k]);
+        if (b->buf[k] && b->cap[k] != SIZE_MAX) cudaFree(b->buf[k]);      // SIZE_MAX: a view into nf_shared
+    if (b->nf_shared) cudaFree(b->nf_shared);
+    if (b->nf_pp_dev) cudaFree(b->nf_pp_dev);
     delete b;
     return MS_OK;
 }

@@ -35,6 +35,8 @@
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
 
 #include "common.cuh"
 
@@ -385,8 +387,44 @@ __device__ inline int nf_to_int(double w, float f, int &bad, int &elo, int &ehi,
 // a CTA holds the tile.  "Side bits set and not running" means the tile is in the FIFO (exactly once).
 constexpr int NF_SIDES = 31;
 constexpr int NF_RUNNING = 256;
+// FIFO capacity = tiles + this: a tile is queued at most once, and every CTA of the grid may hold a ticket for an
+// entry that is not filled yet — two tickets must never share a slot (the grid is at most 148 SMs x 4 CTAs)
+constexpr int NF_RING_SLACK = 1024;
 
-__device__ inline void nf_push(int *ring, int cap, NfCtl *ctl, int tile) {
+// ---- row bands fused over NVLink peer memory (P2P) ---------------------------------------------------------
+// Every band's solver runs at the same time, one cooperative launch per GPU.  A band's FIFO, tile flags and two
+// "mailbox" rows (the neighbours' edge rows, i.e. this band's halo rows of the surface) live in one block that the
+// neighbouring ranks map through CUDA IPC.  A tile on a band edge whose ring changed stores its edge row into the
+// neighbour's mailbox and queues the neighbour's tile with system-scope atomics — the wave of a lake that spans
+// bands runs on without a host round trip.  Termination: each band counts its queued + running tiles; the number
+// of bands with a non-zero count lives on rank 0; whoever brings that to zero raises `done` on every rank.
+constexpr int NF_MAXRANKS = 16;
+struct NfPeer {
+    int *tileflag;     // the neighbour band's tile flag words
+    int *ring;         // ... its FIFO
+    NfCtl *ctl;
+    double *mail;      // ... its mailbox row facing this band
+    int tiles_y, cap;
+};
+struct NfP2P {
+    NfPeer up, down;                // null pointers where the band is not open
+    double *mail_top, *mail_bot;    // this band's own halo rows of the surface (written by the neighbours)
+    int *gactive;                   // rank 0: bands with queued or running tiles
+    int *done_all[NF_MAXRANKS];     // every rank's ctl->done
+    int world;
+};
+
+// queue `tile` on the FIFO (ring, ctl); with `sys` the FIFO may be another GPU's (or be fed by another GPU)
+__device__ inline void nf_push(int *ring, int cap, NfCtl *ctl, int tile, bool sys = false, int *gactive = nullptr) {
+    if (sys) {
+        if (atomicAdd_system(&ctl->pending, 1) == 0) atomicAdd_system(gactive, 1);      // the band wakes up
+        unsigned idx = atomicAdd_system(&ctl->tail, 1u);
+        volatile int *slot = ring + (idx % (unsigned)cap);
+        for (unsigned spins = 0; *slot != -1 && spins < (1u << 23); spins++) __nanosleep(100);
+        *slot = tile;
+        __threadfence_system();
+        return;
+    }
     atomicAdd(&ctl->pending, 1);
     unsigned idx = atomicAdd(&ctl->tail, 1u);
     volatile int *slot = ring + (idx % (unsigned)cap);
@@ -405,7 +443,7 @@ template <bool CAP>
 __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ zsrc, double *W, int *ring, int cap,
                                                   int *tileflag, const int *__restrict__ tilesides, NfCtl *ctl, int rows, int cols, int tiles_x,
                                                   int tiles_y, double sh, double dg, int use_int, double capB_in,
-                                                  int open) {
+                                                  int open, const NfP2P *pp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sw = reinterpret_cast<double *>(smem_raw);
     float *sz = reinterpret_cast<float *>(smem_raw + (NF_T + 2) * NF_LD * 8);
@@ -416,7 +454,11 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
     const double capB = CAP ? (capB_in >= 0 ? capB_in : ((double)ctl->nonseed + 16.0) * dg * 1.001) : 0.0;
     // rows the aprons may read: a band that continues above / below has a halo row there
     const int rlo = (open & 1) ? -1 : 0, rhi = rows + ((open & 2) ? 1 : 0);
-    if (*(volatile unsigned *)&ctl->tail == 0) return;      // nothing was queued (tail only grows)
+    const bool p2p = pp != nullptr;
+    // halo rows of the surface: the ext rows of W, or (P2P) the mailboxes the neighbours write
+    const double *halo_top = p2p ? pp->mail_top : W - (long long)cols;
+    const double *halo_bot = p2p ? pp->mail_bot : W + (long long)rows * cols;
+    if (!p2p && *(volatile unsigned *)&ctl->tail == 0) return;      // nothing was queued (tail only grows)
 
     for (;;) {
         __syncthreads();
@@ -436,7 +478,7 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                 *slot = -1;
                 __threadfence();
                 // taken: while the tile runs, neighbours only leave their side bits; they are looked at when it ends
-                S.flags = atomicExch(tileflag + t, NF_RUNNING) & NF_SIDES;
+                S.flags = (p2p ? atomicExch_system(tileflag + t, NF_RUNNING) : atomicExch(tileflag + t, NF_RUNNING)) & NF_SIDES;
                 S.dirty[1] = 0;
                 S.dirty[2] = 0;
                 S.chgmask = 0;
@@ -470,14 +512,25 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                     if (!dy && !dx) continue;
                     if (!(nbm & (1 << ((dy + 1) * 3 + (dx + 1))))) continue;
                     int y = ty + dy, x = tx + dx;
-                    if (y < 0 || y >= tiles_y || x < 0 || x >= tiles_x) continue;
-                    int nb = y * tiles_x + x;
+                    if (x < 0 || x >= tiles_x) continue;
                     // which side of the neighbour looks at us
                     int bits = (dy < 0 ? 2 : 0) | (dy > 0 ? 1 : 0) | (dx < 0 ? 8 : 0) | (dx > 0 ? 4 : 0);
                     if (dy && dx) bits = dy < 0 ? 2 : 1;      // a corner: one block of that side is enough
+                    if (y < 0 || y >= tiles_y) {
+                        // the tile lies in the neighbouring band: its flag word and FIFO are on another GPU
+                        if (!p2p) continue;
+                        const NfPeer &q = y < 0 ? pp->up : pp->down;
+                        if (!q.tileflag) continue;
+                        int nbq = (y < 0 ? q.tiles_y - 1 : 0) * tiles_x + x;
+                        if (atomicOr_system(q.tileflag + nbq, bits) == 0) nf_push(q.ring, q.cap, q.ctl, nbq, true, pp->gactive);
+                        continue;
+                    }
+                    int nb = y * tiles_x + x;
                     if (!(__ldg(tilesides + nb) & bits)) continue;      // nothing there that could change
                     // an idle tile (no side bits yet, not running) is queued by whoever sets its first side bit
-                    if (atomicOr(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb);
+                    if (p2p) {
+                        if (atomicOr_system(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb, true, pp->gactive);
+                    } else if (atomicOr(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb);
                 }
         };
         bool solved = false;
@@ -495,7 +548,7 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                     rg[j].w0 = rg[j].w1 = rg[j].wa = 0.0;
                     rg[j].f0 = rg[j].f1 = rg[j].fa = 0.f;          // w == f: a wall
                     if (lr < NF_T + 2 && r >= rlo && r < rhi) {
-                        const double *wr = W + (long long)r * cols;
+                        const double *wr = r < 0 ? halo_top : (r >= rows ? halo_bot : W + (long long)r * cols);
                         const float *fr = zsrc + (long long)r * cols;
                         int c = c0 + 2 * lane;
                         if (vec) {
@@ -632,6 +685,17 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                         nbm = __reduce_or_sync(0xffffffffu, nbm);
                         if (lane == 0 && nbm) atomicOr(&S.nb, nbm);
                     }
+                    if (p2p) {
+                        // the band's edge rows go into the neighbours' mailboxes before their tiles are queued
+                        __threadfence();
+                        __syncthreads();
+                        if (ty == 0 && pp->up.mail && (S.ring & 1) && tid < NF_T && c0 + tid < cols)
+                            pp->up.mail[c0 + tid] = __ldcg(W + c0 + tid);
+                        if (ty == tiles_y - 1 && pp->down.mail && (S.ring & 2) && tid >= NF_T && tid < 2 * NF_T &&
+                            c0 + tid - NF_T < cols)
+                            pp->down.mail[c0 + tid - NF_T] = __ldcg(W + (long long)(rows - 1) * cols + c0 + tid - NF_T);
+                        __threadfence_system();
+                    }
                     __threadfence();
                     __syncthreads();
                     if (tid == 0) {
@@ -675,7 +739,8 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                 int lr = q / (NF_T + 2), lc = q - lr * (NF_T + 2);
                 int r = r0 + lr - 1, c = c0 + lc - 1;
                 double v = INFINITY;
-                if (r >= rlo && r < rhi && c >= 0 && c < cols) v = __ldcg(W + (long long)r * cols + c);
+                if (r >= rlo && r < rhi && c >= 0 && c < cols)
+                    v = __ldcg((r < 0 ? halo_top : (r >= rows ? halo_bot : W + (long long)r * cols)) + c);
                 sw[lr * NF_LD + lc] = v;
             }
             for (int q = tid; q < NF_T * NF_T; q += 256) {
@@ -702,6 +767,17 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                         if (c < cols) W[(size_t)r * cols + c] = p[0];
                         if (c + 1 < cols) W[(size_t)r * cols + c + 1] = p[1];
                     }
+                }
+                if (p2p) {
+                    // the band's edge rows go into the neighbours' mailboxes before their tiles are queued
+                    __threadfence();
+                    __syncthreads();
+                    if (ty == 0 && pp->up.mail && (S.ring & 1) && tid < NF_T && c0 + tid < cols)
+                        pp->up.mail[c0 + tid] = __ldcg(W + c0 + tid);
+                    if (ty == tiles_y - 1 && pp->down.mail && (S.ring & 2) && tid >= NF_T && tid < 2 * NF_T &&
+                        c0 + tid - NF_T < cols)
+                        pp->down.mail[c0 + tid - NF_T] = __ldcg(W + (long long)(rows - 1) * cols + c0 + tid - NF_T);
+                    __threadfence_system();
                 }
                 __threadfence();
                 __syncthreads();
@@ -747,9 +823,17 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
         __syncthreads();
         if (tid == 0) {
             // this tile: side bits that arrived while it ran mean it has to run again
-            if (atomicAnd(tileflag + t, ~NF_RUNNING) & NF_SIDES) nf_push(ring, cap, ctl, t);
-            __threadfence();
-            if (atomicSub(&ctl->pending, 1) == 1) atomicExch(&ctl->done, 1);
+            if (p2p) {
+                if (atomicAnd_system(tileflag + t, ~NF_RUNNING) & NF_SIDES) nf_push(ring, cap, ctl, t, true, pp->gactive);
+                __threadfence_system();
+                // the band runs dry: one band less is active; the last one ends every rank's kernel
+                if (atomicSub_system(&ctl->pending, 1) == 1 && atomicSub_system(pp->gactive, 1) == 1)
+                    for (int k = 0; k < pp->world; k++) *(volatile int *)pp->done_all[k] = 1;
+            } else {
+                if (atomicAnd(tileflag + t, ~NF_RUNNING) & NF_SIDES) nf_push(ring, cap, ctl, t);
+                __threadfence();
+                if (atomicSub(&ctl->pending, 1) == 1) atomicExch(&ctl->done, 1);
+            }
         }
     }
 }
@@ -904,7 +988,7 @@ template <bool CAP>
 static int nf_launch_solve(const float *zsrc, double *W, int *ring, int cap, int *tileflag, const int *tilesides,
                            NfCtl *ctl, int rows,
                            int cols, int tiles_x, int tiles_y, int ntiles, double sh, double dg, int use_int,
-                           double capB_in, int open, int64_t units, cudaStream_t s) {
+                           double capB_in, int open, int64_t units, cudaStream_t s, const NfP2P *pp = nullptr) {
     static int grid_blocks = 0;
     if (!grid_blocks) {
         MS_CUDA(cudaFuncSetAttribute(k_nf_solve<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, NF_SMEM));
@@ -918,9 +1002,9 @@ static int nf_launch_solve(const float *zsrc, double *W, int *ring, int cap, int
     void *args[] = {(void *)&zsrc, (void *)&W, (void *)&ring, (void *)&cap, (void *)&tileflag, (void *)&tilesides,
                     (void *)&ctl,
                     (void *)&rows, (void *)&cols, (void *)&tiles_x, (void *)&tiles_y, (void *)&sh, (void *)&dg,
-                    (void *)&use_int, (void *)&capB_in, (void *)&open};
+                    (void *)&use_int, (void *)&capB_in, (void *)&open, (void *)&pp};
     // consumers wait on the FIFO, so every CTA must be resident: cooperative launch guarantees it (or fails)
-    int g = grid_blocks < ntiles ? grid_blocks : ntiles;
+    int g = (grid_blocks < ntiles || pp) ? grid_blocks : ntiles;
     prof_units(units);
     if (g_prof) prof_begin(CAP ? "k_nf_solve<true>" : "k_nf_solve<false>", s);
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_nf_solve<CAP>, dim3(g), dim3(256), args, NF_SMEM, s);
@@ -956,7 +1040,7 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
     }
     int tiles_x = (int)cdiv(cols, NF_T), tiles_y = (int)cdiv(rows, NF_T);
     int ntiles = tiles_x * tiles_y;
-    int cap_ring = ntiles + 64;          // a tile is in the FIFO at most once
+    int cap_ring = ntiles + NF_RING_SLACK;          // a tile is in the FIFO at most once
     DevBuf<int> tileflag, tilesides, ring;
     DevBuf<uint8_t> banned;
     DevBuf<NfCtl> ctl;
@@ -1043,7 +1127,7 @@ static int nf_band_bufs(ms_band *B, NfBandBufs *o) {
     o->tiles_x = (int)cdiv(B->cols, NF_T);
     o->tiles_y = (int)cdiv(B->rows, NF_T);
     o->ntiles = o->tiles_x * o->tiles_y;
-    o->cap_ring = o->ntiles + 64;
+    o->cap_ring = o->ntiles + NF_RING_SLACK;
     o->tileflag = (int *)band_buf(B, BB_NF_FLAG, (size_t)o->ntiles * sizeof(int));
     o->tilesides = (int *)band_buf(B, BB_NF_SIDES, (size_t)o->ntiles * sizeof(int));
     o->ring = (int *)band_buf(B, BB_NF_RING, (size_t)o->cap_ring * sizeof(int));
@@ -1113,6 +1197,203 @@ int ms_band_nf_solve_dev(ms_band *B, const float *dem, const float *filled, doub
     MS_TRY(ms::stream_sync(s));
     if (h->done != 1 && h->tail != 0) {
         set_error("band no-flats: tile solver stopped early (done=%d, pending=%d)", h->done, h->pending);
+        return MS_ERR_NOCONV;
+    }
+    if (tile_visits) *tile_visits = h->visits;
+    return MS_OK;
+}
+
+
+// ---- P2P: shared block, peer mapping, solve -----------------------------------------------------------------
+}  // extern "C"
+
+namespace ms {
+struct NfSharedLayout {
+    size_t off_gactive, off_flag, off_sides, off_ring, off_mtop, off_mbot, total;
+    int tiles_x, tiles_y, ntiles, cap;
+};
+static NfSharedLayout nf_layout(int64_t rows, int64_t cols) {
+    NfSharedLayout L;
+    L.tiles_x = (int)cdiv(cols, NF_T);
+    L.tiles_y = (int)cdiv(rows, NF_T);
+    L.ntiles = L.tiles_x * L.tiles_y;
+    L.cap = L.ntiles + NF_RING_SLACK;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
+    take(sizeof(NfCtl));                       // the control block is at offset 0
+    L.off_gactive = take(sizeof(int));
+    L.off_flag = take((size_t)L.ntiles * sizeof(int));
+    L.off_sides = take((size_t)L.ntiles * sizeof(int));
+    L.off_ring = take((size_t)L.cap * sizeof(int));
+    L.off_mtop = take((size_t)cols * sizeof(double));
+    L.off_mbot = take((size_t)cols * sizeof(double));
+    L.total = o;
+    return L;
+}
+
+__global__ void k_nf_arm(NfCtl *ctl, int *gactive) {
+    if (ctl->pending > 0) atomicAdd_system(gactive, 1);
+}
+}  // namespace ms
+
+extern "C" {
+
+/* info (80 bytes): CUDA IPC handle of the band's shared block, its address in this process, the process id */
+int ms_band_nf_shared_create(ms_band *B, void *info80) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !info80) { set_error("band no-flats P2P: null pointer"); return MS_ERR_ARG; }
+    if (!B->nf_shared) {
+        NfSharedLayout L = nf_layout(B->rows, B->cols);
+        void *p = nullptr;
+        MS_CUDA(cudaMalloc(&p, L.total));
+        MS_CUDA(cudaMemset(p, 0, L.total));
+        B->nf_shared = p;
+        // the solver state of this band lives in the block, where the neighbours can reach it
+        int slots[4] = {BB_NF_CTL, BB_NF_FLAG, BB_NF_SIDES, BB_NF_RING};
+        size_t offs[4] = {0, L.off_flag, L.off_sides, L.off_ring};
+        for (int k = 0; k < 4; k++) {
+            if (B->buf[slots[k]] && B->cap[slots[k]] != SIZE_MAX) cudaFree(B->buf[slots[k]]);
+            B->buf[slots[k]] = (char *)p + offs[k];
+            B->cap[slots[k]] = SIZE_MAX;
+        }
+    }
+    unsigned char *out = (unsigned char *)info80;
+    cudaIpcMemHandle_t h;
+    MS_CUDA(cudaIpcGetMemHandle(&h, B->nf_shared));
+    memcpy(out, &h, 64);
+    unsigned long long addr = (unsigned long long)(uintptr_t)B->nf_shared, pid = (unsigned long long)getpid();
+    memcpy(out + 64, &addr, 8);
+    memcpy(out + 72, &pid, 8);
+    return MS_OK;
+}
+
+/* infos: world x 80 bytes as written by ms_band_nf_shared_create on every rank; rows_all: own rows of every band */
+int ms_band_nf_shared_open(ms_band *B, int rank, int world, const void *infos, const int64_t *rows_all) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !B->nf_shared || !infos || !rows_all || world < 1 || world > NF_MAXRANKS || rank < 0 || rank >= world) {
+        set_error("band no-flats P2P: bad argument");
+        return MS_ERR_ARG;
+    }
+    const unsigned char *in = (const unsigned char *)infos;
+    unsigned long long mypid = (unsigned long long)getpid();
+    for (int k = 0; k < world; k++) {
+        if (B->nf_peer[k]) continue;
+        if (k == rank) { B->nf_peer[k] = B->nf_shared; continue; }
+        unsigned long long addr, pid;
+        memcpy(&addr, in + 80 * k + 64, 8);
+        memcpy(&pid, in + 80 * k + 72, 8);
+        if (pid == mypid) {
+            B->nf_peer[k] = (void *)(uintptr_t)addr;      // a band of the same process: same address space
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, in + 80 * k, 64);
+            void *p = nullptr;
+            MS_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            B->nf_peer[k] = p;
+            B->nf_peer_ipc[k] = 1;
+        }
+    }
+    B->nf_rank = rank;
+    B->nf_world = world;
+    NfP2P pp;
+    memset(&pp, 0, sizeof(pp));
+    NfSharedLayout me = nf_layout(B->rows, B->cols);
+    pp.mail_top = (double *)((char *)B->nf_shared + me.off_mtop);
+    pp.mail_bot = (double *)((char *)B->nf_shared + me.off_mbot);
+    pp.world = world;
+    pp.gactive = (int *)((char *)B->nf_peer[0] + nf_layout(rows_all[0], B->cols).off_gactive);
+    for (int k = 0; k < world; k++) pp.done_all[k] = &((NfCtl *)B->nf_peer[k])->done;
+    for (int side = 0; side < 2; side++) {
+        int k = side ? rank + 1 : rank - 1;
+        if (k < 0 || k >= world || !(B->open & (side ? 2 : 1))) continue;
+        NfSharedLayout L = nf_layout(rows_all[k], B->cols);
+        char *base = (char *)B->nf_peer[k];
+        NfPeer q;
+        q.tileflag = (int *)(base + L.off_flag);
+        q.ring = (int *)(base + L.off_ring);
+        q.ctl = (NfCtl *)base;
+        q.mail = (double *)(base + (side ? L.off_mtop : L.off_mbot));      // the row of theirs that faces this band
+        q.tiles_y = L.tiles_y;
+        q.cap = L.cap;
+        if (side) pp.down = q; else pp.up = q;
+    }
+    if (!B->nf_pp_dev) MS_CUDA(cudaMalloc(&B->nf_pp_dev, sizeof(NfP2P)));
+    MS_CUDA(cudaMemcpy(B->nf_pp_dev, &pp, sizeof(pp), cudaMemcpyHostToDevice));
+    return MS_OK;
+}
+
+/* CAP only: the candidates the fixed neighbours offer (needs the halo rows of fnf after ms_band_nf_init_dev) */
+int ms_band_nf_seedcand_dev(ms_band *B, const float *filled, double *fnf, double short_eps, double diag_eps,
+                            double cap_bound, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !filled || !fnf) { set_error("band no-flats: null pointer"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NfBandBufs nb;
+    MS_TRY(nf_band_bufs(B, &nb));
+    dim3 g2(cdiv(B->cols, 64), cdiv(B->rows, 4));
+    MS_LAUNCH(k_nf_seedcand, g2, 256, 0, s, filled, fnf, nb.ctl, (int)B->rows, (int)B->cols, short_eps, diag_eps, cap_bound,
+              B->open);
+    return MS_OK;
+}
+
+/* P2P step 1 (after init, seed candidates and a halo exchange of fnf): mailboxes := halo rows, FIFO := flagged tiles,
+ * rank 0 clears the active-band counter.  Returns the number of queued tiles.  The caller synchronises all ranks. */
+int ms_band_nf_p2p_prepare_dev(ms_band *B, const double *fnf, int64_t *queued, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !B->nf_pp_dev || !fnf || !queued) { set_error("band no-flats P2P: not set up"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NfBandBufs nb;
+    MS_TRY(nf_band_bufs(B, &nb));
+    NfSharedLayout L = nf_layout(B->rows, B->cols);
+    char *base = (char *)B->nf_shared;
+    size_t rowb = (size_t)B->cols * sizeof(double);
+    if (B->open & 1) MS_CUDA(cudaMemcpyAsync(base + L.off_mtop, fnf - B->cols, rowb, cudaMemcpyDeviceToDevice, s));
+    if (B->open & 2) MS_CUDA(cudaMemcpyAsync(base + L.off_mbot, fnf + B->rows * B->cols, rowb, cudaMemcpyDeviceToDevice, s));
+    MS_CUDA(cudaMemsetAsync(nb.ring, 0xff, (size_t)nb.cap_ring * sizeof(int), s));
+    MS_CUDA(cudaMemsetAsync(nb.ctl, 0, sizeof(NfCtl), s));
+    if (B->nf_rank == 0) MS_CUDA(cudaMemsetAsync(base + L.off_gactive, 0, sizeof(int), s));
+    MS_LAUNCH(k_nf_compact, cdiv(nb.ntiles, 256), 256, 0, s, nb.tileflag, nb.ring, nb.ctl, nb.ntiles);
+    NfCtl *h = (NfCtl *)(host_flags().h + 32);
+    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    *queued = h->pending;
+    return MS_OK;
+}
+
+/* P2P step 2 (all ranks prepared): a band with queued tiles counts itself active.  The caller synchronises again. */
+int ms_band_nf_p2p_arm_dev(ms_band *B, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !B->nf_pp_dev) { set_error("band no-flats P2P: not set up"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NfP2P pp;
+    MS_CUDA(cudaMemcpy(&pp, B->nf_pp_dev, sizeof(pp), cudaMemcpyDeviceToHost));
+    MS_LAUNCH(k_nf_arm, 1, 1, 0, s, (NfCtl *)B->nf_shared, pp.gactive);
+    MS_TRY(ms::stream_sync(s));
+    return MS_OK;
+}
+
+/* P2P step 3: the solve, all ranks at once (capped fast path).  Ends when no band has work left. */
+int ms_band_nf_p2p_solve_dev(ms_band *B, const float *filled, double *fnf, double short_eps, double diag_eps,
+                             double cap_bound, int64_t *tile_visits, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !B->nf_pp_dev || !filled || !fnf) { set_error("band no-flats P2P: not set up"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NfBandBufs nb;
+    MS_TRY(nf_band_bufs(B, &nb));
+    MS_TRY(nf_launch_solve<true>(filled, fnf, nb.ring, nb.cap_ring, nb.tileflag, nb.tilesides, nb.ctl, (int)B->rows,
+                                 (int)B->cols, nb.tiles_x, nb.tiles_y, nb.ntiles, short_eps, diag_eps, g_nf_use_int,
+                                 cap_bound, B->open, B->rows * B->cols, s, (const NfP2P *)B->nf_pp_dev));
+    NfCtl *h = (NfCtl *)(host_flags().h + 32);
+    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    if (h->done != 1) {
+        set_error("band no-flats P2P: solver stopped early (done=%d, pending=%d)", h->done, h->pending);
         return MS_ERR_NOCONV;
     }
     if (tile_visits) *tile_visits = h->visits;

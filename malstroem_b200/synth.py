@@ -95,7 +95,7 @@ def pathological_dem(rows, cols, seed=1):
     return mm.astype(np.float32) * np.float32(0.001)
 
 
-def pathological_dem(rows, cols, seed=3):
+def pathological_spiral_dem(rows, cols, seed=3):
     """BASELINE config 5 in small: stepped plateaus (large exact flats), concentric nested craters (depressions inside
     depressions, 6 levels) centred on rows k*rows/4 so that they straddle band edges, a spiral channel at one exact
     elevation (the longest geodesic one can fold into a square: stresses the no-flats wave and makes the capped fast

@@ -80,11 +80,11 @@ def test_bands_lake_across_every_edge():
 
 
 def test_pathological_single_and_banded():
-    """BASELINE config 5 in small (synth.pathological_dem): exact plateaus (79 % of the cells are lake / flat),
+    """BASELINE config 5 in small (synth.pathological_spiral_dem): exact plateaus (79 % of the cells are lake / flat),
     nested craters on the band edges, a raster-wide flat and a spiral channel with a 9500-step geodesic, on one GPU
     and in bands."""
     from malstroem_b200.pipeline import RasterPipeline
-    dem = synth.pathological_dem(768, 512)
+    dem = synth.pathological_spiral_dem(768, 512)
     want = oracle_all(dem)
     p = RasterPipeline(768, 512)
     h = p.run_host(dem)
@@ -92,6 +92,19 @@ def test_pathological_single_and_banded():
         assert np.array_equal(h[name].numpy(), want[name]), name
     assert p.nlabels == want["n"]
     for nb in (2, 3):
+        pipes = bands.run_threaded(torch.from_numpy(dem).cuda(), nb)
+        try:
+            check(pipes, want)
+        finally:
+            for q in pipes:
+                q.close()
+
+
+def test_pathological_plateaus_banded():
+    """synth.pathological_dem: 5 m plateaus, square-ring craters on the k*rows/8 band edges, a raster-wide flat."""
+    dem = synth.pathological_dem(512, 384)
+    want = oracle_all(dem)
+    for nb in (2, 8):
         pipes = bands.run_threaded(torch.from_numpy(dem).cuda(), nb)
         try:
             check(pipes, want)
@@ -113,7 +126,7 @@ def test_pathological_float64_form_falls_back():
         "from malstroem_b200 import synth\n"
         "from malstroem_b200.pipeline import RasterPipeline\n"
         "from oracle import port\n"
-        "dem = synth.pathological_dem(768, 512)\n"
+        "dem = synth.pathological_spiral_dem(768, 512)\n"
         "p = RasterPipeline(768, 512)\n"
         "h = p.run_host(dem)\n"
         "short, diag = port.minimum_safe_short_and_diag(dem)\n"
