@@ -354,3 +354,116 @@ int orc_keep_labels(const int64_t *lab, int64_t n, const uint8_t *keep, int64_t 
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * net.next_downstream_label / net.pourpoint_network (malstroem/algorithms/net.py:142-192),
+ * the walk itself being flow.trace_downstream (flow.py:279-301): yield the cell, read its direction, stop at
+ * a no-direction code (flow.py:101-115 returns no delta for codes > 7) or when the next cell is outside the
+ * raster.  The start cell is visited first (its label equals the source label, so it never answers).
+ * For each of the np start cells: down[k] = first label on the path that differs from the start cell's label
+ * and, when has_bg, from the background label; found[k] = 0 when the path ends first (Python None).
+ * path_len[k] (optional) = cells yielded up to and including the answering cell — the `geometry` list.
+ * Returns -1 when a walk exceeds rows*cols steps (cyclic directions: the reference would never return).
+ * ---------------------------------------------------------------------------------------------- */
+static const int kDR[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+static const int kDC[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+
+int orc_next_downstream_labels(const uint8_t *fd, const int64_t *lab, int64_t rows, int64_t cols, int64_t np,
+                               const int64_t *pp_row, const int64_t *pp_col, int64_t bg, int has_bg,
+                               int64_t *down, uint8_t *found, int64_t *path_len, int64_t *path_cells,
+                               const int64_t *path_off)
+{
+    for (int64_t k = 0; k < np; k++) {
+        int64_t r = pp_row[k], c = pp_col[k], steps = 0;
+        int64_t src = lab[IDX(r, c)];
+        found[k] = 0;
+        down[k] = 0;
+        for (;;) {
+            if (r < 0 || r >= rows || c < 0 || c >= cols) break;            /* flow.py:294 cell_in_raster */
+            if (path_cells) path_cells[path_off[k] + steps] = r * cols + c;  /* net.py:166-167 */
+            steps++;
+            int64_t l = lab[IDX(r, c)];
+            if (l != src && (!has_bg || l != bg)) {                         /* net.py:168-170 */
+                found[k] = 1;
+                down[k] = l;
+                break;
+            }
+            int d = fd[IDX(r, c)];
+            if (d > 7) break;                                               /* flow.py:296-301 */
+            r += kDR[d];
+            c += kDC[d];
+            if (steps > rows * cols) return -1;
+        }
+        if (path_len) path_len[k] = steps;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Network.rain_event (malstroem/network.py:75-129) for ne events at once.
+ * Nodes are given in insertion order; parent[i] = index of the downstream node, -1 for a root
+ * (dstrnodeid None), -2 for an id that is not a node (such a node and everything upstream of it is never
+ * reached from a root, network.py:100-111,126-128, so it gets no values: present[i] = 0).
+ * Per node and event (network.py:75-98):
+ *   rainv  = area * mm * 0.001                       (left to right)
+ *   up     = sum(spillv of the upstream nodes, in insertion order)     -- Python sum()
+ *   total  = rainv + up;  v = min(total, cap);  spillv = max(0, total - cap)
+ *   pctv   = 100.0 * v / cap, None (here NaN) when cap == 0
+ * sum_mode 0: plain left-to-right float addition (sum() before CPython 3.12).
+ * sum_mode 1: Neumaier compensated addition, which is what sum() does for floats from CPython 3.12 on
+ *             (Python/bltinmodule.c, builtin_sum_impl: cs_add per item, `if (c && isfinite(c)) total += c`).
+ * Outputs are [ne][n] row-major.  Returns -1 on a cycle among reachable nodes (cannot happen from a root).
+ * ---------------------------------------------------------------------------------------------- */
+int orc_rain_events(int64_t n, const int64_t *parent, const double *area, const double *cap, int64_t ne,
+                    const double *mm, int sum_mode, double *rainv, double *spillv, double *v, double *pctv,
+                    uint8_t *present)
+{
+    int64_t *first = malloc(sizeof(int64_t) * (n + 1)), *next = malloc(sizeof(int64_t) * (n + 1));
+    int64_t *last = malloc(sizeof(int64_t) * (n + 1)), *order = malloc(sizeof(int64_t) * (n + 1));
+    int64_t *stack = malloc(sizeof(int64_t) * (n + 1));
+    for (int64_t i = 0; i < n; i++) { first[i] = -1; last[i] = -1; next[i] = -1; present[i] = 0; }
+    for (int64_t i = 0; i < n; i++) {           /* upstream_tree[downstream].append(node), network.py:66-69 */
+        int64_t p = parent[i];
+        if (p < 0) continue;
+        if (first[p] < 0) first[p] = i; else next[last[p]] = i;
+        last[p] = i;
+    }
+    int64_t m = 0;
+    for (int64_t root = 0; root < n; root++) {  /* network.py:100-111: any order with children before parents */
+        if (parent[root] != -1) continue;
+        int64_t sp = 0;
+        stack[sp++] = root;
+        while (sp) {
+            int64_t x = stack[--sp];
+            order[m++] = x;
+            present[x] = 1;
+            for (int64_t ch = first[x]; ch >= 0; ch = next[ch]) stack[sp++] = ch;
+        }
+    }
+    for (int64_t e = 0; e < ne; e++) {
+        double *R = rainv + e * n, *S = spillv + e * n, *V = v + e * n, *P = pctv + e * n;
+        for (int64_t i = 0; i < n; i++) { R[i] = S[i] = V[i] = P[i] = NAN; }
+        for (int64_t k = m - 1; k >= 0; k--) {
+            int64_t x = order[k];
+            double rv = area[x] * mm[e] * 0.001;
+            double up = 0.0, comp = 0.0;
+            for (int64_t ch = first[x]; ch >= 0; ch = next[ch]) {
+                double y = S[ch];
+                if (sum_mode == 0) { up = up + y; continue; }
+                double t = up + y;
+                if (fabs(up) >= fabs(y)) comp += (up - t) + y; else comp += (y - t) + up;
+                up = t;
+            }
+            if (sum_mode == 1 && comp != 0.0 && isfinite(comp)) up += comp;
+            double total = rv + up;
+            double filled = cap[x] < total ? cap[x] : total;            /* min(total, cap): first argument unless cap < total */
+            double d = total - cap[x];
+            R[x] = rv;
+            S[x] = d > 0.0 ? d : 0.0;                                   /* max(0, d) */
+            V[x] = filled;
+            P[x] = cap[x] != 0.0 ? 100.0 * filled / cap[x] : NAN;
+        }
+    }
+    free(first); free(next); free(last); free(order); free(stack);
+    return 0;
+}

@@ -152,3 +152,72 @@ def keep_labels(labelled, keep_label, background=0):
     if lib().orc_keep_labels(_p(lab.ravel()), c_i64(lab.size), _p(keep), c_i64(keep.size), _p(out)):
         raise IndexError("label outside keep list")
     return out.view(bool)
+
+
+# ---------------------------------------------------------------------------------------- SURVEY §8(f)
+def _pp_arrays(pour_points):
+    # net.py:21-40 (_pourpoint_enumerator): json-type pour points or (row, col) pairs
+    ids, cells = [], []
+    for pid, pp in enumerate(pour_points):
+        if isinstance(pp, dict) and 'properties' in pp:
+            pid = pp['properties']['bspot_id']
+            pp = (pp['properties']['cell_row'], pp['properties']['cell_col'])
+        ids.append(pid)
+        cells.append((int(pp[0]), int(pp[1])))
+    cells = np.array(cells, dtype=np.int64).reshape(-1, 2)
+    return ids, np.ascontiguousarray(cells[:, 0]), np.ascontiguousarray(cells[:, 1])
+
+
+def _downstream(flowdir, labeled, rows_, cols_, background_label, geometry):
+    fd = _c(flowdir, np.uint8)
+    lab = _c(labeled, np.int64)
+    n = rows_.size
+    down = np.empty(n, np.int64)
+    found = np.empty(n, np.uint8)
+    plen = np.empty(n, np.int64)
+    has_bg = background_label is not None
+    args = (_p(fd), _p(lab), c_i64(fd.shape[0]), c_i64(fd.shape[1]), c_i64(n), _p(rows_), _p(cols_),
+            c_i64(int(background_label) if has_bg else 0), int(has_bg), _p(down), _p(found), _p(plen))
+    if lib().orc_next_downstream_labels(*args, None, None):
+        raise RuntimeError("cyclic flow directions")
+    paths = None
+    if geometry:
+        off = np.zeros(n + 1, np.int64)
+        np.cumsum(plen, out=off[1:])
+        cells = np.empty(int(off[-1]), np.int64)
+        lib().orc_next_downstream_labels(*args, _p(cells), _p(off))
+        paths = [[(int(i) // fd.shape[1], int(i) % fd.shape[1]) for i in cells[off[k]:off[k + 1]]] for k in range(n)]
+    return down, found.astype(bool), paths
+
+
+def next_downstream_label(flowdir, labeled, cell, background_label=None, geometry=False):
+    # net.py:142-172
+    r = np.array([int(cell[0])], np.int64)
+    c = np.array([int(cell[1])], np.int64)
+    down, found, paths = _downstream(flowdir, labeled, r, c, background_label, geometry)
+    return (int(down[0]) if found[0] else None), (paths[0] if geometry else [])
+
+
+def pourpoint_network(flowdir, labeled, pour_points, background_label=None):
+    # net.py:175-192
+    ids, r, c = _pp_arrays(pour_points)
+    down, found, _ = _downstream(flowdir, labeled, r, c, background_label, False)
+    return [dict(id=ids[k], downstream_id=(int(down[k]) if found[k] else None), nodetype='pourpoint',
+                 pix=(int(r[k]), int(c[k]))) for k in range(len(ids))]
+
+
+def rain_events(parent, area, cap, mm, sum_mode):
+    """network.py:75-129 for all events at once.  parent: node index, -1 root, -2 unknown id.
+    Returns dict of [ne, n] arrays (pctv NaN where the reference says None) and the `present` mask."""
+    parent = _c(parent, np.int64)
+    area = _c(area, np.float64)
+    cap = _c(cap, np.float64)
+    mm = _c(np.atleast_1d(mm), np.float64)
+    n, ne = parent.size, mm.size
+    out = {k: np.empty((ne, n), np.float64) for k in ("rainv", "spillv", "v", "pctv")}
+    present = np.empty(n, np.uint8)
+    if lib().orc_rain_events(c_i64(n), _p(parent), _p(area), _p(cap), c_i64(ne), _p(mm), int(sum_mode),
+                             _p(out["rainv"]), _p(out["spillv"]), _p(out["v"]), _p(out["pctv"]), _p(present)):
+        raise RuntimeError("cycle in the node network")
+    out["present"] = present.astype(bool)
+    return out

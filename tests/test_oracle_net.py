@@ -1,0 +1,27 @@
+"""The CPU oracle's §8(f) functions against outputs of the reference itself (net188.npz / net_small.npz) and the
+known answers of /root/reference/tests/test_raster_net.py:8-21."""
+import numpy as np
+
+import net_cases
+from conftest import _load
+from oracle import port
+
+
+def test_next_downstream_label_and_pourpoint_network_golden(dtm188):
+    net_cases.check_net188(port, _load("net188.npz"), dtm188)
+
+
+def test_net_small_cases(small_cases):
+    net_cases.check_net_small(port, _load("net_small.npz"), small_cases)
+
+
+def test_rain_events_golden():
+    z, zs = _load("net188.npz"), _load("net_small.npz")
+    assert tuple(z["python"][:2]) >= (3, 12)         # fixtures carry Neumaier sums (CPython >= 3.12 sum())
+    net_cases.check_rain(port.rain_events, z, zs, exact=True)
+
+
+def test_rain_plain_sum_within_tolerance():
+    """sum_mode 0 (sum() before CPython 3.12) differs from the fixtures only in the last bits."""
+    z, zs = _load("net188.npz"), _load("net_small.npz")
+    net_cases.check_rain(lambda p, a, c, mm, _m: port.rain_events(p, a, c, mm, 0), z, zs, exact=False)
