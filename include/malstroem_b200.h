@@ -286,6 +286,47 @@ typedef struct ms_host_out {
 int ms_pipeline_host_dev(ms_rasters *io, const ms_host_out *host, void *stream);
 int ms_copies_wait(void);
 
+/* ---- the bluespot network on device ------------------------------------------------ */
+/* net.pourpoint_network / net.next_downstream_label (malstroem/algorithms/net.py:142-192; the walk is
+ * flow.trace_downstream, flow.py:279-301).  For each of the n_pp start cells (pp_row, pp_col): out_down = the first
+ * label on the downstream path that differs from the start cell's label and, when has_background, from `background`;
+ * out_found = 0 when the path ends first (Python None).  labelled: int32 (label_bytes 4) or int64 (8).
+ * Geometry (net.py:166-167), host form only: when out_path_offsets != NULL it receives n_pp + 1 offsets into
+ * out_path_cells (flat cell indices of the cells visited, start cell first, answering cell last); the cells are
+ * written only if out_path_offsets[n_pp] <= path_capacity — otherwise call again with a larger buffer.
+ * MS_ERR_NOCONV on cyclic flow directions (the reference would not return). */
+int ms_pourpoint_network(const uint8_t *flowdir, const void *labelled, int label_bytes, int64_t rows, int64_t cols,
+                         int64_t n_pp, const int64_t *pp_row, const int64_t *pp_col, int64_t background,
+                         int has_background, int64_t *out_down, uint8_t *out_found, int64_t *out_path_offsets,
+                         int64_t *out_path_cells, int64_t path_capacity);
+int ms_pourpoint_network_dev(const uint8_t *flowdir, const void *labelled, int label_bytes, int64_t rows,
+                             int64_t cols, int64_t n_pp, const int64_t *pp_row, const int64_t *pp_col,
+                             int64_t background, int has_background, int64_t *out_down, uint8_t *out_found,
+                             void *stream);
+
+/* Network.rain_event (malstroem/network.py:75-129) for n_events rain depths at once.  Nodes in insertion order;
+ * parent[i] = index of the downstream node, -1 = root (dstrnodeid None), -2 = an id that is not a node.  Outputs
+ * are [n_events][n] row-major: rainv, spillv, v, pctv (NaN where the reference gives None: capacity 0);
+ * out_present[i] = 0 for nodes the reference never reaches from a root (their values are unspecified).
+ * Upstream spill is summed in insertion order of the upstream nodes, sum_mode 0 = plain float addition (sum()
+ * before CPython 3.12), 1 = Neumaier compensated (sum() from CPython 3.12 on).  `mm` is a HOST array in both forms
+ * (n_events <= 16). */
+int ms_rain_events(int64_t n, const int32_t *parent, const double *wshed_area, const double *bspot_vol,
+                   int64_t n_events, const double *mm, int sum_mode, double *out_rainv, double *out_spillv,
+                   double *out_v, double *out_pctv, uint8_t *out_present);
+int ms_rain_events_dev(int64_t n, const int32_t *parent, const double *wshed_area, const double *bspot_vol,
+                       int64_t n_events, const double *mm, int sum_mode, double *out_rainv, double *out_spillv,
+                       double *out_v, double *out_pctv, uint8_t *out_present, void *stream);
+
+/* The chain StreamTool + RainTool run on BluespotTool's tables (streams.py:66-100, rain.py:60-79), device resident,
+ * straight from a finished ms_rasters: node i = bluespot label i (label 0 included, as the reference does —
+ * bluespots.py:74), pour point = ppmin (or ppmax when use_accum_pourpoints), wshed_area = ws_count * cell_area,
+ * bspot_vol = st_sum * cell_area.  out_parent[nlabels + 1] = downstream label or -1; event tables as above,
+ * [n_events][nlabels + 1].  All outputs are device memory. */
+int ms_bluespot_network_dev(const ms_rasters *io, double cell_area, int use_accum_pourpoints, int64_t n_events,
+                            const double *mm, int sum_mode, int32_t *out_parent, double *out_rainv,
+                            double *out_spillv, double *out_v, double *out_pctv, void *stream);
+
 /* synthetic fractal DEM (malstroem_b200/synth.py, bit-identical), generated in place on the device */
 int ms_synth_fractal_dev(float *dem, int64_t rows, int64_t cols, int64_t row0, int64_t col0, int seed,
                          void *stream);

@@ -95,6 +95,12 @@ SIGNATURES = {
     "ms_pipeline_host_dev": (c_int, [c_p, c_p, c_p]),
     "ms_copies_wait": (c_int, []),
     "ms_synth_fractal_dev": (c_int, [c_p, c_i64, c_i64, c_i64, c_i64, c_int, c_p]),
+    "ms_pourpoint_network": (c_int, [c_p, c_p, c_int, c_i64, c_i64, c_i64, c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p,
+                                     c_i64]),
+    "ms_pourpoint_network_dev": (c_int, [c_p, c_p, c_int, c_i64, c_i64, c_i64, c_p, c_p, c_i64, c_int, c_p, c_p, c_p]),
+    "ms_rain_events": (c_int, [c_i64, c_p, c_p, c_p, c_i64, c_p, c_int, c_p, c_p, c_p, c_p, c_p]),
+    "ms_rain_events_dev": (c_int, [c_i64, c_p, c_p, c_p, c_i64, c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "ms_bluespot_network_dev": (c_int, [c_p, c_dbl, c_int, c_i64, c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),
 }
 
 

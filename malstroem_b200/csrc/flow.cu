@@ -415,3 +415,196 @@ int ms_watersheds_from_labels(const uint8_t *flowdir, void *labelled, int label_
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// SURVEY.md §8(f1).  net.pourpoint_network / net.next_downstream_label (net.py:142-192): from each pour point walk
+// downstream (flow.trace_downstream, flow.py:279-301) to the first cell whose label is neither the start cell's nor
+// the background.  That is K7 evaluated at the pour points: with a background label the walk uses K7's compressed
+// forest (ptr = first non-background or terminal cell at or below a cell), so a step through any stretch of
+// background costs one load; only stretches inside the pour point's own bluespot are walked cell by cell.
+// Geometry wanted: the plain walk, once to count the cells and once to write them.
+// ------------------------------------------------------------------------------------------------
+namespace ms {
+
+template <typename L, bool USE_PTR>
+__global__ void __launch_bounds__(128) k_pp_downstream(const uint8_t *__restrict__ fd, const L *__restrict__ lab,
+                                                       const int *__restrict__ ptr, int rows, int cols, int64_t np,
+                                                       const int64_t *__restrict__ pp_row,
+                                                       const int64_t *__restrict__ pp_col, L bg, int has_bg,
+                                                       int64_t *down, uint8_t *found, int64_t *path_len,
+                                                       const int64_t *__restrict__ path_off, int64_t *path_cells,
+                                                       int *err) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= np) return;
+    int r = (int)pp_row[k], c = (int)pp_col[k];
+    int64_t steps = 0, limit = (int64_t)rows * cols;
+    int64_t out = 0;
+    uint8_t ok = 0;
+    if (r >= 0 && r < rows && c >= 0 && c < cols) {
+        int i = r * cols + c;
+        const L src = lab[i];
+        int64_t *pc = path_cells ? path_cells + path_off[k] : nullptr;
+        if (pc) pc[0] = i;
+        steps = 1;
+        for (;;) {
+            int nr, nc;
+            if (!d8_next(r, c, fd[i], rows, cols, &nr, &nc)) break;
+            i = nr * cols + nc;
+            if (USE_PTR) {
+                i = ptr[i];                     // skips background cells; identity for labelled / terminal cells
+                nr = i / cols;
+                nc = i - nr * cols;
+            }
+            r = nr;
+            c = nc;
+            if (pc) pc[steps] = i;
+            steps++;
+            L l = lab[i];
+            if (l != src && !(has_bg && l == bg)) { out = (int64_t)l; ok = 1; break; }
+            if (steps > limit) { *err = 1; break; }
+        }
+    }
+    if (down) { down[k] = out; found[k] = ok; }
+    if (path_len) path_len[k] = steps;
+}
+
+template <typename L>
+static int pp_network_t(const uint8_t *fd, const L *lab, int64_t rows, int64_t cols, int64_t np, const int64_t *pp_row,
+                        const int64_t *pp_col, int64_t bg, int has_bg, int64_t *down, uint8_t *found,
+                        int64_t *path_len, cudaStream_t s) {
+    int64_t n = rows * cols;
+    DevBuf<int> err, ptr;
+    MS_TRY(err.alloc(1, s));
+    MS_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), s));
+    unsigned grid = cdiv(np, 128);
+    if (np > 0) {
+        // the forest pays off when there are many pour points; a handful (or a wanted geometry) walk cell by cell
+        bool forest = has_bg && !path_len && np >= 64;
+        if (forest) {
+            MS_TRY(ptr.alloc((size_t)n, s));
+            MS_TRY(ws_resolve<L>(fd, lab, ptr.p, nullptr, (L)bg, rows, cols, nullptr, s));
+            prof_units(np);
+            MS_LAUNCH((k_pp_downstream<L, true>), grid, 128, 0, s, fd, lab, ptr.p, (int)rows, (int)cols, np, pp_row,
+                      pp_col, (L)bg, has_bg, down, found, path_len, (const int64_t *)nullptr, (int64_t *)nullptr,
+                      err.p);
+        } else {
+            prof_units(np);
+            MS_LAUNCH((k_pp_downstream<L, false>), grid, 128, 0, s, fd, lab, (const int *)nullptr, (int)rows,
+                      (int)cols, np, pp_row, pp_col, (L)bg, has_bg, down, found, path_len, (const int64_t *)nullptr,
+                      (int64_t *)nullptr, err.p);
+        }
+    }
+    int64_t *h = host_flags().h;
+    MS_CUDA(cudaMemcpyAsync(h, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    if (*(int *)h) { set_error("pourpoint_network: cyclic flow directions"); return MS_ERR_NOCONV; }
+    return MS_OK;
+}
+
+int pp_network_dev_impl(const uint8_t *fd, const void *lab, int label_bytes, int64_t rows, int64_t cols, int64_t np,
+                        const int64_t *pp_row, const int64_t *pp_col, int64_t bg, int has_bg, int64_t *down,
+                        uint8_t *found, int64_t *path_len, cudaStream_t s) {
+    if (!fd || !lab || (np > 0 && (!pp_row || !pp_col || !down || !found))) {
+        set_error("pourpoint_network: null pointer");
+        return MS_ERR_ARG;
+    }
+    if (rows < 1 || cols < 1 || rows * cols > (1ll << 30) || np < 0) {
+        set_error("pourpoint_network: unsupported shape %lld x %lld", (long long)rows, (long long)cols);
+        return MS_ERR_SHAPE;
+    }
+    if (label_bytes == 4)
+        return pp_network_t<int32_t>(fd, (const int32_t *)lab, rows, cols, np, pp_row, pp_col, bg, has_bg, down, found,
+                                     path_len, s);
+    if (label_bytes == 8)
+        return pp_network_t<int64_t>(fd, (const int64_t *)lab, rows, cols, np, pp_row, pp_col, bg, has_bg, down, found,
+                                     path_len, s);
+    set_error("pourpoint_network: label_bytes must be 4 or 8");
+    return MS_ERR_ARG;
+}
+
+template <typename L>
+static int pp_paths_t(const uint8_t *fd, const L *lab, int64_t rows, int64_t cols, int64_t np, const int64_t *pp_row,
+                      const int64_t *pp_col, int64_t bg, int has_bg, const int64_t *off, int64_t *cells,
+                      cudaStream_t s) {
+    DevBuf<int> err;
+    MS_TRY(err.alloc(1, s));
+    MS_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), s));
+    MS_LAUNCH((k_pp_downstream<L, false>), cdiv(np, 128), 128, 0, s, fd, lab, (const int *)nullptr, (int)rows,
+              (int)cols, np, pp_row, pp_col, (L)bg, has_bg, (int64_t *)nullptr, (uint8_t *)nullptr,
+              (int64_t *)nullptr, off, cells, err.p);
+    return MS_OK;
+}
+
+}  // namespace ms
+
+extern "C" {
+
+int ms_pourpoint_network_dev(const uint8_t *flowdir, const void *labelled, int label_bytes, int64_t rows,
+                             int64_t cols, int64_t n_pp, const int64_t *pp_row, const int64_t *pp_col,
+                             int64_t background, int has_background, int64_t *out_down, uint8_t *out_found,
+                             void *stream) {
+    MS_TRY(ms::ensure_init());
+    return ms::pp_network_dev_impl(flowdir, labelled, label_bytes, rows, cols, n_pp, pp_row, pp_col, background,
+                                   has_background, out_down, out_found, nullptr, (cudaStream_t)stream);
+}
+
+int ms_pourpoint_network(const uint8_t *flowdir, const void *labelled, int label_bytes, int64_t rows, int64_t cols,
+                         int64_t n_pp, const int64_t *pp_row, const int64_t *pp_col, int64_t background,
+                         int has_background, int64_t *out_down, uint8_t *out_found, int64_t *out_path_offsets,
+                         int64_t *out_path_cells, int64_t path_capacity) {
+    MS_TRY(ms::ensure_init());
+    if (!flowdir || !labelled || rows < 1 || cols < 1 || n_pp < 0 || (label_bytes != 4 && label_bytes != 8) ||
+        (n_pp > 0 && (!pp_row || !pp_col || !out_down || !out_found))) {
+        ms::set_error("pourpoint_network: bad argument");
+        return MS_ERR_ARG;
+    }
+    if (rows * cols > (1ll << 30)) { ms::set_error("pourpoint_network: raster too large"); return MS_ERR_SHAPE; }
+    cudaStream_t s = nullptr;
+    size_t n = (size_t)(rows * cols), np = (size_t)n_pp;
+    ms::DevBuf<uint8_t> f, l, fnd;
+    ms::DevBuf<int64_t> pr, pc, dn, plen;
+    MS_TRY(f.alloc(n, s));
+    MS_TRY(l.alloc(n * label_bytes, s));
+    MS_TRY(pr.alloc(np, s));
+    MS_TRY(pc.alloc(np, s));
+    MS_TRY(dn.alloc(np, s));
+    MS_TRY(fnd.alloc(np, s));
+    MS_CUDA(cudaMemcpyAsync(f.p, flowdir, n, cudaMemcpyHostToDevice, s));
+    MS_CUDA(cudaMemcpyAsync(l.p, labelled, n * label_bytes, cudaMemcpyHostToDevice, s));
+    if (np) {
+        MS_CUDA(cudaMemcpyAsync(pr.p, pp_row, np * 8, cudaMemcpyHostToDevice, s));
+        MS_CUDA(cudaMemcpyAsync(pc.p, pp_col, np * 8, cudaMemcpyHostToDevice, s));
+    }
+    if (out_path_offsets) MS_TRY(plen.alloc(np, s));
+    MS_TRY(ms::pp_network_dev_impl(f.p, l.p, label_bytes, rows, cols, n_pp, pr.p, pc.p, background, has_background,
+                                   dn.p, fnd.p, out_path_offsets ? plen.p : nullptr, s));
+    if (np) {
+        MS_CUDA(cudaMemcpyAsync(out_down, dn.p, np * 8, cudaMemcpyDeviceToHost, s));
+        MS_CUDA(cudaMemcpyAsync(out_found, fnd.p, np, cudaMemcpyDeviceToHost, s));
+    }
+    if (out_path_offsets) {
+        // lengths -> offsets on the host (n_pp is the number of bluespots, not of cells)
+        if (np) MS_CUDA(cudaMemcpyAsync(out_path_offsets + 1, plen.p, np * 8, cudaMemcpyDeviceToHost, s));
+        MS_TRY(ms::stream_sync(s));
+        out_path_offsets[0] = 0;
+        for (size_t k = 0; k < np; k++) out_path_offsets[k + 1] += out_path_offsets[k];
+        int64_t total = out_path_offsets[np];
+        if (np && total > 0 && total <= path_capacity && out_path_cells) {
+            ms::DevBuf<int64_t> off, cells;
+            MS_TRY(off.alloc(np + 1, s));
+            MS_TRY(cells.alloc((size_t)total, s));
+            MS_CUDA(cudaMemcpyAsync(off.p, out_path_offsets, (np + 1) * 8, cudaMemcpyHostToDevice, s));
+            if (label_bytes == 4)
+                MS_TRY(ms::pp_paths_t<int32_t>(f.p, (const int32_t *)l.p, rows, cols, n_pp, pr.p, pc.p, background,
+                                               has_background, off.p, cells.p, s));
+            else
+                MS_TRY(ms::pp_paths_t<int64_t>(f.p, (const int64_t *)l.p, rows, cols, n_pp, pr.p, pc.p, background,
+                                               has_background, off.p, cells.p, s));
+            MS_CUDA(cudaMemcpyAsync(out_path_cells, cells.p, (size_t)total * 8, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    MS_TRY(ms::stream_sync(s));
+    return MS_OK;
+}
+
+}  // extern "C"

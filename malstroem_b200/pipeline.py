@@ -81,6 +81,29 @@ class RasterPipeline(object):
     def table(self, name):
         return self.tables[name][: self.nlabels + 1]
 
+    # ---- the bluespot network and rain events on the finished tables (SURVEY.md §8(f1,f2)) -----------
+    def network(self, cell_area=1.0, events_mm=(), use_accum_pourpoints=False, sum_mode=None):
+        """What StreamTool + RainTool compute from BluespotTool's output (streams.py:66-100, rain.py:60-79), device
+        resident: returns dict of cuda tensors — `parent` int32 [nlabels+1] (downstream bluespot, -1 = none) and
+        rainv / spillv / v / pctv float64 [n_events, nlabels+1] (pctv NaN where the capacity is 0)."""
+        from . import network as _network
+        n = self.nlabels + 1
+        mm = np.ascontiguousarray(np.atleast_1d(np.asarray(events_mm, dtype=np.float64)))
+        ne = int(mm.size)
+        if ne > 16:
+            raise ValueError("network: at most 16 rain events per pass")
+        res = {"parent": torch.empty((n,), dtype=torch.int32, device=self.device)}
+        for k in ("rainv", "spillv", "v", "pctv"):
+            res[k] = torch.empty((ne, n), dtype=torch.float64, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with _lib.lock:
+            _lib.check(_lib.lib().ms_bluespot_network_dev(
+                ctypes.byref(self.io), float(cell_area), 1 if use_accum_pourpoints else 0, ne, _lib.ptr(mm),
+                _network.SUM_MODE if sum_mode is None else sum_mode, res["parent"].data_ptr(),
+                res["rainv"].data_ptr(), res["spillv"].data_ptr(), res["v"].data_ptr(), res["pctv"].data_ptr(),
+                ctypes.c_void_p(stream)), "ms_bluespot_network_dev")
+        return res
+
     # ---- host-buffer run (bench `e2e`): H2D of the DEM, the run, D2H of every raster + table ---------
     def host_buffers(self):
         if self._host is None:

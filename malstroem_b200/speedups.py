@@ -11,7 +11,10 @@ import os
 import warnings
 
 from . import _lib
-from .algorithms import fill as _fill, flow as _flow, label as _label
+import importlib
+
+from . import network as _network
+from .algorithms import fill as _fill, flow as _flow, label as _label, net as _net
 
 available = os.path.exists(_lib.LIB_PATH)
 enabled = False
@@ -23,7 +26,11 @@ REBOUND = {
     "label": ("connected_components", "label_stats", "keep_labels", "label_min_index", "label_max_index",
               "label_count"),
 }
-_OURS = {"fill": _fill, "flow": _flow, "label": _label}
+# the pour-point network functions StreamTool resolves at call time (streams.py:72-74)
+REBOUND_NEXT = {
+    "net": ("next_downstream_label", "pourpoint_network", "geometric_pourpoint_network"),
+}
+_OURS = {"fill": _fill, "flow": _flow, "label": _label, "net": _net}
 
 
 def enable(target=None):
@@ -41,6 +48,25 @@ def enable(target=None):
         for name in names:
             _orig[(modname, name)] = (mod, getattr(mod, name))
             setattr(mod, name, getattr(_OURS[modname], name))
+    for modname, names in REBOUND_NEXT.items():
+        mod = getattr(target, modname, None)
+        if mod is None:
+            try:
+                mod = importlib.import_module(target.__name__ + "." + modname)
+            except ImportError:
+                continue
+        for name in names:
+            _orig[(modname, name)] = (mod, getattr(mod, name))
+            setattr(mod, name, getattr(_OURS[modname], name))
+    # RainTool holds the class itself (rain.py:17), so the method is replaced on the class;
+    # Network.rain_event below only needs the instance's `nodes` list, which the reference class keeps too
+    try:
+        ref_network = importlib.import_module(target.__name__.split(".")[0] + ".network")
+        cls = ref_network.Network
+        _orig[("network", "Network.rain_event")] = (cls, cls.__dict__["rain_event"])
+        cls.rain_event = _rain_event_on_reference_instance
+    except (ImportError, AttributeError, KeyError):
+        pass
     ref_speedups = getattr(target, "speedups", None)
     if ref_speedups is not None:
         _orig[("speedups", "enabled")] = (ref_speedups, ref_speedups.enabled)
@@ -48,11 +74,20 @@ def enable(target=None):
     enabled = True
 
 
+def _rain_event_on_reference_instance(self, mmrain):
+    """Network.rain_event (network.py:113-129) for an instance of the REFERENCE's class."""
+    ours = _network.Network.__new__(_network.Network)
+    ours.nodes = self.nodes
+    events = _network.Network.rain_events(ours, [mmrain])[0]
+    self._node_rain_values = {e['nodeid']: e for e in events}
+    return events
+
+
 def disable():
     global enabled
     if not _orig:
         return
     for (modname, name), (mod, fn) in _orig.items():
-        setattr(mod, name, fn)
+        setattr(mod, name.split(".")[-1], fn)
     _orig.clear()
     enabled = False
