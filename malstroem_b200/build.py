@@ -6,8 +6,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "csrc", "_obj")
-LIB = os.path.join(HERE, "libmalstroem_b200.so")
+# MS_BUILD_TAG=_x builds a variant (with MS_NVCC_EXTRA flags) into libmalstroem_b200_x.so; load it with MS_LIB=<path>
+TAG = os.environ.get("MS_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "csrc", "_obj" + TAG)
+LIB = os.path.join(HERE, "libmalstroem_b200%s.so" % TAG)
 SOURCES = ["core.cu", "primitives.cu", "fill.cu", "noflats.cu", "flow.cu", "accum.cu", "labels.cu", "pipeline.cu", "synth.cu", "network.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # no --use_fast_math: denormals (ftz=false), exact division and no FMA contraction are part of the contract

@@ -197,7 +197,16 @@ struct RelaxF64 {
 // to exactly dq ulps more, so the relaxation is an integer chamfer distance transform.  Cells that
 // cannot change (seeds, the raster border, cells outside the raster) are walls; they were taken into account as
 // sources once, by k_nf_seedcand.
+// In-tile relaxation of the integer form: NF_SWEEP 1 = directional cone sweeps (nf_tile_sweeps), 0 = the dirty-block
+// Jacobi iteration (RelaxI32::block + nf_tile_iterate).
+#ifndef NF_SWEEP
+#define NF_SWEEP 1
+#endif
+#if NF_SWEEP
+constexpr int NF_ILD = NF_T + 3;          // shared row stride in ints: odd, so rows AND columns are conflict-free
+#else
 constexpr int NF_ILD = NF_T + 8;          // shared row stride in ints: even (64-bit pair loads), 8 banks per row
+#endif
 constexpr int D_INF = 0x3fffffff;         // lake cell not reached yet
 constexpr int D_WALL = 0x40000000;        // not updatable, not a source
 constexpr int D_LIMIT = 0x20000000;       // a tile whose distances get this large is left to the float64 form
@@ -215,6 +224,7 @@ struct RelaxI32 {
     __device__ inline int2 weights(int lr, int lc) const {
         return wtab[(se[lr * NF_T + lc] - elo8) & (NF_NBIN - 1)];
     }
+#if !NF_SWEEP
     __device__ inline bool block(int b, unsigned *sides) const {
         const unsigned full = 0xffffffffu;
         int lane = threadIdx.x & 31;
@@ -260,6 +270,7 @@ struct RelaxI32 {
         *sides = sds;
         return any;
     }
+#endif
 };
 
 struct NfTileShared {
@@ -276,6 +287,7 @@ struct NfTileShared {
     int e, elo;        // largest / smallest binade exponent of the tile's lake cells (integer form needs e == elo)
     int bad;           // tile does not qualify for the integer form
     int dmax;          // largest finite distance loaded
+    int any;           // sweeps: some warp changed a cell in the current round
 };
 
 // blocks of the tile that can be affected by what the tile was queued for (bit 4: everything)
@@ -344,6 +356,136 @@ __device__ inline int nf_tile_iterate(const R &rx, NfTileShared &S, F &flush) {
     if (S.chgmask) flush();
     return it;
 }
+
+#if NF_SWEEP
+// ---- integer form, directional cone sweeps ---------------------------------------------------------------------
+// The tile problem is a chamfer distance transform with obstacles: D(c) = min over the 8 neighbours n of D(n) + w,
+// walls (>= D_WALL) neither change nor feed anything, apron cells feed but do not change.  Instead of relaxing 8x8
+// blocks until quiet, four warps each sweep the whole tile in one direction (down, up, right, left): line k is
+// computed from line k - 1 through the three neighbours of the direction's cone,
+//      D(k, j) = min( D(k, j), D(k-1, j) + short, min(D(k-1, j-1), D(k-1, j+1)) + diag ),
+// the previous line held in registers (a lane owns positions `lane` and `lane + 32` of a line, neighbours come by
+// shuffle), one line per ~40 cycles.  A shortest chamfer path in open water uses two move types of one octant, which
+// both lie in one of the four cones, so one round of sweeps settles open water; every bend around an obstacle costs
+// another round.  The sweeps run concurrently on the shared tile (updates by atomicMin: every candidate is an upper
+// bound, stale reads only delay); rounds repeat until one changes nothing, which is the fixed point.
+// DIR 0: down (lines = rows, ascending), 1: up, 2: right (lines = columns, ascending), 3: left.
+template <int DIR, bool UNI>
+__device__ inline bool nf_sweep(int *sd, const unsigned char *se, const int2 *wtab, int elo8, int *overflow,
+                                unsigned long long &chg, int &rings) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    constexpr bool ROWS = DIR < 2;                 // lines are rows
+    constexpr int STEP = (DIR & 1) ? -1 : 1;
+    constexpr int LS = ROWS ? NF_ILD : 1;          // stride between lines
+    constexpr int PS = ROWS ? 1 : NF_ILD;          // stride along a line
+    const int first = STEP > 0 ? 0 : NF_T - 1;
+    // cell (line, pos) of the tile: sd[(line + 1) * LS + (pos + 1) * PS]
+    int *base = sd + LS + PS;
+    const int up = (lane + 31) & 31, dn = (lane + 1) & 31;
+    int2 wu = wtab[0];
+    const int *prev = base + (first - STEP) * LS;  // the apron line the sweep starts from
+    int pA = prev[lane * PS], pB = prev[(lane + 32) * PS], eL = prev[-PS], eR = prev[NF_T * PS];
+    int *cur = base + first * LS;
+    int cA = cur[lane * PS], cB = cur[(lane + 32) * PS];
+    bool any = false;
+#pragma unroll 2
+    for (int k = 0; k < NF_T; k++) {
+        const int line = first + STEP * k;
+        // prefetch what the next line needs from shared memory (stale values only delay)
+        int *nxt = cur + STEP * LS;
+        int nA = 0, nB = 0, nL, nR;
+        nL = cur[-PS];
+        nR = cur[NF_T * PS];
+        if (k + 1 < NF_T) { nA = nxt[lane * PS]; nB = nxt[(lane + 32) * PS]; }
+        int rA = __shfl_sync(full, pA, up), rB = __shfl_sync(full, pB, up);
+        int qA = __shfl_sync(full, pA, dn), qB = __shfl_sync(full, pB, dn);
+        int LA = lane == 0 ? eL : rA, LB = lane == 0 ? rA : rB;
+        int RA = lane == 31 ? qB : qA, RB = lane == 31 ? eR : qB;
+        if (cA <= D_INF) {
+            int2 w = wu;
+            if (!UNI) {
+                int lr = ROWS ? line : lane, lc = ROWS ? lane : line;
+                w = wtab[(se[lr * NF_T + lc] - elo8) & (NF_NBIN - 1)];
+            }
+            int m = min(pA + w.x, min(LA, RA) + w.y);
+            if (m < cA) {
+                atomicMin(cur + lane * PS, m);
+                cA = m;
+                any = true;
+                if (m >= D_LIMIT) *overflow = 1;
+                int lr = ROWS ? line : lane, lc = ROWS ? lane : line;
+                chg |= 1ull << ((lr >> 3) * 8 + (lc >> 3));
+                rings |= (lr == 0 ? 1 : 0) | (lr == NF_T - 1 ? 2 : 0) | (lc == 0 ? 4 : 0) | (lc == NF_T - 1 ? 8 : 0);
+            }
+        }
+        if (cB <= D_INF) {
+            int2 w = wu;
+            if (!UNI) {
+                int lr = ROWS ? line : lane + 32, lc = ROWS ? lane + 32 : line;
+                w = wtab[(se[lr * NF_T + lc] - elo8) & (NF_NBIN - 1)];
+            }
+            int m = min(pB + w.x, min(LB, RB) + w.y);
+            if (m < cB) {
+                atomicMin(cur + (lane + 32) * PS, m);
+                cB = m;
+                any = true;
+                if (m >= D_LIMIT) *overflow = 1;
+                int lr = ROWS ? line : lane + 32, lc = ROWS ? lane + 32 : line;
+                chg |= 1ull << ((lr >> 3) * 8 + (lc >> 3));
+                rings |= (lr == 0 ? 1 : 0) | (lr == NF_T - 1 ? 2 : 0) | (lc == 0 ? 4 : 0) | (lc == NF_T - 1 ? 8 : 0);
+            }
+        }
+        pA = cA; pB = cB; eL = nL; eR = nR;
+        cA = nA; cB = nB;
+        cur = nxt;
+    }
+    return __any_sync(full, any);
+}
+
+// All four sweeps, round after round, until a round changes nothing.  On return S.chgmask / S.ring say which 8x8
+// blocks and which sides of the tile changed.  Called by all 256 threads (warps 4-7 only keep the barriers).
+__device__ inline int nf_tile_sweeps(int *sd, const unsigned char *se, NfTileShared &S) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool uni = S.e == S.elo;
+    const int elo8 = S.elo & 0xff;
+    unsigned long long chg = 0;
+    int rings = 0, rounds = 0;
+    for (;;) {
+        bool ch = false;
+        if (uni) {
+            if (warp == 0) ch = nf_sweep<0, true>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
+            else if (warp == 1) ch = nf_sweep<1, true>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
+            else if (warp == 2) ch = nf_sweep<2, true>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
+            else if (warp == 3) ch = nf_sweep<3, true>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
+        } else {
+            if (warp == 0) ch = nf_sweep<0, false>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
+            else if (warp == 1) ch = nf_sweep<1, false>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
+            else if (warp == 2) ch = nf_sweep<2, false>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
+            else if (warp == 3) ch = nf_sweep<3, false>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
+        }
+        if (ch && lane == 0) S.any = 1;
+        __syncthreads();
+        const int again = S.any && !S.bad;
+        rounds++;
+        __syncthreads();
+        if (!again) break;
+        if (threadIdx.x == 0) S.any = 0;
+        __syncthreads();
+    }
+    if (warp < 4) {
+        unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)chg);
+        unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(chg >> 32));
+        rings = __reduce_or_sync(0xffffffffu, rings);
+        if (lane == 0) {
+            if (lo | hi) atomicOr(&S.chgmask, ((unsigned long long)hi << 32) | lo);
+            if (rings) atomicOr(&S.ring, rings);
+        }
+    }
+    __syncthreads();
+    return rounds;
+}
+#endif
 
 // lake cell (w > f) -> integer distance; anything else -> wall.  Tracks the range of binades seen (elo..ehi).
 __device__ inline int nf_binade(double fd) {
@@ -449,6 +591,7 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
     float *sz = reinterpret_cast<float *>(smem_raw + (NF_T + 2) * NF_LD * 8);
     int *sdi = reinterpret_cast<int *>(smem_raw);
     unsigned char *se = smem_raw + (NF_T + 2) * NF_ILD * 4;          // integer form: binade byte per interior cell
+    float *sfi = reinterpret_cast<float *>(se + NF_T * NF_T);        // integer form: F per interior cell (write-back)
     __shared__ NfTileShared S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double capB = CAP ? (capB_in >= 0 ? capB_in : ((double)ctl->nonseed + 16.0) * dg * 1.001) : 0.0;
@@ -461,8 +604,9 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
     if (!p2p && *(volatile unsigned *)&ctl->tail == 0) return;      // nothing was queued (tail only grows)
 
     for (;;) {
-        __syncthreads();
-        if (tid == 0) {
+        // The next tile is taken by thread 32 while thread 0 is still signing off the previous one (below): both are
+        // chains of global atomics, and nobody touches S between the barrier that ends a visit and this point.
+        if (tid == 32) {
             // take the next FIFO entry; wait for it to be filled unless all work is done
             unsigned my = atomicAdd(&ctl->head, 1u);
             volatile int *slot = ring + (my % (unsigned)cap);
@@ -491,6 +635,7 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                 S.elo = INT_MAX;
                 S.bad = 0;
                 S.dmax = 0;
+                S.any = 0;
                 atomicAdd(&ctl->visits, 1);
             }
             S.k = t;
@@ -504,29 +649,30 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
 #endif
         const int ty = t / tiles_x, tx = t - ty * tiles_x;
         const int r0 = ty * NF_T, c0 = tx * NF_T;
-        // queue the neighbour tiles named by S.nb (tid 0, after the tile's writes were fenced)
+        // queue the neighbour tiles named by S.nb: threads 0..8 take one neighbour each (after the tile's writes were
+        // fenced), so the global atomics of all neighbours are in flight together instead of one thread's chain
         auto push_neighbours = [&]() {
             int nbm = S.nb;
-            for (int dy = -1; dy <= 1; dy++)
-                for (int dx = -1; dx <= 1; dx++) {
-                    if (!dy && !dx) continue;
-                    if (!(nbm & (1 << ((dy + 1) * 3 + (dx + 1))))) continue;
+                {
+                    const int dy = tid / 3 - 1, dx = tid % 3 - 1;
+                    if (tid >= 9 || (!dy && !dx)) return;
+                    if (!(nbm & (1 << ((dy + 1) * 3 + (dx + 1))))) return;
                     int y = ty + dy, x = tx + dx;
-                    if (x < 0 || x >= tiles_x) continue;
+                    if (x < 0 || x >= tiles_x) return;
                     // which side of the neighbour looks at us
                     int bits = (dy < 0 ? 2 : 0) | (dy > 0 ? 1 : 0) | (dx < 0 ? 8 : 0) | (dx > 0 ? 4 : 0);
                     if (dy && dx) bits = dy < 0 ? 2 : 1;      // a corner: one block of that side is enough
                     if (y < 0 || y >= tiles_y) {
                         // the tile lies in the neighbouring band: its flag word and FIFO are on another GPU
-                        if (!p2p) continue;
+                        if (!p2p) return;
                         const NfPeer &q = y < 0 ? pp->up : pp->down;
-                        if (!q.tileflag) continue;
+                        if (!q.tileflag) return;
                         int nbq = (y < 0 ? q.tiles_y - 1 : 0) * tiles_x + x;
                         if (atomicOr_system(q.tileflag + nbq, bits) == 0) nf_push(q.ring, q.cap, q.ctl, nbq, true, pp->gactive);
-                        continue;
+                        return;
                     }
                     int nb = y * tiles_x + x;
-                    if (!(__ldg(tilesides + nb) & bits)) continue;      // nothing there that could change
+                    if (!(__ldg(tilesides + nb) & bits)) return;      // nothing there that could change
                     // an idle tile (no side bits yet, not running) is queued by whoever sets its first side bit
                     if (p2p) {
                         if (atomicOr_system(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb, true, pp->gactive);
@@ -577,6 +723,7 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                         if (lr >= 1 && lr <= NF_T) {
                             se[(lr - 1) * NF_T + 2 * lane] = e0;
                             se[(lr - 1) * NF_T + 2 * lane + 1] = e1;
+                            *reinterpret_cast<float2 *>(sfi + (lr - 1) * NF_T + 2 * lane) = make_float2(rg[j].f0, rg[j].f1);
                         }
                     }
                 }
@@ -650,7 +797,7 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                                 int d = p[q];
                                 if (c + q < cols && d < D_INF) {
                                     size_t i = (size_t)r * cols + c + q;
-                                    double fd = (double)__ldg(zsrc + i);
+                                    double fd = (double)sfi[lr * NF_T + lc + q];
                                     double ulp = __longlong_as_double((long long)(nf_binade(fd) - 52 + 1023) << 52);
                                     W[i] = __dadd_rn(fd, __dmul_rn((double)d, ulp));
                                 }
@@ -698,8 +845,9 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                     }
                     __threadfence();
                     __syncthreads();
+                    push_neighbours();
+                    __syncthreads();
                     if (tid == 0) {
-                        push_neighbours();
                         S.nb = 0;
                         S.ring = 0;
                         S.chgmask = 0;
@@ -709,7 +857,12 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
 #ifdef NF_STATS
                 tc1 = clock64(); tg1 = gtimer();
 #endif
+#if NF_SWEEP
+                int its = nf_tile_sweeps(sdi, se, S);
+                if (S.chgmask) flush();
+#else
                 int its = nf_tile_iterate(rx, S, flush);
+#endif
 #ifdef NF_STATS
                 nit = its;
 #endif
@@ -793,7 +946,11 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                             if (hit) nbm |= 1 << ((dy + 1) * 3 + (dx + 1));
                         }
                     S.nb = nbm;
-                    push_neighbours();
+                }
+                __syncthreads();
+                push_neighbours();
+                __syncthreads();
+                if (tid == 0) {
                     S.nb = 0;
                     S.ring = 0;
                     S.chgmask = 0;
@@ -845,16 +1002,21 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
 // test of a halo-row cell would need a second halo row.)
 constexpr int NI_A = NF_T + 4;          // tile + 2-cell apron
 
+// With Dg != nullptr (the integer-raster solve, below) the kernel also writes the tile of the padded int32 raster
+// Dg — lake / flat cell: its distance above F in ulps (D_INF: not reached yet), anything else: D_WALL — and
+// tmeta[tile] = the binade range of the lake cells of the tile and its apron; *irbad is raised when a cell or tile
+// does not qualify for the integer form.
 __global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ z, const float *__restrict__ F,
                                                       double *__restrict__ W, int *tileflag, int *tilesides, NfCtl *ctl,
-                                                      int rows, int cols, int tiles_x, double sh, double dg, double capB) {
+                                                      int rows, int cols, int tiles_x, double sh, double dg, double capB,
+                                                      int *__restrict__ Dg, int P, int *tmeta, int *irbad) {
     __shared__ float sz[NI_A * NI_A], sf[NI_A * NI_A];
     __shared__ unsigned char fixedc[(NF_T + 2) * (NF_T + 2)];      // 1: W = z there for good (seed or raster border)
-    __shared__ int s_sides;
+    __shared__ int s_sides, s_elo, s_ehi, s_bad;
     int tile = blockIdx.x;
     int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     int r0 = ty * NF_T, c0 = tx * NF_T, tid = threadIdx.x;
-    if (tid == 0) s_sides = 0;
+    if (tid == 0) { s_sides = 0; s_elo = INT_MAX; s_ehi = INT_MIN; s_bad = 0; }
     for (int k = tid; k < NI_A * NI_A; k += 256) {
         int lr = k / NI_A, lc = k - lr * NI_A;
         int r = r0 + lr - 2, c = c0 + lc - 2;
@@ -878,13 +1040,27 @@ __global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ 
             }
         }
         fixedc[k] = fx;
+        if (Dg && !fx && r >= 0 && r < rows && c >= 0 && c < cols) {
+            // a lake cell of the tile or its apron: its binade counts for the tile's weight table
+            float f = sf[(lr + 1) * NI_A + (lc + 1)];
+            if (f == 0.f) atomicOr(&s_bad, 1);
+            else {
+                int e = nf_binade((double)f);
+                if (e < -900) atomicOr(&s_bad, 1);
+                atomicMin(&s_elo, e);
+                atomicMax(&s_ehi, e);
+            }
+        }
     }
     __syncthreads();
     int nonseed = 0, sides = 0;
     for (int k = tid; k < NF_T * NF_T; k += 256) {
         int lr = k >> 6, lc = k & 63;
         int r = r0 + lr, c = c0 + lc;
-        if (r >= rows || c >= cols) continue;
+        if (r >= rows || c >= cols) {
+            if (Dg) Dg[(size_t)(r + 1) * P + (c + 4)] = D_WALL;      // the padded raster covers whole tiles
+            continue;
+        }
         const unsigned char *fx = fixedc + (lr + 1) * (NF_T + 2) + (lc + 1);
         const float *pz = sz + (lr + 2) * NI_A + (lc + 2);
         double w;
@@ -907,6 +1083,12 @@ __global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ 
                      (lc == NF_T - 1 || c == cols - 2 ? 8 : 0);
         }
         W[(size_t)r * cols + c] = w;
+        if (Dg) {
+            int bad = 0, elo = 0, ehi = 0, dmax = 0;
+            unsigned char e8;
+            Dg[(size_t)(r + 1) * P + (c + 4)] = nf_to_int(w, sf[(lr + 2) * NI_A + (lc + 2)], bad, elo, ehi, dmax, &e8);
+            if (bad) atomicOr(&s_bad, 1);
+        }
     }
     if (sides) atomicOr(&s_sides, sides);
     int cnt = __syncthreads_count(nonseed > 0);
@@ -915,6 +1097,12 @@ __global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ 
     if (tid == 0 && cnt) {
         tileflag[tile] = 16;
         tilesides[tile] = s_sides;
+    }
+    if (Dg && tid == 0) {
+        int span = s_ehi >= s_elo ? s_ehi - s_elo : 0;
+        if (s_bad || span >= NF_NBIN) *irbad = 1;
+        // [15:0] lowest binade exponent (signed), [19:16] span, bit 20: the tile or its apron holds a lake cell
+        tmeta[tile] = s_ehi >= s_elo ? ((s_elo & 0xffff) | (span << 16) | (1 << 20)) : 0;
     }
 }
 
@@ -969,6 +1157,255 @@ __global__ void __launch_bounds__(256) k_nf_verify(const float *__restrict__ z, 
     if (threadIdx.x == 0 && cnt) atomicAdd(&ctl->nviol, cnt);
 }
 
+
+// =====================================================================================================
+// Integer-raster solve (single GPU, capped fast path).  ncu on the W-based solver above showed where a tile visit
+// goes: 40 % of all instructions convert the float64 tile + apron to the integer form and back, on every visit
+// (profiles/r01c_nf_*).  Here the integer form is the state: k_nf_init_tile writes a padded int32 raster Dg
+// (pitch P = 64 * tiles_x + 8, one wall row above and below, 4 wall columns left, >= 4 right, so every tile + apron
+// is an in-bounds, 16-byte aligned 66 x 72 block), a visit copies that block to shared memory with cp.async (no
+// registers, no conversion, one DRAM round trip), relaxes it, and stores the changed 8x8 blocks back as integers.
+// W = F + D * ulp(F) is written once at the end (k_nf_from_int).  The FIFO / flag protocol is the one of
+// k_nf_solve.  Anything that does not fit the integer form (k_nf_init_tile's *irbad, a distance beyond D_LIMIT,
+// weights that are not whole ulps) raises *irbad and the caller falls back to the W-based solver.
+// =====================================================================================================
+constexpr int IR_LD = NF_T + 8;                 // shared row = columns c0 - 4 .. c0 + 67 of Dg
+constexpr int IR_SMEM = (NF_T + 2) * IR_LD * 4 + NF_T * NF_T;
+
+__global__ void __launch_bounds__(256) k_fill_i32(int *p, int v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+struct RelaxIR {
+    int *sd;
+    const unsigned char *se;   // per interior cell: low byte of the binade exponent (only read when !uni)
+    const int2 *wtab;
+    int elo8;
+    bool uni;
+    int *overflow;
+    __device__ inline int2 weights(int lr, int lc) const {
+        return uni ? wtab[0] : wtab[(se[lr * NF_T + lc] - elo8) & (NF_NBIN - 1)];
+    }
+    __device__ inline bool block(int b, unsigned *sides) const {
+        const unsigned full = 0xffffffffu;
+        int lane = threadIdx.x & 31;
+        int lr = (b >> 3) * 8 + (lane >> 2), lc = (b & 7) * 8 + (lane & 3) * 2;
+        int *p = sd + (lr + 1) * IR_LD + (lc + 4);          // even index: (p[0], p[1]) is an aligned pair
+        int2 own = *reinterpret_cast<const int2 *>(p);
+        int w0 = own.x, w1 = own.y;
+        bool live = (w0 <= D_INF) || (w1 <= D_INF);
+        *sides = 0;
+        if (!__any_sync(full, live)) return false;
+        int sq = 0, dq = 0, sq1 = 0, dq1 = 0;
+        if (live) {
+            int2 wa = weights(lr, lc), wb = weights(lr, lc + 1);
+            sq = wa.x; dq = wa.y; sq1 = wb.x; dq1 = wb.y;
+        }
+        unsigned sds = 0;
+        bool any = false;
+        for (int it = 0;; it++) {
+            bool ch = false;
+            if (live) {
+                const int2 ua = *reinterpret_cast<const int2 *>(p - IR_LD - 2), ub = *reinterpret_cast<const int2 *>(p - IR_LD);
+                const int2 uc = *reinterpret_cast<const int2 *>(p - IR_LD + 2);
+                const int2 ma = *reinterpret_cast<const int2 *>(p - 2), mc = *reinterpret_cast<const int2 *>(p + 2);
+                const int2 da = *reinterpret_cast<const int2 *>(p + IR_LD - 2), db = *reinterpret_cast<const int2 *>(p + IR_LD);
+                const int2 dc = *reinterpret_cast<const int2 *>(p + IR_LD + 2);
+                const int a0 = ua.y, a1 = ub.x, a2 = ub.y, a3 = uc.x, l = ma.y, r = mc.x;
+                const int c0 = da.y, c1 = db.x, c2 = db.y, c3 = dc.x;
+                if (w0 <= D_INF) {
+                    int m = min(imin4(a0, a2, c0, c2) + dq, imin4(a1, l, w1, c1) + sq);
+                    if (m < w0) { w0 = m; p[0] = m; ch = true; if (m >= D_LIMIT) *overflow = 1; }
+                }
+                if (w1 <= D_INF) {
+                    int m = min(imin4(a1, a3, c1, c3) + dq1, imin4(a2, w0, r, c2) + sq1);
+                    if (m < w1) { w1 = m; p[1] = m; ch = true; if (m >= D_LIMIT) *overflow = 1; }
+                }
+            }
+            __syncwarp();
+            unsigned bal = __ballot_sync(full, ch);
+            if (!bal) break;
+            any = true;
+            sds |= nf_sides(bal);
+            if (it == NF_BLOCK_ITERS - 1) { sds |= 16u; break; }
+        }
+        *sides = sds;
+        return any;
+    }
+};
+
+__global__ void __launch_bounds__(256, 4) k_nf_solve_ir(const float *__restrict__ F, int *Dg, int P, int *ring, int cap,
+                                                        int *tileflag, const int *__restrict__ tilesides,
+                                                        const int *__restrict__ tmeta, NfCtl *ctl, int *irbad, int rows,
+                                                        int cols, int tiles_x, int tiles_y, double sh, double dg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int *sd = reinterpret_cast<int *>(smem_raw);
+    unsigned char *se = smem_raw + (NF_T + 2) * IR_LD * 4;
+    __shared__ NfTileShared S;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (*(volatile unsigned *)&ctl->tail == 0 || *(volatile int *)irbad) return;      // nothing queued / not for this form
+    const unsigned sd_base = (unsigned)__cvta_generic_to_shared(sd);
+
+    for (;;) {
+        // thread 32 takes the next tile while thread 0 still signs off the previous one (see k_nf_solve)
+        if (tid == 32) {
+            unsigned my = atomicAdd(&ctl->head, 1u);
+            volatile int *slot = ring + (my % (unsigned)cap);
+            int t = -1;
+            for (unsigned spins = 0;; spins++) {
+                t = *slot;
+                if (t >= 0) break;
+                if (*(volatile int *)&ctl->done) break;
+                __nanosleep(200);
+                if (spins > (1u << 23)) { atomicExch(&ctl->done, 2); break; }      // watchdog (~2 s): never hang the GPU
+            }
+            if (t >= 0) {
+                *slot = -1;
+                __threadfence();
+                S.flags = atomicExch(tileflag + t, NF_RUNNING) & NF_SIDES;
+                S.dirty[1] = 0;
+                S.dirty[2] = 0;
+                S.chgmask = 0;
+                S.ring = 0;
+                S.nb = 0;
+                S.grab[0] = S.grab[1] = S.grab[2] = 0;
+                S.midflush = 0;
+                S.bad = 0;
+                S.any = 0;
+                int meta = __ldg(tmeta + t);
+                S.elo = (int)(short)(meta & 0xffff);
+                S.e = S.elo + ((meta >> 16) & 15);
+                S.dmax = (meta >> 20) & 1;          // here: the tile or its apron holds a lake cell
+                atomicAdd(&ctl->visits, 1);
+            }
+            S.k = t;
+        }
+        __syncthreads();
+        const int t = S.k;
+        if (t < 0) break;
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        const int r0 = ty * NF_T, c0 = tx * NF_T;
+        if (S.dmax) {
+            // ---- tile + apron: 66 rows x 18 chunks of 16 bytes, straight from L2 / HBM into shared memory
+            const int *src0 = Dg + (size_t)r0 * P + c0;        // row r0 - 1, column c0 - 4 of the padded raster
+            for (int q = tid; q < (NF_T + 2) * 18; q += 256) {
+                int lr = q / 18, ch = q - lr * 18;
+                const int *src = src0 + (size_t)lr * P + ch * 4;
+                unsigned dst = sd_base + (unsigned)((lr * IR_LD + ch * 4) * 4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            const bool uni = S.e == S.elo;
+            if (!uni) {
+                // several binades in the tile: the per-cell binade byte comes from F
+                for (int q = tid; q < NF_T * NF_T; q += 256) {
+                    int r = r0 + (q >> 6), c = c0 + (q & 63);
+                    se[q] = (r < rows && c < cols) ? (unsigned char)(nf_binade((double)__ldg(F + (size_t)r * cols + c)) & 0xff) : 0;
+                }
+            }
+            // weights per binade: short must be a whole number of ulps, diag must not sit on a rounding tie
+            if (tid < NF_NBIN) {
+                int e = S.elo + tid;
+                int2 wt = make_int2(0, 0);
+                if (e <= S.e) {
+                    double inv_ulp = __longlong_as_double((long long)(1023 - (e - 52)) << 52);
+                    double sqd = sh * inv_ulp, dqx = dg * inv_ulp, dqd = rint(dqx);
+                    double fr2 = fabs(dqx - floor(dqx) - 0.5);
+                    bool good = sqd >= 1.0 && sqd == rint(sqd) && dqd >= 1.0 && fr2 > 1e-9 &&
+                                dqd < (double)(1 << 27) && sqd < (double)(1 << 27);
+                    if (good) wt = make_int2((int)sqd, (int)dqd);
+                    else S.bad = 1;
+                }
+                S.wtab[tid] = wt;
+            }
+            if (tid == 0) S.dirty[0] = nf_region(S.flags);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            if (!S.bad) {
+                RelaxIR rx{sd, se, S.wtab, S.elo & 0xff, uni, &S.bad};
+                auto flush = [&]() {
+                    if (S.bad) return;
+                    // the blocks that changed go back as they are: a lane holds two adjacent cells (8-byte store)
+                    unsigned long long mm = S.chgmask;
+                    for (int idx = 0; mm; idx++) {
+                        int b = __ffsll((long long)mm) - 1;
+                        mm &= mm - 1;
+                        if ((idx & 7) != warp) continue;
+                        int lr = (b >> 3) * 8 + (lane >> 2), lc = (b & 7) * 8 + (lane & 3) * 2;
+                        const int2 v = *reinterpret_cast<const int2 *>(sd + (lr + 1) * IR_LD + (lc + 4));
+                        *reinterpret_cast<int2 *>(Dg + (size_t)(r0 + lr + 1) * P + (c0 + lc + 4)) = v;
+                    }
+                    // neighbours that can gain from the new ring (see k_nf_solve)
+                    int side = tid >> 6, k = tid & 63;          // 0 top, 1 bottom, 2 left, 3 right
+                    if (S.ring & (1 << side)) {
+                        int lr = side == 0 ? 0 : (side == 1 ? NF_T - 1 : k);
+                        int lc = side == 2 ? 0 : (side == 3 ? NF_T - 1 : k);
+                        int d = sd[(lr + 1) * IR_LD + (lc + 4)];
+                        int nbm = 0;
+                        if (d < D_INF) {
+                            int2 wt = rx.weights(lr, lc);
+#pragma unroll
+                            for (int o = -1; o <= 1; o++) {
+                                int ar = side == 0 ? -1 : (side == 1 ? NF_T : lr + o);
+                                int ac = side == 2 ? -1 : (side == 3 ? NF_T : lc + o);
+                                int da = sd[(ar + 1) * IR_LD + (ac + 4)];
+                                int w = (o == 0) ? wt.x : wt.y;
+                                if (da <= D_INF && d + w < da) {
+                                    int dy = ar < 0 ? -1 : (ar >= NF_T ? 1 : 0), dx = ac < 0 ? -1 : (ac >= NF_T ? 1 : 0);
+                                    nbm |= 1 << ((dy + 1) * 3 + (dx + 1));
+                                }
+                            }
+                        }
+                        nbm = __reduce_or_sync(0xffffffffu, nbm);
+                        if (lane == 0 && nbm) atomicOr(&S.nb, nbm);
+                    }
+                    __threadfence();
+                    __syncthreads();
+                    if (tid < 9 && tid != 4) {
+                        const int dy = tid / 3 - 1, dx = tid % 3 - 1;
+                        const int y = ty + dy, x = tx + dx;
+                        if ((S.nb & (1 << tid)) && x >= 0 && x < tiles_x && y >= 0 && y < tiles_y) {
+                            int bits = (dy < 0 ? 2 : 0) | (dy > 0 ? 1 : 0) | (dx < 0 ? 8 : 0) | (dx > 0 ? 4 : 0);
+                            if (dy && dx) bits = dy < 0 ? 2 : 1;      // a corner: one block of that side is enough
+                            int nb = y * tiles_x + x;
+                            if ((__ldg(tilesides + nb) & bits) && atomicOr(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb);
+                        }
+                    }
+                    __syncthreads();
+                    if (tid == 0) { S.nb = 0; S.ring = 0; S.chgmask = 0; }
+                    __syncthreads();
+                };
+                nf_tile_iterate(rx, S, flush);
+            }
+            if (S.bad && tid == 0) atomicExch(irbad, 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // side bits that arrived while the tile ran mean it has to run again
+            if (atomicAnd(tileflag + t, ~NF_RUNNING) & NF_SIDES) nf_push(ring, cap, ctl, t);
+            __threadfence();
+            if (atomicSub(&ctl->pending, 1) == 1) atomicExch(&ctl->done, 1);
+        }
+    }
+}
+
+// W = F + D * ulp(F) for the lake / flat cells the integer solve reached (exact: one binade, D * ulp is a multiple
+// of ulp below 2^29 ulps).  Everything else keeps what k_nf_init_tile wrote (z, or +inf for an unreached cell,
+// which then fails the verification).
+__global__ void __launch_bounds__(256) k_nf_from_int(const float *__restrict__ F, const int *__restrict__ Dg, int P,
+                                                     double *__restrict__ W, int rows, int cols) {
+    int c = (blockIdx.x * 64 + (threadIdx.x & 63));
+    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (r >= rows || c >= cols) return;
+    int d = __ldg(Dg + (size_t)(r + 1) * P + (c + 4));
+    if (d >= D_INF) return;
+    size_t i = (size_t)r * cols + c;
+    double fd = (double)__ldg(F + i);
+    double ulp = __longlong_as_double((long long)(nf_binade(fd) - 52 + 1023) << 52);
+    W[i] = __dadd_rn(fd, __dmul_rn((double)d, ulp));
+}
+
 }  // namespace ms
 
 /* The cap of the fast path: candidates more than this above the plain fill are ignored.  The solution exceeds the
@@ -1017,6 +1454,37 @@ static int nf_launch_solve(const float *zsrc, double *W, int *ring, int cap, int
     return MS_OK;
 }
 
+int g_nf_ir = 1;           // MS_NF_IR=0 keeps the W-based solver (k_nf_solve) on the single-GPU capped path
+
+static int nf_launch_solve_ir(const float *F, int *Dg, int P, int *ring, int cap, int *tileflag, const int *tilesides,
+                              const int *tmeta, NfCtl *ctl, int *irbad, int rows, int cols, int tiles_x, int tiles_y,
+                              int ntiles, double sh, double dg, int64_t units, cudaStream_t s) {
+    static int grid_blocks = 0;
+    if (!grid_blocks) {
+        MS_CUDA(cudaFuncSetAttribute(k_nf_solve_ir, cudaFuncAttributeMaxDynamicSharedMemorySize, IR_SMEM));
+        int dev = 0, sms = 0, per_sm = 0;
+        MS_CUDA(cudaGetDevice(&dev));
+        MS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        MS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nf_solve_ir, 256, IR_SMEM));
+        if (per_sm < 1) { set_error("fill_terrain_no_flats: solver kernel does not fit on an SM"); return MS_ERR_CUDA; }
+        grid_blocks = sms * per_sm;
+    }
+    void *args[] = {(void *)&F, (void *)&Dg, (void *)&P, (void *)&ring, (void *)&cap, (void *)&tileflag,
+                    (void *)&tilesides, (void *)&tmeta, (void *)&ctl, (void *)&irbad, (void *)&rows, (void *)&cols,
+                    (void *)&tiles_x, (void *)&tiles_y, (void *)&sh, (void *)&dg};
+    int g = grid_blocks < ntiles ? grid_blocks : ntiles;
+    prof_units(units);
+    if (g_prof) prof_begin("k_nf_solve_ir", s);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_nf_solve_ir, dim3(g), dim3(256), args, IR_SMEM, s);
+    if (g_prof) prof_end(s);
+    g_launches++;
+    if (e != cudaSuccess) {
+        set_error("%s:%d: cooperative launch k_nf_solve_ir -> %s", __FILE__, __LINE__, cudaGetErrorString(e));
+        return MS_ERR_CUDA;
+    }
+    return MS_OK;
+}
+
 int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, double dg, double *out,
                            int64_t rows, int64_t cols, int64_t *stats, cudaStream_t s) {
     if (!dtm || !out) { set_error("fill_terrain_no_flats: null pointer"); return MS_ERR_ARG; }
@@ -1036,6 +1504,8 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
     if (!env_done) {
         const char *e = getenv("MS_NF_INT");
         if (e && e[0] == '0') g_nf_use_int = 0;
+        e = getenv("MS_NF_IR");
+        if (e && e[0] == '0') g_nf_ir = 0;
         env_done = true;
     }
     int tiles_x = (int)cdiv(cols, NF_T), tiles_y = (int)cdiv(rows, NF_T);
@@ -1050,6 +1520,16 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
     MS_TRY(ctl.alloc(1, s));
     bool cap = sh > 0 && dg > 0;      // capped fast path first; a verification failure falls back to the generic one
     const double cap_bound = ms_nf_cap_bound(rows, cols, dg);
+    // integer-raster form of the capped solve: padded int32 raster (see k_nf_solve_ir)
+    bool use_ir = cap && g_nf_use_int && g_nf_ir;
+    const int P = tiles_x * NF_T + 8;
+    const size_t dg_cells = (size_t)P * ((size_t)tiles_y * NF_T + 2);
+    DevBuf<int> Dg, tmeta, irbad;
+    if (use_ir) {
+        MS_TRY(Dg.alloc(dg_cells, s));
+        MS_TRY(tmeta.alloc((size_t)ntiles, s));
+        MS_TRY(irbad.alloc(1, s));
+    }
     dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
     int64_t visits = 0, tries = 0;
@@ -1059,14 +1539,25 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
         MS_CUDA(cudaMemsetAsync(tilesides.p, 0, (size_t)ntiles * sizeof(int), s));
         MS_CUDA(cudaMemsetAsync(ring.p, 0xff, (size_t)cap_ring * sizeof(int), s));
         MS_CUDA(cudaMemsetAsync(ctl.p, 0, sizeof(NfCtl), s));
+        const bool ir = cap && use_ir;
+        if (ir) {
+            prof_units((int64_t)dg_cells);
+            MS_LAUNCH(k_fill_i32, cdiv((int64_t)dg_cells, 256), 256, 0, s, Dg.p, D_WALL, dg_cells);
+            MS_CUDA(cudaMemsetAsync(irbad.p, 0, sizeof(int), s));
+        }
         if (cap)
             MS_LAUNCH(k_nf_init_tile, ntiles, 256, 0, s, dtm, filled, out, tileflag.p, tilesides.p, ctl.p, (int)rows,
-                      (int)cols, tiles_x, sh, dg, cap_bound);
+                      (int)cols, tiles_x, sh, dg, cap_bound, ir ? Dg.p : (int *)nullptr, P, tmeta.p, irbad.p);
         else
             MS_LAUNCH(k_nf_init, g2, 256, 0, s, dtm, filled, out, banned.p, tileflag.p, tilesides.p, ctl.p, (int)rows,
                       (int)cols, tiles_x, 0);
         MS_LAUNCH(k_nf_compact, cdiv(ntiles, 256), 256, 0, s, tileflag.p, ring.p, ctl.p, ntiles);
-        if (cap) {
+        if (ir) {
+            MS_TRY(nf_launch_solve_ir(filled, Dg.p, P, ring.p, cap_ring, tileflag.p, tilesides.p, tmeta.p, ctl.p, irbad.p,
+                                      (int)rows, (int)cols, tiles_x, tiles_y, ntiles, sh, dg, n, s));
+            prof_units(n);
+            MS_LAUNCH(k_nf_from_int, g2, 256, 0, s, filled, Dg.p, P, out, (int)rows, (int)cols);
+        } else if (cap) {
             MS_TRY(nf_launch_solve<true>(filled, out, ring.p, cap_ring, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols, tiles_x,
                                          tiles_y, ntiles, sh, dg, g_nf_use_int, cap_bound, 0, n, s));
         } else {
@@ -1075,8 +1566,15 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
         }
         MS_LAUNCH(k_nf_verify, g2, 256, 0, s, dtm, out, banned.p, ctl.p, (int)rows, (int)cols, sh, dg, 0);
         MS_CUDA(cudaMemcpyAsync(h, ctl.p, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+        int *h_irbad = (int *)(h + 1);
+        *h_irbad = 0;
+        if (ir) MS_CUDA(cudaMemcpyAsync(h_irbad, irbad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
         MS_TRY(ms::stream_sync(s));
         visits += h->visits;
+        if (ir && *h_irbad) {       // something does not fit the integer form: the W-based solver takes over
+            use_ir = false;
+            continue;
+        }
         if (h->done != 1 && h->tail != 0) {
             set_error("fill_terrain_no_flats: tile solver stopped early (done=%d, pending=%d)", h->done, h->pending);
             return MS_ERR_NOCONV;

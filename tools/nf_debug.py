@@ -41,7 +41,7 @@ nflog(log.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nl), 0)
 k = min(nl.value, 262144)
 log = log[: 4 * k].reshape(k, 4)
 os.makedirs("gpurun_out", exist_ok=True)
-np.save("gpurun_out/nf_log_%d.npy" % S, log)
+np.save("gpurun_out/nf_log_%d%s.npy" % (S, os.environ.get("MS_TAG", "")), log)
 print("logged", k, "visits")
 print("load phase: warp0 loads+convert %d cyc, reduce+sync %d cyc (means per visit)" % (out[13] // max(st[1], 1), out[14] // max(st[1], 1)))
 print("sample out-of-range cell: W=%r F=%r count=%d" % (np.array([out[13]], dtype=np.uint64).view(np.float64)[0], np.array([out[14]], dtype=np.uint64).view(np.float64)[0], out[12]))
