@@ -197,16 +197,7 @@ struct RelaxF64 {
 // to exactly dq ulps more, so the relaxation is an integer chamfer distance transform.  Cells that
 // cannot change (seeds, the raster border, cells outside the raster) are walls; they were taken into account as
 // sources once, by k_nf_seedcand.
-// In-tile relaxation of the integer form: NF_SWEEP 1 = directional cone sweeps (nf_tile_sweeps), 0 = the dirty-block
-// Jacobi iteration (RelaxI32::block + nf_tile_iterate).
-#ifndef NF_SWEEP
-#define NF_SWEEP 1
-#endif
-#if NF_SWEEP
-constexpr int NF_ILD = NF_T + 3;          // shared row stride in ints: odd, so rows AND columns are conflict-free
-#else
 constexpr int NF_ILD = NF_T + 8;          // shared row stride in ints: even (64-bit pair loads), 8 banks per row
-#endif
 constexpr int D_INF = 0x3fffffff;         // lake cell not reached yet
 constexpr int D_WALL = 0x40000000;        // not updatable, not a source
 constexpr int D_LIMIT = 0x20000000;       // a tile whose distances get this large is left to the float64 form
@@ -224,7 +215,6 @@ struct RelaxI32 {
     __device__ inline int2 weights(int lr, int lc) const {
         return wtab[(se[lr * NF_T + lc] - elo8) & (NF_NBIN - 1)];
     }
-#if !NF_SWEEP
     __device__ inline bool block(int b, unsigned *sides) const {
         const unsigned full = 0xffffffffu;
         int lane = threadIdx.x & 31;
@@ -270,7 +260,6 @@ struct RelaxI32 {
         *sides = sds;
         return any;
     }
-#endif
 };
 
 struct NfTileShared {
@@ -351,141 +340,12 @@ __device__ inline int nf_tile_iterate(const R &rx, NfTileShared &S, F &flush) {
             if (rings) atomicOr(&S.ring, rings);
         }
         __syncthreads();
-        if (NF_MIDFLUSH && S.midflush && S.ring && (NF_FLUSH_ALWAYS || ((it + 1) & it) == 0)) flush();
+        if (S.midflush && S.ring && (NF_FLUSH_ALWAYS || ((it + 1) & it) == 0)) flush();
     }
     if (S.chgmask) flush();
     return it;
 }
 
-#if NF_SWEEP
-// ---- integer form, directional cone sweeps ---------------------------------------------------------------------
-// The tile problem is a chamfer distance transform with obstacles: D(c) = min over the 8 neighbours n of D(n) + w,
-// walls (>= D_WALL) neither change nor feed anything, apron cells feed but do not change.  Instead of relaxing 8x8
-// blocks until quiet, four warps each sweep the whole tile in one direction (down, up, right, left): line k is
-// computed from line k - 1 through the three neighbours of the direction's cone,
-//      D(k, j) = min( D(k, j), D(k-1, j) + short, min(D(k-1, j-1), D(k-1, j+1)) + diag ),
-// the previous line held in registers (a lane owns positions `lane` and `lane + 32` of a line, neighbours come by
-// shuffle), one line per ~40 cycles.  A shortest chamfer path in open water uses two move types of one octant, which
-// both lie in one of the four cones, so one round of sweeps settles open water; every bend around an obstacle costs
-// another round.  The sweeps run concurrently on the shared tile (updates by atomicMin: every candidate is an upper
-// bound, stale reads only delay); rounds repeat until one changes nothing, which is the fixed point.
-// DIR 0: down (lines = rows, ascending), 1: up, 2: right (lines = columns, ascending), 3: left.
-template <int DIR, bool UNI>
-__device__ inline bool nf_sweep(int *sd, const unsigned char *se, const int2 *wtab, int elo8, int *overflow,
-                                unsigned long long &chg, int &rings) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    constexpr bool ROWS = DIR < 2;                 // lines are rows
-    constexpr int STEP = (DIR & 1) ? -1 : 1;
-    constexpr int LS = ROWS ? NF_ILD : 1;          // stride between lines
-    constexpr int PS = ROWS ? 1 : NF_ILD;          // stride along a line
-    const int first = STEP > 0 ? 0 : NF_T - 1;
-    // cell (line, pos) of the tile: sd[(line + 1) * LS + (pos + 1) * PS]
-    int *base = sd + LS + PS;
-    const int up = (lane + 31) & 31, dn = (lane + 1) & 31;
-    int2 wu = wtab[0];
-    const int *prev = base + (first - STEP) * LS;  // the apron line the sweep starts from
-    int pA = prev[lane * PS], pB = prev[(lane + 32) * PS], eL = prev[-PS], eR = prev[NF_T * PS];
-    int *cur = base + first * LS;
-    int cA = cur[lane * PS], cB = cur[(lane + 32) * PS];
-    bool any = false;
-#pragma unroll 2
-    for (int k = 0; k < NF_T; k++) {
-        const int line = first + STEP * k;
-        // prefetch what the next line needs from shared memory (stale values only delay)
-        int *nxt = cur + STEP * LS;
-        int nA = 0, nB = 0, nL, nR;
-        nL = cur[-PS];
-        nR = cur[NF_T * PS];
-        if (k + 1 < NF_T) { nA = nxt[lane * PS]; nB = nxt[(lane + 32) * PS]; }
-        int rA = __shfl_sync(full, pA, up), rB = __shfl_sync(full, pB, up);
-        int qA = __shfl_sync(full, pA, dn), qB = __shfl_sync(full, pB, dn);
-        int LA = lane == 0 ? eL : rA, LB = lane == 0 ? rA : rB;
-        int RA = lane == 31 ? qB : qA, RB = lane == 31 ? eR : qB;
-        if (cA <= D_INF) {
-            int2 w = wu;
-            if (!UNI) {
-                int lr = ROWS ? line : lane, lc = ROWS ? lane : line;
-                w = wtab[(se[lr * NF_T + lc] - elo8) & (NF_NBIN - 1)];
-            }
-            int m = min(pA + w.x, min(LA, RA) + w.y);
-            if (m < cA) {
-                atomicMin(cur + lane * PS, m);
-                cA = m;
-                any = true;
-                if (m >= D_LIMIT) *overflow = 1;
-                int lr = ROWS ? line : lane, lc = ROWS ? lane : line;
-                chg |= 1ull << ((lr >> 3) * 8 + (lc >> 3));
-                rings |= (lr == 0 ? 1 : 0) | (lr == NF_T - 1 ? 2 : 0) | (lc == 0 ? 4 : 0) | (lc == NF_T - 1 ? 8 : 0);
-            }
-        }
-        if (cB <= D_INF) {
-            int2 w = wu;
-            if (!UNI) {
-                int lr = ROWS ? line : lane + 32, lc = ROWS ? lane + 32 : line;
-                w = wtab[(se[lr * NF_T + lc] - elo8) & (NF_NBIN - 1)];
-            }
-            int m = min(pB + w.x, min(LB, RB) + w.y);
-            if (m < cB) {
-                atomicMin(cur + (lane + 32) * PS, m);
-                cB = m;
-                any = true;
-                if (m >= D_LIMIT) *overflow = 1;
-                int lr = ROWS ? line : lane + 32, lc = ROWS ? lane + 32 : line;
-                chg |= 1ull << ((lr >> 3) * 8 + (lc >> 3));
-                rings |= (lr == 0 ? 1 : 0) | (lr == NF_T - 1 ? 2 : 0) | (lc == 0 ? 4 : 0) | (lc == NF_T - 1 ? 8 : 0);
-            }
-        }
-        pA = cA; pB = cB; eL = nL; eR = nR;
-        cA = nA; cB = nB;
-        cur = nxt;
-    }
-    return __any_sync(full, any);
-}
-
-// All four sweeps, round after round, until a round changes nothing.  On return S.chgmask / S.ring say which 8x8
-// blocks and which sides of the tile changed.  Called by all 256 threads (warps 4-7 only keep the barriers).
-__device__ inline int nf_tile_sweeps(int *sd, const unsigned char *se, NfTileShared &S) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool uni = S.e == S.elo;
-    const int elo8 = S.elo & 0xff;
-    unsigned long long chg = 0;
-    int rings = 0, rounds = 0;
-    for (;;) {
-        bool ch = false;
-        if (uni) {
-            if (warp == 0) ch = nf_sweep<0, true>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
-            else if (warp == 1) ch = nf_sweep<1, true>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
-            else if (warp == 2) ch = nf_sweep<2, true>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
-            else if (warp == 3) ch = nf_sweep<3, true>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
-        } else {
-            if (warp == 0) ch = nf_sweep<0, false>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
-            else if (warp == 1) ch = nf_sweep<1, false>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
-            else if (warp == 2) ch = nf_sweep<2, false>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
-            else if (warp == 3) ch = nf_sweep<3, false>(sd, se, S.wtab, elo8, &S.bad, chg, rings);
-        }
-        if (ch && lane == 0) S.any = 1;
-        __syncthreads();
-        const int again = S.any && !S.bad;
-        rounds++;
-        __syncthreads();
-        if (!again) break;
-        if (threadIdx.x == 0) S.any = 0;
-        __syncthreads();
-    }
-    if (warp < 4) {
-        unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)chg);
-        unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(chg >> 32));
-        rings = __reduce_or_sync(0xffffffffu, rings);
-        if (lane == 0) {
-            if (lo | hi) atomicOr(&S.chgmask, ((unsigned long long)hi << 32) | lo);
-            if (rings) atomicOr(&S.ring, rings);
-        }
-    }
-    __syncthreads();
-    return rounds;
-}
-#endif
 
 // lake cell (w > f) -> integer distance; anything else -> wall.  Tracks the range of binades seen (elo..ehi).
 __device__ inline int nf_binade(double fd) {
@@ -530,8 +390,8 @@ __device__ inline int nf_to_int(double w, float f, int &bad, int &elo, int &ehi,
 constexpr int NF_SIDES = 31;
 constexpr int NF_RUNNING = 256;
 // FIFO capacity = tiles + this: a tile is queued at most once, and every CTA of the grid may hold a ticket for an
-// entry that is not filled yet — two tickets must never share a slot (the grid is at most 148 SMs x 4 CTAs)
-constexpr int NF_RING_SLACK = 1024;
+// entry that is not filled yet — two tickets must never share a slot (the grid is at most 148 SMs x 8 CTAs)
+constexpr int NF_RING_SLACK = 2048;
 
 // ---- row bands fused over NVLink peer memory (P2P) ---------------------------------------------------------
 // Every band's solver runs at the same time, one cooperative launch per GPU.  A band's FIFO, tile flags and two
@@ -857,12 +717,7 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
 #ifdef NF_STATS
                 tc1 = clock64(); tg1 = gtimer();
 #endif
-#if NF_SWEEP
-                int its = nf_tile_sweeps(sdi, se, S);
-                if (S.chgmask) flush();
-#else
                 int its = nf_tile_iterate(rx, S, flush);
-#endif
 #ifdef NF_STATS
                 nit = its;
 #endif
@@ -1171,6 +1026,11 @@ __global__ void __launch_bounds__(256) k_nf_verify(const float *__restrict__ z, 
 // =====================================================================================================
 constexpr int IR_LD = NF_T + 8;                 // shared row = columns c0 - 4 .. c0 + 67 of Dg
 constexpr int IR_SMEM = (NF_T + 2) * IR_LD * 4 + NF_T * NF_T;
+// threads per CTA of the integer-raster solver.  A visit is mostly one dependent chain (stall_barrier dominates the
+// warp samples), so more, smaller CTAs per SM keep more tiles in flight while the FIFO is full.
+#ifndef IR_NT
+#define IR_NT 256
+#endif
 
 __global__ void __launch_bounds__(256) k_fill_i32(int *p, int v, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1235,7 +1095,175 @@ struct RelaxIR {
     }
 };
 
-__global__ void __launch_bounds__(256, 4) k_nf_solve_ir(const float *__restrict__ F, int *Dg, int P, int *ring, int cap,
+// ---- in-tile relaxation by directional cone sweeps with dirty-line gating (IR_SWEEP 1; 0 = dirty 8x8 blocks) ----
+// The tile problem is a chamfer distance transform with obstacles.  A sweep computes line k from line k - 1 through
+// the three neighbours of its direction's cone (down, up: lines are rows; right, left: lines are columns),
+//      D(k, j) = min( D(k, j), D(k-1, j) + short, min(D(k-1, j-1), D(k-1, j+1)) + diag ),
+// one warp per direction, the previous line in registers (a lane owns positions `lane` and `lane + 32`, neighbours
+// by shuffle), branch-free, ~60 cycles per line.  A shortest chamfer path in open water uses two move types of one
+// octant, both of which lie in one cone, so one sweep carries a wave straight across the tile; every bend around an
+// obstacle needs another round.  Gating: per direction a 64-bit mask of lines that must be looked at (because the
+// line before them changed).  A sweep starts at its first dirty line and stops when nothing it carries forward
+// changed and no dirty line lies ahead; every change marks the lines that read the changed cell in the other
+// three directions.  The four sweeps of a round run concurrently on the shared tile (updates by atomicMin: every
+// candidate is an upper bound, stale reads only delay); rounds repeat until all masks are empty = the fixed point.
+#ifndef IR_SWEEP
+#define IR_SWEEP 0
+#endif
+// IR_MIDFLUSH 1: while CTAs are idle (fewer tiles queued or running than the grid has CTAs) a tile forwards its ring
+// to the neighbours after iterations 1, 2, 4, ... instead of only when it has settled, so the wave of a large lake
+// is pipelined across tiles in the tail of the solve.  Measured at 8192^2 (round 1): 66 k -> 72 k visits, no-flats
+// stage 5.9 -> 6.3 ms — off.  IR_SWEEP 1 (the cone sweeps above) measured 6.65 ms against 5.9 ms for the dirty
+// blocks: a single warp runs a line in ~350 cycles (85 dependent instructions), so a sweep across the tile costs as
+// much as the block iteration does with all 8 warps — off as well; both are kept as measured alternatives.
+#ifndef IR_MIDFLUSH
+#define IR_MIDFLUSH 0
+#endif
+
+struct IrSweepState {
+    unsigned long long mA, mB;     // lines in which this lane's first / second cell changed (all rounds of a visit)
+    int vmax;                      // largest value written
+};
+
+template <int DIR, bool UNI>
+__device__ inline void ir_sweep(int *sd, const RelaxIR &rx, unsigned *ld, IrSweepState &st) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    constexpr bool ROWS = DIR < 2;
+    constexpr int STEP = (DIR & 1) ? -1 : 1;
+    constexpr int LS = ROWS ? IR_LD : 1;           // stride between lines
+    constexpr int PS = ROWS ? 1 : IR_LD;           // stride along a line
+    constexpr int OPP = DIR ^ 1, XUP = ROWS ? 2 : 0, XDN = ROWS ? 3 : 1;
+    unsigned lo = 0, hi = 0;
+    if (lane == 0) { lo = atomicExch(&ld[DIR * 2], 0u); hi = atomicExch(&ld[DIR * 2 + 1], 0u); }
+    lo = __shfl_sync(full, lo, 0);
+    hi = __shfl_sync(full, hi, 0);
+    unsigned long long m = ((unsigned long long)hi << 32) | lo;
+    if (!m) return;
+    if (STEP < 0) m = __brevll(m);                 // bit k = the k-th line in sweep order
+    const int k0 = __ffsll((long long)m) - 1;
+    const int first = STEP > 0 ? 0 : NF_T - 1;
+    int *base = sd + IR_LD + 4;                    // cell (0, 0)
+    const int up = (lane + 31) & 31, dn = (lane + 1) & 31;
+    const int2 wu = rx.wtab[0];
+    int *cur = base + (first + STEP * k0) * LS;
+    const int *prev = cur - STEP * LS;
+    int pA = prev[lane * PS], pB = prev[(lane + 32) * PS], eL = prev[-PS], eR = prev[NF_T * PS];
+    int cA = cur[lane * PS], cB = cur[(lane + 32) * PS];
+    bool carry = false;
+    unsigned long long opp = 0;
+    unsigned posA = 0, posB = 0;
+    for (int k = k0; k < NF_T; k++) {
+        if (!carry && !(m >> k)) break;            // nothing carried forward, no dirty line ahead
+        const int line = first + STEP * k;
+        int *nxt = cur + STEP * LS;
+        // what the next line needs from shared memory (the clamp keeps the last prefetch inside the apron)
+        const int nL = cur[-PS], nR = cur[NF_T * PS];
+        const int nA = nxt[lane * PS], nB = nxt[(lane + 32) * PS];
+        const int rA = __shfl_sync(full, pA, up), rB = __shfl_sync(full, pB, up);
+        const int qA = __shfl_sync(full, pA, dn), qB = __shfl_sync(full, pB, dn);
+        const int LA = lane == 0 ? eL : rA, LB = lane == 0 ? rA : rB;
+        const int RA = lane == 31 ? qB : qA, RB = lane == 31 ? eR : qB;
+        int2 wa = wu, wb = wu;
+        if (!UNI) {
+            wa = ROWS ? rx.weights(line, lane) : rx.weights(lane, line);
+            wb = ROWS ? rx.weights(line, lane + 32) : rx.weights(lane + 32, line);
+        }
+        const int mAv = min(pA + wa.x, min(LA, RA) + wa.y);
+        const int mBv = min(pB + wb.x, min(LB, RB) + wb.y);
+        const bool uA = cA <= D_INF && mAv < cA, uB = cB <= D_INF && mBv < cB;
+        if (uA) atomicMin(cur + lane * PS, mAv);
+        if (uB) atomicMin(cur + (lane + 32) * PS, mBv);
+        cA = uA ? mAv : cA;
+        cB = uB ? mBv : cB;
+        st.mA |= (unsigned long long)uA << line;
+        st.mB |= (unsigned long long)uB << line;
+        st.vmax = max(st.vmax, max(uA ? mAv : 0, uB ? mBv : 0));
+        const unsigned bA = __ballot_sync(full, uA), bB = __ballot_sync(full, uB);
+        carry = (bA | bB) != 0;
+        if (carry) {
+            // remember which lines the other sweeps must look at (kept in registers, published after the sweep:
+            // the masks are only read at the start of a sweep)
+            const int back = line - STEP;          // the opposite sweep reads this line when it computes `back`
+            if (back >= 0 && back < NF_T) opp |= 1ull << back;
+            posA |= bA;
+            posB |= bB;
+        }
+        pA = cA; pB = cB; eL = nL; eR = nR;
+        cA = nA; cB = nB;
+        cur = nxt;
+    }
+    if (lane == 0 && (opp | posA | posB)) {
+        __threadfence_block();
+        // the crossing sweeps: position j changed -> their lines j + 1 (ascending) and j - 1 (descending)
+        const unsigned ulo = posA << 1, uhi = (posB << 1) | (posA >> 31);
+        const unsigned dlo = (posA >> 1) | (posB << 31), dhi = posB >> 1;
+        if ((unsigned)opp) atomicOr(&ld[OPP * 2], (unsigned)opp);
+        if ((unsigned)(opp >> 32)) atomicOr(&ld[OPP * 2 + 1], (unsigned)(opp >> 32));
+        if (ulo) atomicOr(&ld[XUP * 2], ulo);
+        if (uhi) atomicOr(&ld[XUP * 2 + 1], uhi);
+        if (dlo) atomicOr(&ld[XDN * 2], dlo);
+        if (dhi) atomicOr(&ld[XDN * 2 + 1], dhi);
+    }
+}
+
+// All sweeps, round after round, until no line is dirty.  On return S.chgmask / S.ring say which 8x8 blocks and which
+// sides of the tile changed; S.bad is raised when a distance left the trusted range.  Called by all 256 threads
+// (warps 4-7 only keep the barriers); S.ld was set from the tile's flag word before the preceding barrier.
+__device__ inline int ir_tile_sweeps(int *sd, const RelaxIR &rx, NfTileShared &S, unsigned *ld) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    IrSweepState st{0ull, 0ull, 0};
+    int rounds = 0;
+    for (;;) {
+        if (rx.uni) {
+            if (warp == 0) ir_sweep<0, true>(sd, rx, ld, st);
+            else if (warp == 1) ir_sweep<1, true>(sd, rx, ld, st);
+            else if (warp == 2) ir_sweep<2, true>(sd, rx, ld, st);
+            else if (warp == 3) ir_sweep<3, true>(sd, rx, ld, st);
+        } else {
+            if (warp == 0) ir_sweep<0, false>(sd, rx, ld, st);
+            else if (warp == 1) ir_sweep<1, false>(sd, rx, ld, st);
+            else if (warp == 2) ir_sweep<2, false>(sd, rx, ld, st);
+            else if (warp == 3) ir_sweep<3, false>(sd, rx, ld, st);
+        }
+        rounds++;
+        __syncthreads();
+        const unsigned any = ld[0] | ld[1] | ld[2] | ld[3] | ld[4] | ld[5] | ld[6] | ld[7];
+        __syncthreads();
+        if (!any) break;
+    }
+    if (warp < 4) {
+        // lines x positions -> 8x8 blocks and ring sides
+        const bool rows = warp < 2;
+        unsigned long long chg = 0;
+        int rings = 0;
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const bool a = (st.mA >> (8 * g)) & 0xffull, b = (st.mB >> (8 * g)) & 0xffull;
+            // rows-type sweep: line group g = block row, position lane (+32) -> block column; columns-type: transposed
+            if (a) chg |= 1ull << (rows ? g * 8 + (lane >> 3) : (lane >> 3) * 8 + g);
+            if (b) chg |= 1ull << (rows ? g * 8 + 4 + (lane >> 3) : (4 + (lane >> 3)) * 8 + g);
+        }
+        const unsigned long long mm = st.mA | st.mB;
+        const int first_line = (int)(mm & 1ull), last_line = (int)(mm >> 63);
+        const int first_pos = (lane == 0 && st.mA) ? 1 : 0, last_pos = (lane == 31 && st.mB) ? 1 : 0;
+        if (rows) rings = first_line * 1 | last_line * 2 | first_pos * 4 | last_pos * 8;
+        else rings = first_line * 4 | last_line * 8 | first_pos * 1 | last_pos * 2;
+        unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)chg);
+        unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(chg >> 32));
+        rings = __reduce_or_sync(0xffffffffu, rings);
+        int vmax = __reduce_max_sync(0xffffffffu, st.vmax);
+        if (lane == 0) {
+            if (lo | hi) atomicOr(&S.chgmask, ((unsigned long long)hi << 32) | lo);
+            if (rings) atomicOr(&S.ring, rings);
+            if (vmax >= D_LIMIT) S.bad = 1;
+        }
+    }
+    __syncthreads();
+    return rounds;
+}
+
+__global__ void __launch_bounds__(IR_NT, 1024 / IR_NT) k_nf_solve_ir(const float *__restrict__ F, int *Dg, int P, int *ring, int cap,
                                                         int *tileflag, const int *__restrict__ tilesides,
                                                         const int *__restrict__ tmeta, NfCtl *ctl, int *irbad, int rows,
                                                         int cols, int tiles_x, int tiles_y, double sh, double dg) {
@@ -1243,6 +1271,7 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve_ir(const float *__restrict_
     int *sd = reinterpret_cast<int *>(smem_raw);
     unsigned char *se = smem_raw + (NF_T + 2) * IR_LD * 4;
     __shared__ NfTileShared S;
+    __shared__ unsigned s_ld[8];            // IR_SWEEP: dirty lines per direction (down, up, right, left) x 2 words
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (*(volatile unsigned *)&ctl->tail == 0 || *(volatile int *)irbad) return;      // nothing queued / not for this form
     const unsigned sd_base = (unsigned)__cvta_generic_to_shared(sd);
@@ -1270,7 +1299,7 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve_ir(const float *__restrict_
                 S.ring = 0;
                 S.nb = 0;
                 S.grab[0] = S.grab[1] = S.grab[2] = 0;
-                S.midflush = 0;
+                S.midflush = IR_MIDFLUSH && *(volatile int *)&ctl->pending < (int)gridDim.x;
                 S.bad = 0;
                 S.any = 0;
                 int meta = __ldg(tmeta + t);
@@ -1284,12 +1313,15 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve_ir(const float *__restrict_
         __syncthreads();
         const int t = S.k;
         if (t < 0) break;
+#ifdef NF_STATS
+        unsigned long long tg0 = gtimer(), tg1 = 0; int nit = 0;
+#endif
         const int ty = t / tiles_x, tx = t - ty * tiles_x;
         const int r0 = ty * NF_T, c0 = tx * NF_T;
         if (S.dmax) {
             // ---- tile + apron: 66 rows x 18 chunks of 16 bytes, straight from L2 / HBM into shared memory
             const int *src0 = Dg + (size_t)r0 * P + c0;        // row r0 - 1, column c0 - 4 of the padded raster
-            for (int q = tid; q < (NF_T + 2) * 18; q += 256) {
+            for (int q = tid; q < (NF_T + 2) * 18; q += IR_NT) {
                 int lr = q / 18, ch = q - lr * 18;
                 const int *src = src0 + (size_t)lr * P + ch * 4;
                 unsigned dst = sd_base + (unsigned)((lr * IR_LD + ch * 4) * 4);
@@ -1299,7 +1331,7 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve_ir(const float *__restrict_
             const bool uni = S.e == S.elo;
             if (!uni) {
                 // several binades in the tile: the per-cell binade byte comes from F
-                for (int q = tid; q < NF_T * NF_T; q += 256) {
+                for (int q = tid; q < NF_T * NF_T; q += IR_NT) {
                     int r = r0 + (q >> 6), c = c0 + (q & 63);
                     se[q] = (r < rows && c < cols) ? (unsigned char)(nf_binade((double)__ldg(F + (size_t)r * cols + c)) & 0xff) : 0;
                 }
@@ -1320,6 +1352,17 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve_ir(const float *__restrict_
                 S.wtab[tid] = wt;
             }
             if (tid == 0) S.dirty[0] = nf_region(S.flags);
+            if (tid < 8) {
+                // what the tile was queued for: everything, or the first line behind each side whose apron changed
+                const int f = S.flags, d = tid >> 1, w = tid & 1;
+                unsigned v = 0;
+                if (f & 16) v = 0xffffffffu;
+                else if (d == 0 && (f & 1) && w == 0) v = 1u;             // top apron -> row 0, downwards
+                else if (d == 1 && (f & 2) && w == 1) v = 0x80000000u;    // bottom apron -> row 63, upwards
+                else if (d == 2 && (f & 4) && w == 0) v = 1u;             // left apron -> column 0, rightwards
+                else if (d == 3 && (f & 8) && w == 1) v = 0x80000000u;    // right apron -> column 63, leftwards
+                s_ld[tid] = v;
+            }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
             if (!S.bad) {
@@ -1331,14 +1374,15 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve_ir(const float *__restrict_
                     for (int idx = 0; mm; idx++) {
                         int b = __ffsll((long long)mm) - 1;
                         mm &= mm - 1;
-                        if ((idx & 7) != warp) continue;
+                        if ((idx % (IR_NT / 32)) != warp) continue;
                         int lr = (b >> 3) * 8 + (lane >> 2), lc = (b & 7) * 8 + (lane & 3) * 2;
                         const int2 v = *reinterpret_cast<const int2 *>(sd + (lr + 1) * IR_LD + (lc + 4));
                         *reinterpret_cast<int2 *>(Dg + (size_t)(r0 + lr + 1) * P + (c0 + lc + 4)) = v;
                     }
                     // neighbours that can gain from the new ring (see k_nf_solve)
-                    int side = tid >> 6, k = tid & 63;          // 0 top, 1 bottom, 2 left, 3 right
-                    if (S.ring & (1 << side)) {
+                    for (int sidx = tid; sidx < 4 * NF_T; sidx += IR_NT) {
+                        const int side = sidx >> 6, k = sidx & 63;      // 0 top, 1 bottom, 2 left, 3 right (warp-uniform)
+                        if (!(S.ring & (1 << side))) continue;
                         int lr = side == 0 ? 0 : (side == 1 ? NF_T - 1 : k);
                         int lc = side == 2 ? 0 : (side == 3 ? NF_T - 1 : k);
                         int d = sd[(lr + 1) * IR_LD + (lc + 4)];
@@ -1376,10 +1420,31 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve_ir(const float *__restrict_
                     if (tid == 0) { S.nb = 0; S.ring = 0; S.chgmask = 0; }
                     __syncthreads();
                 };
-                nf_tile_iterate(rx, S, flush);
+#ifdef NF_STATS
+                tg1 = gtimer();
+#endif
+#if IR_SWEEP
+                int its = ir_tile_sweeps(sd, rx, S, s_ld);
+                if (S.chgmask) flush();
+#else
+                int its = nf_tile_iterate(rx, S, flush);
+#endif
+#ifdef NF_STATS
+                nit = its;
+#endif
+                (void)its;
             }
             if (S.bad && tid == 0) atomicExch(irbad, 1);
         }
+#ifdef NF_STATS
+        if (tid == 0) {
+            unsigned k = atomicAdd(&g_nf_nlog, 1u);
+            if (k < 262144u) {
+                g_nf_log[4 * k] = tg0; g_nf_log[4 * k + 1] = tg1; g_nf_log[4 * k + 2] = gtimer();
+                g_nf_log[4 * k + 3] = (unsigned long long)t | ((unsigned long long)nit << 32) | ((unsigned long long)blockIdx.x << 48);
+            }
+        }
+#endif
         __syncthreads();
         if (tid == 0) {
             // side bits that arrived while the tile ran mean it has to run again
@@ -1465,7 +1530,7 @@ static int nf_launch_solve_ir(const float *F, int *Dg, int P, int *ring, int cap
         int dev = 0, sms = 0, per_sm = 0;
         MS_CUDA(cudaGetDevice(&dev));
         MS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        MS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nf_solve_ir, 256, IR_SMEM));
+        MS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nf_solve_ir, IR_NT, IR_SMEM));
         if (per_sm < 1) { set_error("fill_terrain_no_flats: solver kernel does not fit on an SM"); return MS_ERR_CUDA; }
         grid_blocks = sms * per_sm;
     }
@@ -1475,7 +1540,7 @@ static int nf_launch_solve_ir(const float *F, int *Dg, int P, int *ring, int cap
     int g = grid_blocks < ntiles ? grid_blocks : ntiles;
     prof_units(units);
     if (g_prof) prof_begin("k_nf_solve_ir", s);
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_nf_solve_ir, dim3(g), dim3(256), args, IR_SMEM, s);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_nf_solve_ir, dim3(g), dim3(IR_NT), args, IR_SMEM, s);
     if (g_prof) prof_end(s);
     g_launches++;
     if (e != cudaSuccess) {
