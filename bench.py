@@ -34,7 +34,7 @@ BYTES_PER_CELL = 79.0     # compulsory traffic of the eight st
 STAGE_BYTES = {
     "k_descent_tile": 12, "k_forest_jump_list": 12, "k_ws_tile<L>": 9, "k_forest_jump": 12, "k_rootflag": 12, "k_catchment_ids": 12, "k_minedge<false>": 12, "k_minedge<true>": 12,
     "k_fill_final": 12, "k_scan_reduce<SELF>": 8, "k_scan_final<SELF>": 8,
-    "k_nf_init": 12, "k_nf_seedcand": 12, "k_nf_solve<true>": 12, "k_nf_solve<false>": 12, "k_nf_solve_ir": 12, "k_nf_from_int": 12, "k_nf_init_tile": 12, "k_nf_verify": 12,
+    "k_nf_init": 12, "k_nf_seedcand": 12, "k_nf_solve<true>": 12, "k_nf_solve<false>": 12, "k_nf_solve_ir": 12, "k_nf_finish_ir": 12, "k_nf_init_tile": 12, "k_nf_verify": 12,
     "k_flowdir": 9, "k_acc_tile_a": 9, "k_acc_tile_c": 9, "k_acc_links": 9, "k_acc_node_trace": 9,
     "k_cc_tile<T>": 8, "k_cc_border": 8, "k_cc_flatten": 8, "k_cc_number": 8,
     "k_label_stats<T>": 8, "k_ws_ptr<L>": 9, "k_ws_assign<L>": 9, "k_label_count": 9,
@@ -295,6 +295,16 @@ def run_ours(args):
         units = dunits if dunits else dn * n
         bpc = STAGE_BYTES.get(dname, 8)
         achieved = bpc * units / (dms * 1e-3) / 1e9
+        traffic = None
+        try:        # per-launch DRAM bytes of this kernel at this size from the committed ncu capture, if there is one
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "top_kernel_traffic.json")) as f:
+                ent = json.load(f).get(dname, {}).get(str(S))
+            if ent and world == 1:
+                traffic = {"dram_bytes_per_launch": ent["dram_bytes_per_launch"],
+                           "vs_algorithmic": round(ent["dram_bytes_per_launch"] / (bpc * units / max(dn, 1)), 3),
+                           "source": ent["source"]}
+        except (OSError, ValueError):
+            pass
         kernels = {k: {"launches": v[0], "ms_per_step": round(v[1] / args.steps, 3),
                        "share": round(v[1] / tot_ms, 4)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -314,7 +324,7 @@ def run_ours(args):
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": dname, "achieved": round(achieved, 2), "peak": peak,
                              "peak_kind": peak_kind, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                             "traffic": None, "bytes_per_unit": bpc, "units_per_launch": units // max(dn, 1),
+                             "traffic": traffic, "bytes_per_unit": bpc, "units_per_launch": units // max(dn, 1),
                              "launch_ms": round(dms / max(dn, 1), 4), "share_of_kernel_time": round(dms / tot_ms, 4),
                              "pipeline_frac": round(value * 1e6 * BYTES_PER_CELL / (world * peak * 1e9), 5)},
                 "kernels": kernels, "clocks": clocks}

@@ -937,7 +937,7 @@ __global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ 
             sides |= (lr == 0 ? 1 : 0) | (lr == NF_T - 1 || r == rows - 2 ? 2 : 0) | (lc == 0 ? 4 : 0) |
                      (lc == NF_T - 1 || c == cols - 2 ? 8 : 0);
         }
-        W[(size_t)r * cols + c] = w;
+        if (!Dg) W[(size_t)r * cols + c] = w;      // the integer-raster solve writes W once, at the end (k_nf_finish_ir)
         if (Dg) {
             int bad = 0, elo = 0, ehi = 0, dmax = 0;
             unsigned char e8;
@@ -1020,7 +1020,7 @@ __global__ void __launch_bounds__(256) k_nf_verify(const float *__restrict__ z, 
 // (pitch P = 64 * tiles_x + 8, one wall row above and below, 4 wall columns left, >= 4 right, so every tile + apron
 // is an in-bounds, 16-byte aligned 66 x 72 block), a visit copies that block to shared memory with cp.async (no
 // registers, no conversion, one DRAM round trip), relaxes it, and stores the changed 8x8 blocks back as integers.
-// W = F + D * ulp(F) is written once at the end (k_nf_from_int).  The FIFO / flag protocol is the one of
+// W = F + D * ulp(F) is written once at the end, and verified in the same pass (k_nf_finish_ir).  The FIFO / flag protocol is the one of
 // k_nf_solve.  Anything that does not fit the integer form (k_nf_init_tile's *irbad, a distance beyond D_LIMIT,
 // weights that are not whole ulps) raises *irbad and the caller falls back to the W-based solver.
 // =====================================================================================================
@@ -1455,20 +1455,56 @@ __global__ void __launch_bounds__(IR_NT, 1024 / IR_NT) k_nf_solve_ir(const float
     }
 }
 
-// W = F + D * ulp(F) for the lake / flat cells the integer solve reached (exact: one binade, D * ulp is a multiple
-// of ulp below 2^29 ulps).  Everything else keeps what k_nf_init_tile wrote (z, or +inf for an unreached cell,
-// which then fails the verification).
-__global__ void __launch_bounds__(256) k_nf_from_int(const float *__restrict__ F, const int *__restrict__ Dg, int P,
-                                                     double *__restrict__ W, int rows, int cols) {
-    int c = (blockIdx.x * 64 + (threadIdx.x & 63));
-    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (r >= rows || c >= cols) return;
-    int d = __ldg(Dg + (size_t)(r + 1) * P + (c + 4));
-    if (d >= D_INF) return;
-    size_t i = (size_t)r * cols + c;
-    double fd = (double)__ldg(F + i);
-    double ulp = __longlong_as_double((long long)(nf_binade(fd) - 52 + 1023) << 52);
-    W[i] = __dadd_rn(fd, __dmul_rn((double)d, ulp));
+// End of the integer-raster solve: W is written once, and verified on the way.  A CTA rebuilds the float64 surface
+// of a 64x64 tile + apron in shared memory — lake / flat cell: W = F + D * ulp(F) (exact: one binade, D * ulp is a
+// multiple of ulp below 2^29 ulps; +inf if the solve never reached the cell), anything else: W = z — stores the
+// tile and checks W == max(z, min(min4diag W + diag, min4edge W + short)) at every interior cell (SURVEY.md A.2:
+// passing it certifies the surface, however it was computed).  Violations are counted in ctl->nviol.
+__global__ void __launch_bounds__(256) k_nf_finish_ir(const float *__restrict__ z, const float *__restrict__ F,
+                                                      const int *__restrict__ Dg, int P, double *__restrict__ W,
+                                                      NfCtl *ctl, int rows, int cols, int tiles_x, double sh, double dg) {
+    constexpr int LD = NF_T + 2;
+    __shared__ double sW[LD * LD];
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int r0 = ty * NF_T, c0 = tx * NF_T;
+    for (int k = tid; k < LD * LD; k += 256) {
+        int lr = k / LD, lc = k - lr * LD;
+        int r = r0 + lr - 1, c = c0 + lc - 1;
+        double w = INFINITY;
+        if (r >= 0 && r < rows && c >= 0 && c < cols) {
+            size_t i = (size_t)r * cols + c;
+            int d = __ldg(Dg + (size_t)(r + 1) * P + (c + 4));
+            if (d > D_INF) w = (double)__ldg(z + i);
+            else if (d < D_INF) {
+                double fd = (double)__ldg(F + i);
+                double ulp = __longlong_as_double((long long)(nf_binade(fd) - 52 + 1023) << 52);
+                w = __dadd_rn(fd, __dmul_rn((double)d, ulp));
+            }
+        }
+        sW[k] = w;
+    }
+    __syncthreads();
+    int bad = 0;
+    for (int k = tid; k < NF_T * NF_T; k += 256) {
+        int lr = k >> 6, lc = k & 63;
+        int r = r0 + lr, c = c0 + lc;
+        if (r >= rows || c >= cols) continue;
+        const double *p = sW + (lr + 1) * LD + (lc + 1);
+        size_t i = (size_t)r * cols + c;
+        double w = *p;
+        W[i] = w;
+        if (r > 0 && c > 0 && r < rows - 1 && c < cols - 1) {
+            double d4 = dmin2(p[-LD - 1], dmin2(p[-LD + 1], dmin2(p[LD - 1], p[LD + 1])));
+            double e4 = dmin2(p[-LD], dmin2(p[-1], dmin2(p[1], p[LD])));
+            double m = dmin2(__dadd_rn(d4, dg), __dadd_rn(e4, sh));
+            double zc = (double)__ldg(z + i);
+            double g = m >= zc ? m : zc;
+            if (g != w) bad = 1;
+        }
+    }
+    int cnt = __syncthreads_count(bad);
+    if (tid == 0 && cnt) atomicAdd(&ctl->nviol, cnt);
 }
 
 }  // namespace ms
@@ -1621,7 +1657,8 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
             MS_TRY(nf_launch_solve_ir(filled, Dg.p, P, ring.p, cap_ring, tileflag.p, tilesides.p, tmeta.p, ctl.p, irbad.p,
                                       (int)rows, (int)cols, tiles_x, tiles_y, ntiles, sh, dg, n, s));
             prof_units(n);
-            MS_LAUNCH(k_nf_from_int, g2, 256, 0, s, filled, Dg.p, P, out, (int)rows, (int)cols);
+            MS_LAUNCH(k_nf_finish_ir, ntiles, 256, 0, s, dtm, filled, Dg.p, P, out, ctl.p, (int)rows, (int)cols, tiles_x, sh,
+                      dg);
         } else if (cap) {
             MS_TRY(nf_launch_solve<true>(filled, out, ring.p, cap_ring, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols, tiles_x,
                                          tiles_y, ntiles, sh, dg, g_nf_use_int, cap_bound, 0, n, s));
@@ -1629,7 +1666,7 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
             MS_TRY(nf_launch_solve<false>(dtm, out, ring.p, cap_ring, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols, tiles_x,
                                           tiles_y, ntiles, sh, dg, 0, -1.0, 0, n, s));
         }
-        MS_LAUNCH(k_nf_verify, g2, 256, 0, s, dtm, out, banned.p, ctl.p, (int)rows, (int)cols, sh, dg, 0);
+        if (!ir) MS_LAUNCH(k_nf_verify, g2, 256, 0, s, dtm, out, banned.p, ctl.p, (int)rows, (int)cols, sh, dg, 0);
         MS_CUDA(cudaMemcpyAsync(h, ctl.p, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
         int *h_irbad = (int *)(h + 1);
         *h_irbad = 0;

@@ -10,6 +10,9 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 L = _lib.lib(); L.ms_init(0)
 dev = torch.device("cuda", 0)
 dem = synth_fractal(S, S, seed=1)
+if os.environ.get("MS_DEM") == "patho":          # BASELINE config 5 input (tools/c5_check.py)
+    from c5_check import pathological_dem_device
+    dem = pathological_dem_device(S)
 n = S * S
 filled = torch.empty((S, S), dtype=torch.float32, device=dev); depths = torch.empty_like(filled)
 fnf = torch.empty((S, S), dtype=torch.float64, device=dev); fd = torch.empty((S, S), dtype=torch.uint8, device=dev)
