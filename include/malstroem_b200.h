@@ -327,6 +327,16 @@ int ms_bluespot_network_dev(const ms_rasters *io, double cell_area, int use_accu
                             const double *mm, int sum_mode, int32_t *out_parent, double *out_rainv,
                             double *out_spillv, double *out_v, double *out_pctv, void *stream);
 
+/* The pour-point network for one band of a raster split by rows (one band per GPU): out_parent[i] = downstream
+ * bluespot of label i (-1: none) for the pour points (GLOBAL row / column) inside rows [first_row, first_row +
+ * band_rows), INT32_MIN for all others — combine the bands with a max all-reduce.  wsheds is the band's finished
+ * watershed raster, ws_above / ws_below the neighbours' facing rows of theirs (NULL at the raster's edge).  Valid on
+ * the D8 surface of the no-flats fill, where a pour point leaves its bluespot with its first step (MS_ERR_ARG
+ * otherwise).  Synchronises the stream. */
+int ms_band_pp_parent_dev(const uint8_t *flowdir, const int32_t *wsheds, const int32_t *ws_above, const int32_t *ws_below,
+                          int64_t band_rows, int64_t cols, int64_t first_row, int64_t total_rows, int64_t n,
+                          const int64_t *pp_row, const int64_t *pp_col, int32_t *out_parent, void *stream);
+
 /* synthetic fractal DEM (malstroem_b200/synth.py, bit-identical), generated in place on the device */
 int ms_synth_fractal_dev(float *dem, int64_t rows, int64_t cols, int64_t row0, int64_t col0, int seed,
                          void *stream);

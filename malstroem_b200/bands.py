@@ -563,6 +563,36 @@ class BandPipeline(object):
             self.tables[key + "_row"] = rows_[k * m:(k + 1) * m]
             self.tables[key + "_col"] = cols_[k * m:(k + 1) * m]
 
+    # ---- the bluespot network and rain events on the finished tables (SURVEY.md §8(f1,f2)) -----------------------
+    def network(self, cell_area=1.0, events_mm=(), use_accum_pourpoints=False, sum_mode=None):
+        """RasterPipeline.network for a banded run: every rank ends up with the complete tables — `parent` int32
+        [nlabels+1] and rainv / spillv / v / pctv float64 [n_events, nlabels+1].  Each band answers for the pour
+        points it owns (one lookup in the watershed raster, halo rows exchanged with the neighbours), a max
+        all-reduce combines them, and the rain events are evaluated on every rank from the replicated tables."""
+        from . import network as _network
+        comm, dev, n, st = self.comm, self.device, self.nlabels + 1, self._stream()
+        key = "ppmax" if use_accum_pourpoints else "ppmin"
+        ws = self.out["wsheds"]
+        above, below = comm.exchange(ws[0].contiguous(), ws[self.rows - 1].contiguous())
+        parent = torch.empty(n, dtype=torch.int32, device=dev)
+        self._call("ms_band_pp_parent_dev", _p(self.out["flowdir"]), _p(ws), _p(above) if above is not None else None,
+                   _p(below) if below is not None else None, self.rows, self.cols, self.r0, self.R, n,
+                   _p(self.tables[key + "_row"].contiguous()), _p(self.tables[key + "_col"].contiguous()), _p(parent), st)
+        comm.all_reduce(parent, "max")
+        parent.clamp_(min=-1)                                # a label without a pour point: no downstream node
+        mm = np.ascontiguousarray(np.atleast_1d(np.asarray(events_mm, dtype=np.float64)))
+        ne = int(mm.size)
+        res = {"parent": parent}
+        area = (self.tables["ws_count"].double() * float(cell_area)).contiguous()
+        cap = (self.tables["st_sum"] * float(cell_area)).contiguous()
+        for k in ("rainv", "spillv", "v", "pctv"):
+            res[k] = torch.empty((ne, n), dtype=torch.float64, device=dev)
+        if ne:
+            self._call("ms_rain_events_dev", n, _p(parent), _p(area), _p(cap), ne, _lib.ptr(mm),
+                       _network.SUM_MODE if sum_mode is None else sum_mode, _p(res["rainv"]), _p(res["spillv"]),
+                       _p(res["v"]), _p(res["pctv"]), None, st)
+        return res
+
     # ---- host-buffer front end (bench `e2e`): H2D of the band's DEM rows, the run, D2H of every raster + table
     def host_buffers(self):
         if getattr(self, "_host", None) is None:
@@ -594,9 +624,10 @@ class BandPipeline(object):
         return self.rows * self.cols * per_cell + (self.nlabels + 1) * per_label
 
 
-def run_threaded(dem, nbands, device=0):
+def run_threaded(dem, nbands, device=0, after=None):
     """One process, one GPU, `nbands` bands as threads (the decomposition without NCCL): returns the BandPipelines
-    after the run.  `dem`: cuda float32 tensor [rows, cols]."""
+    after the run.  `dem`: cuda float32 tensor [rows, cols].  `after(pipeline)`, if given, runs in every band's
+    thread after the run (for calls that communicate, like `network`); its result is kept in `p.after_result`."""
     rows, cols = dem.shape
     grp = ThreadGroup(nbands)
     pipes, errs = [None] * nbands, []
@@ -608,6 +639,8 @@ def run_threaded(dem, nbands, device=0):
             pipes[rank] = p
             p.dem.copy_(dem[p.r0:p.r1])
             p.run()
+            if after is not None:
+                p.after_result = after(p)
         except BaseException as e:      # noqa: BLE001 - report and release the other threads
             errs.append(e)
             grp.barrier.abort()

@@ -198,6 +198,40 @@ __global__ void __launch_bounds__(256) k_net_tables(const int64_t *__restrict__ 
     cap[i] = __dmul_rn(st_sum[i], cell_area);               // bluespots.py:77  stats[1]['sum'] * cell_area
 }
 
+// ---- row bands (SURVEY.md §8(e) for the §8(f) rows) -----------------------------------------------------------------
+// On the D8 surface of the no-flats fill a bluespot's pour point (min of the surface, or max of the accumulated flow,
+// over the bluespot) flows out of its bluespot with its first step and never comes back: the surface only falls and
+// the accumulation only grows along a path.  So "the first label downstream that is neither mine nor background" is
+// the watershed label (K7, already resolved across bands) of the cell the pour point flows into — one lookup, with
+// the neighbours' edge rows of the watershed raster as halo.  Each band answers for the pour points it owns
+// (everything else INT32_MIN, so a max all-reduce combines the bands); *err is raised if a lookup returns the pour
+// point's own label, i.e. the raster is not such a surface (use the single-GPU walker then).
+__global__ void __launch_bounds__(256) k_band_pp_parent(const uint8_t *__restrict__ fd, const int32_t *__restrict__ ws,
+                                                        const int32_t *__restrict__ ws_above,
+                                                        const int32_t *__restrict__ ws_below, int rows, int cols,
+                                                        int64_t r0, int64_t R, int64_t n,
+                                                        const int64_t *__restrict__ pp_row,
+                                                        const int64_t *__restrict__ pp_col, int32_t *parent, int *err) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t r = pp_row[i], c = pp_col[i];
+    if (r < r0 || r >= r0 + rows || c < 0 || c >= cols) { parent[i] = INT32_MIN; return; }
+    int d = fd[(r - r0) * cols + c];
+    int32_t out = -1;
+    if (d <= 7) {
+        int64_t nr = r + kDR[d], nc = c + kDC[d];
+        if (nr >= 0 && nr < R && nc >= 0 && nc < cols) {
+            int32_t v;
+            if (nr < r0) v = ws_above ? ws_above[nc] : 0;
+            else if (nr >= r0 + rows) v = ws_below ? ws_below[nc] : 0;
+            else v = ws[(nr - r0) * cols + nc];
+            if (v == (int32_t)i && i != 0) *err = 1;
+            if (v != 0 && v != (int32_t)i) out = v;
+        }
+    }
+    parent[i] = out;
+}
+
 int pp_network_dev_impl(const uint8_t *fd, const void *lab, int label_bytes, int64_t rows, int64_t cols, int64_t np,
                         const int64_t *pp_row, const int64_t *pp_col, int64_t bg, int has_bg, int64_t *down,
                         uint8_t *found, int64_t *path_len, cudaStream_t s);      // flow.cu
@@ -279,6 +313,31 @@ int ms_bluespot_network_dev(const ms_rasters *io, double cell_area, int use_accu
     if (n_events > 0)
         MS_TRY(ms::rain_events_dev_impl(n, out_parent, area.p, cap.p, n_events, mm, sum_mode, out_rainv, out_spillv,
                                         out_v, out_pctv, nullptr, s));
+    return MS_OK;
+}
+
+int ms_band_pp_parent_dev(const uint8_t *flowdir, const int32_t *wsheds, const int32_t *ws_above, const int32_t *ws_below,
+                          int64_t band_rows, int64_t cols, int64_t first_row, int64_t total_rows, int64_t n,
+                          const int64_t *pp_row, const int64_t *pp_col, int32_t *out_parent, void *stream) {
+    MS_TRY(ms::ensure_init());
+    if (!flowdir || !wsheds || !pp_row || !pp_col || !out_parent || band_rows < 1 || cols < 1 || n < 0) {
+        ms::set_error("band pour-point network: bad argument");
+        return MS_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    ms::DevBuf<int> err;
+    MS_TRY(err.alloc(1, s));
+    MS_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), s));
+    if (n > 0)
+        MS_LAUNCH(ms::k_band_pp_parent, ms::cdiv(n, 256), 256, 0, s, flowdir, wsheds, ws_above, ws_below, (int)band_rows,
+                  (int)cols, first_row, total_rows, n, pp_row, pp_col, out_parent, err.p);
+    int64_t *h = ms::host_flags().h;
+    MS_CUDA(cudaMemcpyAsync(h, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    if (*(int *)h) {
+        ms::set_error("band pour-point network: a pour point flows back into its own bluespot (not a no-flats D8 surface)");
+        return MS_ERR_ARG;
+    }
     return MS_OK;
 }
 

@@ -136,3 +136,32 @@ def test_pathological_float64_form_falls_back():
     env = dict(os.environ, MS_NF_INT="0", PYTHONPATH=root)
     r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "fallback ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("shape,nbands,seed", [((512, 384), 4, 21), ((448, 300), 3, 22)])
+def test_band_network_and_rain_equal_oracle(shape, nbands, seed):
+    """SURVEY.md 8(f1,f2) across bands: downstream bluespots and rain events of the banded run == the oracle's
+    pourpoint_network / rain_events on the whole raster (both pour-point variants), on every rank."""
+    from malstroem_b200 import network
+    dem = synth.fractal_dem(shape[0], shape[1], seed=seed)
+    want = oracle_all(dem)
+    mm = [10.0, 30.0, 100.0]
+    pipes = bands.run_threaded(torch.from_numpy(dem).cuda(), nbands,
+                               after=lambda p: (p.network(0.16, mm), p.network(0.16, mm, use_accum_pourpoints=True)))
+    try:
+        area = np.zeros(want["n"] + 1)
+        area[:len(want["count"])] = want["count"]
+        area *= 0.16
+        for k, key in enumerate(("ppmin", "ppmax")):
+            cells = list(zip(want[key]["row"].tolist(), want[key]["col"].tolist()))
+            nodes = port.pourpoint_network(want["flowdir"], want["labels"], cells, 0)
+            parent = np.array([-1 if d["downstream_id"] is None else d["downstream_id"] for d in nodes])
+            for p in pipes:
+                got = p.after_result[k]
+                assert np.array_equal(got["parent"].cpu().numpy(), parent), key
+                ref = port.rain_events(parent, area, p.tables["st_sum"].cpu().numpy() * 0.16, mm, network.SUM_MODE)
+                for q in ("rainv", "spillv", "v", "pctv"):
+                    assert np.array_equal(got[q].cpu().numpy(), ref[q], equal_nan=True), (key, q)
+    finally:
+        for p in pipes:
+            p.close()
