@@ -318,6 +318,9 @@ def run_ours(args):
                                % (world, S, world * S, S) if banded else "%d independent rasters, one per GPU" % world),
                            "l2": "inputs (%.0f MB DEM, %.1f GB working set) exceed the 126 MB L2; no flush" %
                                  (n * 4 / 1e6, n * 37 / 1e9),
+                           "e2e_d2h": "filled f32, depths f32, flowdir u8, accum f64, bluespot labels i32, watersheds i32 "
+                                      "(what DemTool / BluespotTool write, dem.py:67-93, bluespots.py:169,189) + all "
+                                      "per-label tables; the float64 no-flats surface is an intermediate and stays in HBM",
                            "nlabels": pipe.nlabels, "stats": pipe.stats},
                 "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": pipe.bytes_h2d(),
                         "d2h_bytes_per_step": pipe.bytes_d2h(), "ms_per_step": round(e2e_ms / e2e_steps, 3)},

@@ -598,7 +598,8 @@ class BandPipeline(object):
         if getattr(self, "_host", None) is None:
             h = {"dem": torch.empty((self.rows, self.cols), dtype=torch.float32).pin_memory()}
             for name, t in self.out.items():
-                h[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                if name != "fnf":      # an intermediate of the reference's tools (dem.py:80-86): stays in HBM
+                    h[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
             self._host = h
         return self._host
 
@@ -609,7 +610,8 @@ class BandPipeline(object):
         self.dem.copy_(h["dem"], non_blocking=True)
         self.run()
         for name, t in self.out.items():
-            h[name].copy_(t, non_blocking=True)
+            if name in h:
+                h[name].copy_(t, non_blocking=True)
         tabs = {k: v.cpu() for k, v in self.tables.items()}
         torch.cuda.current_stream(self.device).synchronize()
         h["tables"] = tabs
@@ -619,7 +621,7 @@ class BandPipeline(object):
         return self.rows * self.cols * 4
 
     def bytes_d2h(self):
-        per_cell = sum(t.element_size() for t in self.out.values())
+        per_cell = sum(t.element_size() for k, t in self.out.items() if k != "fnf")
         per_label = sum(t.element_size() for t in self.tables.values())
         return self.rows * self.cols * per_cell + (self.nlabels + 1) * per_label
 

@@ -39,9 +39,14 @@ __device__ inline void cc_union(int *parent, int a, int b) {
 // cells on tile edges are merged through global memory afterwards (k_cc_border): 3 % of the raster instead of all.
 constexpr int CT = 64;
 
+// Shared-memory layout of the tile forest: one pad word per 16 cells.  A thread owns 16 consecutive cells, so with
+// the plain layout the lanes of a warp would sit 16 words apart (2 banks in use, 16-way conflicts on every access);
+// with the pad lane t's cells start at word 17 t and the 32 lanes hit 32 different banks.
+__device__ inline int cpad(int i) { return i + (i >> 4); }
+
 __device__ inline int cc_find_s(const int *p, int x) {
-    int q = p[x];
-    while (q != x) { x = q; q = p[x]; }
+    int q = p[cpad(x)];
+    while (q != x) { x = q; q = p[cpad(x)]; }
     return x;
 }
 
@@ -51,7 +56,7 @@ __device__ inline void cc_union_s(int *p, int a, int b) {
         b = cc_find_s(p, b);
         if (a == b) return;
         if (a > b) { int t = a; a = b; b = t; }
-        int old = atomicMin(p + b, a);
+        int old = atomicMin(p + cpad(b), a);
         if (old == b) return;
         b = old;
     }
@@ -60,57 +65,74 @@ __device__ inline void cc_union_s(int *p, int a, int b) {
 template <typename T>
 __global__ void __launch_bounds__(256) k_cc_tile(const T *__restrict__ data, int *__restrict__ parent, int rows, int cols,
                                                  int tiles_x) {
-    __shared__ int sp[CT * CT];
+    __shared__ int sp[CT * CT + CT * CT / 16];
     int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     int r0 = ty * CT, c0 = tx * CT, tid = threadIdx.x;
-    // a thread owns 16 consecutive cells of one row: runs are linked while loading
+    // Coalesced load of the tile's foreground bits: a warp reads half a row per instruction and votes it into one word
+    // of the row masks.  Then a thread owns 16 consecutive cells of one row (runs are linked while its cells are set up).
+    __shared__ unsigned rowmask[CT * 2];
+#pragma unroll 4
+    for (int u = 0; u < 16; u++) {
+        int k = tid + 256 * u;
+        int rr = r0 + (k >> 6), cc = c0 + (k & 63);
+        bool f = rr < rows && cc < cols && is_fg(data[(size_t)rr * cols + cc]);
+        unsigned b = __ballot_sync(0xffffffffu, f);
+        if ((tid & 31) == 0) rowmask[k >> 5] = b;
+    }
+    __syncthreads();
     int lr = tid >> 2, cb = (tid & 3) * 16;
     int r = r0 + lr;
-    unsigned fg = 0;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        int c = c0 + cb + k;
-        if (r < rows && c < cols && is_fg(data[(size_t)r * cols + c])) fg |= 1u << k;
-    }
+    unsigned fg = (rowmask[lr * 2 + (cb >> 5)] >> (cb & 31)) & 0xffffu;
     {
         int run = -1;
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             int idx = lr * CT + cb + k;
-            if (fg & (1u << k)) { if (run < 0) run = idx; sp[idx] = run; }
-            else { sp[idx] = -1; run = -1; }
+            if (fg & (1u << k)) { if (run < 0) run = idx; sp[cpad(idx)] = run; }
+            else { sp[cpad(idx)] = -1; run = -1; }
         }
     }
     __syncthreads();
     // join the 16-cell segments of a row, then the rows
-    if (cb > 0 && (fg & 1u) && sp[lr * CT + cb - 1] >= 0) cc_union_s(sp, lr * CT + cb, lr * CT + cb - 1);
+    if (cb > 0 && (fg & 1u) && sp[cpad(lr * CT + cb - 1)] >= 0) cc_union_s(sp, lr * CT + cb, lr * CT + cb - 1);
     __syncthreads();
     if (lr > 0) {
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             if (!(fg & (1u << k))) continue;
             int lc = cb + k, i = lr * CT + lc, up = i - CT;
-            if (sp[up] >= 0) {
+            if (sp[cpad(up)] >= 0) {
                 // N is foreground: NW and NE (if foreground) are row-linked to N already; only the first cell of a
                 // run, or a cell whose NW is background, adds information
-                if (lc == 0 || sp[i - 1] < 0 || sp[up - 1] < 0) cc_union_s(sp, i, up);
+                if (lc == 0 || sp[cpad(i - 1)] < 0 || sp[cpad(up - 1)] < 0) cc_union_s(sp, i, up);
             } else {
-                if (lc > 0 && sp[up - 1] >= 0) cc_union_s(sp, i, up - 1);
-                if (lc < CT - 1 && sp[up + 1] >= 0) cc_union_s(sp, i, up + 1);
+                if (lc > 0 && sp[cpad(up - 1)] >= 0) cc_union_s(sp, i, up - 1);
+                if (lc < CT - 1 && sp[cpad(up + 1)] >= 0) cc_union_s(sp, i, up + 1);
             }
         }
     }
     __syncthreads();
+    // every cell's tile-local root as a GLOBAL cell index: found with the forest intact, then staged in shared memory
+    // so that the raster is written with full rows of the tile per instruction
+    int vout[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        int c = c0 + cb + k;
-        if (r >= rows || c >= cols) continue;
         int v = -1;
         if (fg & (1u << k)) {
             int root = cc_find_s(sp, lr * CT + cb + k);
             v = (r0 + (root >> 6)) * cols + c0 + (root & 63);
         }
-        parent[(size_t)r * cols + c] = v;
+        vout[k] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; k++) sp[cpad(lr * CT + cb + k)] = vout[k];
+    __syncthreads();
+#pragma unroll 4
+    for (int u = 0; u < 16; u++) {
+        int k = tid + 256 * u;
+        int rr = r0 + (k >> 6), cc = c0 + (k & 63);
+        if (rr < rows && cc < cols) parent[(size_t)rr * cols + cc] = sp[cpad(k)];
     }
 }
 

@@ -1468,21 +1468,38 @@ __global__ void __launch_bounds__(256) k_nf_finish_ir(const float *__restrict__ 
     const int tile = blockIdx.x, tid = threadIdx.x;
     const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     const int r0 = ty * NF_T, c0 = tx * NF_T;
-    for (int k = tid; k < LD * LD; k += 256) {
-        int lr = k / LD, lc = k - lr * LD;
-        int r = r0 + lr - 1, c = c0 + lc - 1;
-        double w = INFINITY;
-        if (r >= 0 && r < rows && c >= 0 && c < cols) {
-            size_t i = (size_t)r * cols + c;
-            int d = __ldg(Dg + (size_t)(r + 1) * P + (c + 4));
-            if (d > D_INF) w = (double)__ldg(z + i);
-            else if (d < D_INF) {
-                double fd = (double)__ldg(F + i);
-                double ulp = __longlong_as_double((long long)(nf_binade(fd) - 52 + 1023) << 52);
-                w = __dadd_rn(fd, __dmul_rn((double)d, ulp));
+    // 66 x 66 cells, 18 per thread in three batches of six: the loads of a batch do not depend on each other's
+    // values (z and F are read whether or not the cell turns out to be a lake cell), so they are all in flight together
+#pragma unroll 1
+    for (int batch = 0; batch < 3; batch++) {
+        int dv[6];
+        float zv[6], fv[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            int k = tid + 256 * (batch * 6 + j);
+            int lr = k / LD, lc = k - lr * LD;
+            int r = r0 + lr - 1, c = c0 + lc - 1;
+            dv[j] = D_WALL; zv[j] = INFINITY; fv[j] = 0.f;
+            if (k < LD * LD && r >= 0 && r < rows && c >= 0 && c < cols) {
+                size_t i = (size_t)r * cols + c;
+                dv[j] = __ldg(Dg + (size_t)(r + 1) * P + (c + 4));
+                zv[j] = __ldg(z + i);
+                fv[j] = __ldg(F + i);
             }
         }
-        sW[k] = w;
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            int k = tid + 256 * (batch * 6 + j);
+            if (k >= LD * LD) continue;
+            double w = (double)zv[j];                   // seeds, border cells; +inf outside the raster
+            if (dv[j] == D_INF) w = INFINITY;           // a lake cell the solve never reached
+            else if (dv[j] < D_INF) {
+                double fd = (double)fv[j];
+                double ulp = __longlong_as_double((long long)(nf_binade(fd) - 52 + 1023) << 52);
+                w = __dadd_rn(fd, __dmul_rn((double)dv[j], ulp));
+            }
+            sW[k] = w;
+        }
     }
     __syncthreads();
     int bad = 0;

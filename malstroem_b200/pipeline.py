@@ -24,6 +24,11 @@ STAT_NAMES = ("boruvka_rounds", "catchments", "noflat_rounds", "noflat_tile_visi
 class RasterPipeline(object):
     """Buffers for one `rows x cols` raster on one GPU and the call that fills them."""
 
+    # rasters the host-buffer front end brings back: what the reference's tools write (dem.py:67-93: filled, flowdir,
+    # depths, accum; bluespots.py:169,189: bluespot labels, watersheds).  The no-flats surface is an intermediate there
+    # (dem.py:80-86 computes it for the flow directions and drops it), so it stays in HBM unless asked for.
+    HOST_RASTERS = ("filled", "depths", "flowdir", "accum", "labels", "wsheds")
+
     def __init__(self, rows, cols, device=0, with_accum=True, table_capacity=None):
         if not torch.cuda.is_available():
             raise RuntimeError("malstroem_b200.pipeline needs a CUDA device (there is no CPU fallback)")
@@ -105,10 +110,16 @@ class RasterPipeline(object):
         return res
 
     # ---- host-buffer run (bench `e2e`): H2D of the DEM, the run, D2H of every raster + table ---------
+    def host_rasters(self):
+        return [k for k in self.out if k in self.HOST_RASTERS or (k == "fnf" and self.host_fnf)]
+
+    host_fnf = False      # set True to also ship the float64 no-flats surface to the host
+
     def host_buffers(self):
         if self._host is None:
             h = {"dem": torch.empty((self.rows, self.cols), dtype=torch.float32).pin_memory()}
-            for name, t in self.out.items():
+            for name in self.host_rasters():
+                t = self.out[name]
                 h[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
             for name, t in self.tables.items():
                 h[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
@@ -117,7 +128,7 @@ class RasterPipeline(object):
 
     def run_host(self, dem_host=None):
         """dem_host: pinned (or pageable) float32 CPU tensor / ndarray.  Returns the dict of pinned host
-        tensors holding every output raster and the first nlabels+1 entries of every table."""
+        tensors holding the output rasters (HOST_RASTERS) and the first nlabels+1 entries of every table."""
         h = self.host_buffers()
         if dem_host is not None:
             src = torch.from_numpy(dem_host) if isinstance(dem_host, np.ndarray) else dem_host
@@ -125,7 +136,7 @@ class RasterPipeline(object):
                 h["dem"].copy_(src)
         self.dem.copy_(h["dem"], non_blocking=True)
         ho = _lib.MsHostOut()
-        for name in self.out:
+        for name in self.host_rasters():
             setattr(ho, name, h[name].data_ptr())
         self.run(host_out=ho)          # rasters leave through the copy stream while the later stages run
         m = self.nlabels + 1
@@ -141,7 +152,7 @@ class RasterPipeline(object):
 
     def bytes_d2h(self):
         n = self.rows * self.cols
-        per_cell = sum(t.element_size() for t in self.out.values())
+        per_cell = sum(self.out[k].element_size() for k in self.host_rasters())
         per_label = sum(t.element_size() for t in self.tables.values())
         return n * per_cell + (self.nlabels + 1) * per_label
 

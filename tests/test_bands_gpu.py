@@ -87,6 +87,7 @@ def test_pathological_single_and_banded():
     dem = synth.pathological_spiral_dem(768, 512)
     want = oracle_all(dem)
     p = RasterPipeline(768, 512)
+    p.host_fnf = True                 # also bring the no-flats surface back (an intermediate otherwise)
     h = p.run_host(dem)
     for name in ("filled", "depths", "fnf", "flowdir", "accum", "labels", "wsheds"):
         assert np.array_equal(h[name].numpy(), want[name]), name
@@ -128,6 +129,7 @@ def test_pathological_float64_form_falls_back():
         "from oracle import port\n"
         "dem = synth.pathological_spiral_dem(768, 512)\n"
         "p = RasterPipeline(768, 512)\n"
+        "p.host_fnf = True\n"
         "h = p.run_host(dem)\n"
         "short, diag = port.minimum_safe_short_and_diag(dem)\n"
         "assert np.array_equal(h['fnf'].numpy(), port.fill_terrain_no_flats(dem, short, diag))\n"

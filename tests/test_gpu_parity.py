@@ -235,6 +235,7 @@ def test_pipeline_matches_functions():
     from malstroem_b200.pipeline import RasterPipeline
     dem = synth.fractal_dem(600, 800, seed=9)
     p = RasterPipeline(600, 800)
+    p.host_fnf = True                 # also bring the no-flats surface back (an intermediate otherwise)
     h = p.run_host(dem)
     f, dep = fill.fill_terrain_and_depths(dem)
     assert eq(h["filled"].numpy(), f) and eq(h["depths"].numpy(), dep)

@@ -23,6 +23,21 @@ for k in range(reps):
     t0 = time.perf_counter(); p.run(); torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
     if rank == 0:
         print("run %d: %.1f ms  %.2f Gcell/s  nlabels %d  stats %s" % (k, dt * 1e3, R * C / dt / 1e9, p.nlabels, p.stats), flush=True)
+# the bluespot network and 10 / 30 / 100 mm rain events on the replicated tables (SURVEY.md 8(f1,f2))
+events = [10.0, 30.0, 100.0]
+torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+net = p.network(cell_area=0.16, events_mm=events)
+torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
+if rank == 0:
+    roots = net["parent"] < 0
+    cap = p.tables["st_sum"] * 0.16
+    msg = []
+    for e, mm_ in enumerate(events):
+        r, s_, v = net["rainv"][e], net["spillv"][e], net["v"][e]
+        lhs, rhs = float(r.sum()), float(v.sum() + s_[roots].sum())
+        viol = int(((v < 0) | (v > cap) | (s_ < 0) | ((s_ > 0) & (v < cap))).sum())
+        msg.append("%g mm: conservation error %.1e, violations %d, full bluespots %d" % (mm_, abs(lhs - rhs) / max(lhs, 1e-300), viol, int(((v >= cap) & (cap > 0)).sum())))
+    print("network + %d rain events: %.1f ms, %d nodes, %d roots; %s" % (len(events), dt * 1e3, net["parent"].numel(), int(roots.sum()), "; ".join(msg)), flush=True)
 bad = torch.tensor(bc.certify(p, CH=1024, skip_top=1 if rank > 0 else 0, skip_bottom=1 if rank + 1 < world else 0)[:3],
                    dtype=torch.float64, device="cuda")
 acc = p.out["accum"]
