@@ -136,22 +136,25 @@ __global__ void __launch_bounds__(256) k_cc_tile(const T *__restrict__ data, int
     }
 }
 
-// merges across tile edges: cells of a tile's first row look up (3 neighbours), cells of its first column look left
-__global__ void __launch_bounds__(256) k_cc_border(int *parent, int rows, int cols) {
-    int c = blockIdx.x * 64 + (threadIdx.x & 63);
-    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
+// merges across tile edges: cells of a tile's first row look up (3 neighbours), cells of its first column look left.
+// One CTA of 128 threads per tile: threads 0..63 are the tile's first row, 64..127 its first column (the raster is not
+// swept for the 3 % of cells that have something to do).
+__global__ void __launch_bounds__(128) k_cc_border(int *parent, int rows, int cols, int tiles_x) {
+    int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    int t = threadIdx.x & 63;
+    bool top = threadIdx.x < 64;
+    int r = ty * CT + (top ? 0 : t), c = tx * CT + (top ? t : 0);
     if (r >= rows || c >= cols) return;
-    bool toprow = (r % CT) == 0 && r > 0, leftcol = (c % CT) == 0 && c > 0;
-    if (!toprow && !leftcol) return;
     int i = r * cols + c;
     if (parent[i] < 0) return;
-    if (toprow) {
+    if (top) {
+        if (r == 0) return;
         int up = i - cols;
         if (c > 0 && parent[up - 1] >= 0) cc_union(parent, i, up - 1);
         if (parent[up] >= 0) cc_union(parent, i, up);
         if (c < cols - 1 && parent[up + 1] >= 0) cc_union(parent, i, up + 1);
-    }
-    if (leftcol) {
+    } else {
+        if (c == 0) return;
         if (r > 0 && parent[i - cols - 1] >= 0) cc_union(parent, i, i - cols - 1);
         if (parent[i - 1] >= 0) cc_union(parent, i, i - 1);
         if (r < rows - 1 && parent[i + cols - 1] >= 0) cc_union(parent, i, i + cols - 1);
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(256) k_cc_number(const int *__restrict__ paren
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int p = parent[i];
-    labels[i] = p < 0 ? 0 : rank[p] + 1;
+    labels[i] = p < 0 ? 0 : rank[cc_find(parent, p)] + 1;
 }
 
 template <typename T>
@@ -190,8 +193,9 @@ int cc_dev_t(const T *data, int32_t *labels, int64_t rows, int64_t cols, int64_t
     int tiles_x = (int)cdiv(cols, CT), tiles_y = (int)cdiv(rows, CT);
     prof_units(n);
     MS_LAUNCH(k_cc_tile<T>, tiles_x * tiles_y, 256, 0, s, data, parent.p, (int)rows, (int)cols, tiles_x);
-    MS_LAUNCH(k_cc_border, g2, 256, 0, s, parent.p, (int)rows, (int)cols);
-    MS_LAUNCH(k_cc_flatten, g1, 256, 0, s, parent.p, (int *)nullptr, n);
+    MS_LAUNCH(k_cc_border, tiles_x * tiles_y, 128, 0, s, parent.p, (int)rows, (int)cols, tiles_x);
+    // roots are the cells that point at themselves, flattened or not: number them in raster order, then every cell
+    // walks its (2-4 hop) chain once and takes its root's number — no separate flattening pass
     MS_TRY(exclusive_scan_selfptr(parent.p, flag.p, n, nlabels_dev, s));
     MS_LAUNCH(k_cc_number, g1, 256, 0, s, parent.p, flag.p, labels, n);
     return MS_OK;
@@ -265,7 +269,7 @@ int cc_band_local_t(ms_band *B, const T *data, int64_t cell_offset, int64_t *roo
     dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
     int tiles_x = (int)cdiv(cols, CT), tiles_y = (int)cdiv(rows, CT);
     MS_LAUNCH(k_cc_tile<T>, tiles_x * tiles_y, 256, 0, s, data, parent, (int)rows, (int)cols, tiles_x);
-    MS_LAUNCH(k_cc_border, g2, 256, 0, s, parent, (int)rows, (int)cols);
+    MS_LAUNCH(k_cc_border, tiles_x * tiles_y, 128, 0, s, parent, (int)rows, (int)cols, tiles_x);
     MS_LAUNCH(k_cc_flatten, cdiv(n, 256), 256, 0, s, parent, rank, n);
     MS_LAUNCH(k_cc_edge_roots, cdiv(cols, 256), 256, 0, s, parent, cell_offset, (int)rows, (int)cols, root_top, root_bot);
     return MS_OK;

@@ -1032,9 +1032,20 @@ constexpr int IR_SMEM = (NF_T + 2) * IR_LD * 4 + NF_T * NF_T;
 #define IR_NT 256
 #endif
 
-__global__ void __launch_bounds__(256) k_fill_i32(int *p, int v, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
+// the wall frame of the padded raster: row 0, the rows below the tiles, and 4 columns either side of every tile row
+// (k_nf_init_tile writes everything inside, including the cells of edge tiles that lie beyond the raster)
+__global__ void __launch_bounds__(256) k_ir_frame(int *Dg, int P, int inner_rows) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * (int64_t)P) {
+        int64_t row = i < P ? 0 : inner_rows + 1;
+        Dg[row * P + (i < P ? i : i - P)] = D_WALL;
+        return;
+    }
+    i -= 2 * (int64_t)P;
+    if (i >= 8 * (int64_t)inner_rows) return;
+    int64_t row = 1 + i / 8;
+    int k = (int)(i & 7);
+    Dg[row * P + (k < 4 ? k : P - 8 + k)] = D_WALL;
 }
 
 struct RelaxIR {
@@ -1659,8 +1670,8 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
         MS_CUDA(cudaMemsetAsync(ctl.p, 0, sizeof(NfCtl), s));
         const bool ir = cap && use_ir;
         if (ir) {
-            prof_units((int64_t)dg_cells);
-            MS_LAUNCH(k_fill_i32, cdiv((int64_t)dg_cells, 256), 256, 0, s, Dg.p, D_WALL, dg_cells);
+            const int inner_rows = tiles_y * NF_T;
+            MS_LAUNCH(k_ir_frame, cdiv(2 * (int64_t)P + 8 * (int64_t)inner_rows, 256), 256, 0, s, Dg.p, P, inner_rows);
             MS_CUDA(cudaMemsetAsync(irbad.p, 0, sizeof(int), s));
         }
         if (cap)
