@@ -654,6 +654,175 @@ int label_extreme_dev_impl(const double *data, const int32_t *lab, int64_t rows,
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// The per-label tables of the whole path in two passes (device-resident pipeline only; the numpy-level functions
+// keep their one-table kernels above).  BluespotTool asks for label_stats(depths, labels), label_count(wsheds),
+// label_min_index(fnf, labels) and label_max_index(accum, labels) (bluespots.py:160-205): five rasters, the labels
+// read four times.  Pass A reads every raster once — depth min / max / sum / count, the extreme keys of the no-flats
+// surface and of the accumulation per bluespot (warp-aggregated: lanes of one label grouped with match.any, one lane
+// issues the atomics; label 0 stays in registers) and the watershed histogram.  Pass B finds the smallest flat index
+// holding each extreme (raster-order tie-break, label.py:101-166) for both tables at once.
+// 28 + 20 B/cell instead of 8 + 4 + 12 + 12 + 12 + 12.
+// ------------------------------------------------------------------------------------------------
+template <bool ACC>
+__global__ void __launch_bounds__(256) k_tables_a(const float *__restrict__ depths, const int32_t *__restrict__ lab,
+                                                  const double *__restrict__ fnf, const double *__restrict__ accum,
+                                                  const int32_t *__restrict__ ws, int64_t n, int64_t nlabels,
+                                                  uint32_t *tmin, uint32_t *tmax, double *tsum,
+                                                  unsigned long long *tcnt, unsigned long long *kmin,
+                                                  unsigned long long *kmax, unsigned long long *wcnt, int *err) {
+    const unsigned full = 0xffffffffu;
+    uint32_t bmin = 0xffffffffu, bmax = 0;
+    double bsum = 0.0;
+    unsigned long long bcnt = 0, bwz = 0, bkmin = ~0ull, bkmax = 0ull;
+    int64_t span = (int64_t)gridDim.x * blockDim.x;
+    int64_t nround = (n + span - 1) / span;
+    for (int64_t it = 0; it < nround; it++) {
+        int64_t i = it * span + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        int lbl = -1, w = -1;
+        float v = 0.f;
+        double f = 0.0, a = 0.0;
+        if (i < n) {
+            lbl = lab[i];
+            w = ws[i];
+            v = depths[i];
+            f = fnf[i];
+            if (ACC) a = accum[i];
+            if (lbl < 0 || lbl > nlabels) { *err = 1; lbl = -1; }
+            if (w < 0 || w > nlabels) { *err = 1; w = -1; }
+        }
+        const bool vok = (v == v), fok = (f == f), aok = (a == a);
+        const unsigned long long fk = fok ? okey64(f) : ~0ull, ak = aok ? okey64(a) : 0ull;
+        if (lbl == 0) {
+            uint32_t k = okey32(v);
+            if (vok) { bmin = k < bmin ? k : bmin; bmax = k > bmax ? k : bmax; }
+            bsum += (double)v;
+            bcnt++;
+            bkmin = fk < bkmin ? fk : bkmin;
+            if (ACC) bkmax = ak > bkmax ? ak : bkmax;
+        }
+        if (w == 0) bwz++;
+        unsigned act = __ballot_sync(full, lbl > 0);
+        if (lbl > 0) {
+            unsigned g = __match_any_sync(act, lbl);
+            uint32_t k = okey32(vok ? v : 0.f);
+            uint32_t kmn = grp_min(g, vok ? k : 0xffffffffu);
+            uint32_t kmx = grp_max(g, vok ? k : 0u);
+            double sm = grp_sum(g, (double)v);
+            unsigned long long gfk = grp_min(g, fk);
+            unsigned long long gak = ACC ? grp_max(g, ak) : 0ull;
+            if ((int)(__ffs(g) - 1) == (int)(threadIdx.x & 31)) {
+                if (kmn < tmin[lbl]) atomicMin(tmin + lbl, kmn);
+                if (kmx > tmax[lbl]) atomicMax(tmax + lbl, kmx);
+                atomicAdd(tsum + lbl, sm);
+                atomicAdd(tcnt + lbl, (unsigned long long)__popc(g));
+                if (gfk < kmin[lbl]) atomicMin(kmin + lbl, gfk);
+                if (ACC && gak > kmax[lbl]) atomicMax(kmax + lbl, gak);
+            }
+        }
+        unsigned actw = __ballot_sync(full, w > 0);
+        if (w > 0) {
+            unsigned g = __match_any_sync(actw, w);
+            if ((int)(__ffs(g) - 1) == (int)(threadIdx.x & 31)) atomicAdd(wcnt + w, (unsigned long long)__popc(g));
+        }
+    }
+    // CTA reduction of the label-0 accumulators
+    uint32_t wmin = grp_min(full, bmin), wmax = grp_max(full, bmax);
+    unsigned long long wkmin = grp_min(full, bkmin), wkmax = grp_max(full, bkmax);
+    double wsum = bsum;
+    unsigned long long wc = bcnt, wz = bwz;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        wsum += __shfl_xor_sync(full, wsum, o);
+        wc += __shfl_xor_sync(full, wc, o);
+        wz += __shfl_xor_sync(full, wz, o);
+    }
+    __shared__ uint32_t smin[8], smax[8];
+    __shared__ double ssum[8];
+    __shared__ unsigned long long scnt[8], swz[8], skmin[8], skmax[8];
+    int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    if (lane == 0) { smin[wp] = wmin; smax[wp] = wmax; ssum[wp] = wsum; scnt[wp] = wc; swz[wp] = wz; skmin[wp] = wkmin; skmax[wp] = wkmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; k++) {
+            wmin = smin[k] < wmin ? smin[k] : wmin;
+            wmax = smax[k] > wmax ? smax[k] : wmax;
+            wsum += ssum[k];
+            wc += scnt[k];
+            wz += swz[k];
+            wkmin = skmin[k] < wkmin ? skmin[k] : wkmin;
+            wkmax = skmax[k] > wkmax ? skmax[k] : wkmax;
+        }
+        if (wc) {
+            atomicMin(tmin, wmin);
+            atomicMax(tmax, wmax);
+            atomicAdd(tsum, wsum);
+            atomicAdd(tcnt, wc);
+            atomicMin(kmin, wkmin);
+            if (ACC) atomicMax(kmax, wkmax);
+        }
+        if (wz) atomicAdd(wcnt, wz);
+    }
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(256) k_tables_b(const int32_t *__restrict__ lab, const double *__restrict__ fnf,
+                                                  const double *__restrict__ accum, int64_t n, int64_t nlabels,
+                                                  const unsigned long long *__restrict__ kmin,
+                                                  const unsigned long long *__restrict__ kmax, int *imin, int *imax) {
+    int64_t span = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += span) {
+        int lbl = lab[i];
+        if (lbl < 0 || lbl > nlabels) continue;
+        double f = fnf[i];
+        if (f == f && okey64(f) == kmin[lbl] && (int)i < imin[lbl]) atomicMin(imin + lbl, (int)i);
+        if (ACC) {
+            double a = accum[i];
+            if (a == a && okey64(a) == kmax[lbl] && (int)i < imax[lbl]) atomicMin(imax + lbl, (int)i);
+        }
+    }
+}
+
+// io: the pipeline's rasters and tables (see ms_rasters); all tables are written for labels 0..nlabels
+int pipeline_tables_dev_impl(const float *depths, const int32_t *lab, const double *fnf, const double *accum,
+                             const int32_t *ws, int64_t rows, int64_t cols, int64_t nlabels, double *st_min,
+                             double *st_max, double *st_sum, int64_t *st_count, int64_t *ws_count, double *pmin_v,
+                             int64_t *pmin_r, int64_t *pmin_c, double *pmax_v, int64_t *pmax_r, int64_t *pmax_c,
+                             int *err_dev, cudaStream_t s) {
+    int64_t n = rows * cols, m = nlabels + 1;
+    const bool acc = accum && pmax_v;
+    DevBuf<uint32_t> tmin, tmax;
+    DevBuf<unsigned long long> tcnt, kmin, kmax;
+    DevBuf<int> imin, imax;
+    MS_TRY(tmin.alloc((size_t)m, s));
+    MS_TRY(tmax.alloc((size_t)m, s));
+    MS_TRY(tcnt.alloc((size_t)m, s));
+    MS_TRY(kmin.alloc((size_t)m, s));
+    MS_TRY(kmax.alloc((size_t)m, s));
+    MS_TRY(imin.alloc((size_t)m, s));
+    MS_TRY(imax.alloc((size_t)m, s));
+    unsigned gm = cdiv(m, 256);
+    MS_LAUNCH(k_stats_init<uint32_t>, gm, 256, 0, s, tmin.p, tmax.p, st_sum, tcnt.p, m, 0xffffffffu);
+    MS_LAUNCH(k_fill_u64, gm, 256, 0, s, kmin.p, ~0ull, imin.p, INT32_MAX, m);
+    MS_LAUNCH(k_fill_u64, gm, 256, 0, s, kmax.p, 0ull, imax.p, INT32_MAX, m);
+    MS_CUDA(cudaMemsetAsync(ws_count, 0, (size_t)m * sizeof(int64_t), s));
+    int64_t want = (n + 255) / 256;
+    int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
+    prof_units(n);
+    if (acc) MS_LAUNCH(k_tables_a<true>, blocks, 256, 0, s, depths, lab, fnf, accum, ws, n, nlabels, tmin.p, tmax.p, st_sum,
+                       tcnt.p, kmin.p, kmax.p, (unsigned long long *)ws_count, err_dev);
+    else MS_LAUNCH(k_tables_a<false>, blocks, 256, 0, s, depths, lab, fnf, accum, ws, n, nlabels, tmin.p, tmax.p, st_sum,
+                   tcnt.p, kmin.p, kmax.p, (unsigned long long *)ws_count, err_dev);
+    MS_LAUNCH(k_stats_finish<float>, gm, 256, 0, s, tmin.p, tmax.p, tcnt.p, st_min, st_max, st_count, m);
+    prof_units(n);
+    if (acc) MS_LAUNCH(k_tables_b<true>, blocks, 256, 0, s, lab, fnf, accum, n, nlabels, kmin.p, kmax.p, imin.p, imax.p);
+    else MS_LAUNCH(k_tables_b<false>, blocks, 256, 0, s, lab, fnf, accum, n, nlabels, kmin.p, kmax.p, imin.p, imax.p);
+    MS_LAUNCH(k_extreme_finish, gm, 256, 0, s, fnf, imin.p, m, (int)cols, 0, pmin_v, pmin_r, pmin_c);
+    if (acc) MS_LAUNCH(k_extreme_finish, gm, 256, 0, s, accum, imax.p, m, (int)cols, 1, pmax_v, pmax_r, pmax_c);
+    return MS_OK;
+}
+
+
 // Row-band arg-min / arg-max (K8', K8''): phase 1 = the band's extreme value per label (as float64, so the bands'
 // tables combine with an ordinary min / max all-reduce); phase 2 = with the global extreme per label, the
 // smallest GLOBAL flat index among the band's cells that hold it (combined with a min all-reduce).

@@ -22,6 +22,11 @@ int label_stats_dev_impl(const void *data, int dtype, const int32_t *lab, int64_
 int label_extreme_dev_impl(const double *data, const int32_t *lab, int64_t rows, int64_t cols, int64_t nlabels,
                            int want_max, double *oval, int64_t *orow, int64_t *ocol, int *err_dev, cudaStream_t s);
 int label_count_dev_impl(const int32_t *lab, int64_t n, int64_t nbins, int64_t *cnt, int *err_dev, cudaStream_t s);
+int pipeline_tables_dev_impl(const float *depths, const int32_t *lab, const double *fnf, const double *accum,
+                             const int32_t *ws, int64_t rows, int64_t cols, int64_t nlabels, double *st_min,
+                             double *st_max, double *st_sum, int64_t *st_count, int64_t *ws_count, double *pmin_v,
+                             int64_t *pmin_r, int64_t *pmin_c, double *pmax_v, int64_t *pmax_r, int64_t *pmax_c,
+                             int *err_dev, cudaStream_t s);
 }  // namespace ms
 
 namespace {
@@ -107,13 +112,24 @@ extern "C" int ms_pipeline_host_dev(ms_rasters *io, const ms_host_out *host, voi
                   (long long)io->table_capacity);
         return MS_ERR_ARG;
     }
-    if (io->st_min)
+    // every table asked for (the usual case): two fused passes over the rasters (labels.cu: k_tables_a / k_tables_b)
+    const bool fused = io->st_min && io->st_max && io->st_sum && io->st_count && io->ws_count && io->ppmin_value &&
+                       io->ppmin_row && io->ppmin_col;
+    if (io->st_min && !fused)
         MS_TRY(label_stats_dev_impl(io->depths, MS_F32, io->labels, n, io->nlabels, io->st_min, io->st_max, io->st_sum,
                                     io->st_count, err.p, s));
     // bluespots.py:183-186
     MS_CUDA(cudaMemcpyAsync(io->wsheds, io->labels, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
     MS_TRY(watersheds_dev_impl(io->flowdir, io->wsheds, 4, rows, cols, 0, io->stats, s));
     MS_TRY(ship(host->wsheds, io->wsheds, (size_t)n * sizeof(int32_t), s));
+    if (fused) {
+        // bluespots.py:160, 186, 195-206 (both pour-point variants)
+        MS_TRY(pipeline_tables_dev_impl(io->depths, io->labels, io->fnf, io->accum, io->wsheds, rows, cols, io->nlabels,
+                                        io->st_min, io->st_max, io->st_sum, io->st_count, io->ws_count, io->ppmin_value,
+                                        io->ppmin_row, io->ppmin_col, io->accum ? io->ppmax_value : nullptr, io->ppmax_row,
+                                        io->ppmax_col, err.p, s));
+        return MS_OK;
+    }
     if (io->ws_count) MS_TRY(label_count_dev_impl(io->wsheds, n, io->nlabels + 1, io->ws_count, err.p, s));
     // bluespots.py:195-206 (both pour-point variants)
     if (io->ppmin_value)
