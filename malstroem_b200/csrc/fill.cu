@@ -177,12 +177,15 @@ constexpr unsigned FOREIGN_BIT = 0x80000000u;
 
 constexpr int ME_PER_THREAD = 4;      // cells per thread: one list append (atomic) per 1024 cells
 
+// FIRST: round 1, where every catchment is its own component (comp[l] == l) and nothing is frozen yet — the component
+// lookups (a gather per neighbour across a catchment boundary) are skipped.
+template <bool FIRST>
 __device__ inline bool minedge_cell(const float *__restrict__ z, const int *__restrict__ lab,
                                     const int *__restrict__ comp, const uint8_t *__restrict__ frozen,
                                     unsigned long long *best, int rows, int cols, int i, int r, int c) {
     int l = lab[i];
-    int cc = l ? comp[l] : 0;
-    if (cc == 0 || (frozen && frozen[cc])) return false;
+    int cc = FIRST ? l : (l ? comp[l] : 0);
+    if (cc == 0 || (!FIRST && frozen && frozen[cc])) return false;
     float zc = z[i];
     unsigned long long bk = KEY_NONE;
     // interior cell (label != 0 implies not on the border): all 8 neighbours are in the raster, or in a halo row
@@ -200,7 +203,7 @@ __device__ inline bool minedge_cell(const float *__restrict__ z, const int *__re
             }
             int lj = __ldg(lab + j);
             if (lj == l) continue;
-            if (__ldg(comp + lj) == cc) continue;
+            if (!FIRST && __ldg(comp + lj) == cc) continue;
             float w = fmaxf(zc, __ldg(z + j));
             // symmetric edge id: lower cell index and the direction to the higher one (E, SW, S, SE)
             int lo = j < i ? j : i;
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(256) k_minedge(const float *__restrict__ z, co
             if (r < rows && c < cols) i = r * cols + c;
         }
         cell[u] = i;
-        if (i >= 0 && minedge_cell(z, lab, comp, frozen, best, rows, cols, i, r, c)) keepbits |= 1u << u;
+        if (i >= 0 && minedge_cell<!LIST>(z, lab, comp, frozen, best, rows, cols, i, r, c)) keepbits |= 1u << u;
     }
     // append the survivors: block-wide exclusive scan of the per-thread counts, one atomic per CTA
     __shared__ int wsum[8];
