@@ -241,6 +241,18 @@ int ms_band_extreme_value_dev(const double *data, const int32_t *labels, int64_t
 int ms_band_extreme_index_dev(const double *data, const int32_t *labels, int64_t n, int64_t nlabels,
                               const double *value, int64_t cell_offset, int64_t *out_index, void *stream);
 
+/* All per-label tables of a band in two fused passes over its rasters.  Phase A: partial label_stats(depths, labels),
+ * label_count(wsheds) and the extreme values of fnf (min) / accum (max) per label, +-inf where the band does not see
+ * a label: combine across bands with min / max / sum all-reduces.  Phase B: with the GLOBAL extremes, the smallest
+ * global flat index holding each (INT64_MAX: not in this band): combine with a min all-reduce. */
+int ms_band_tables_a_dev(const float *depths, const int32_t *labels, const double *fnf, const double *accum,
+                         const int32_t *wsheds, int64_t n, int64_t nlabels, double *st_min, double *st_max,
+                         double *st_sum, int64_t *st_count, int64_t *ws_count, double *vmin, double *vmax,
+                         void *stream);
+int ms_band_tables_b_dev(const int32_t *labels, const double *fnf, const double *accum, int64_t n, int64_t nlabels,
+                         const double *vmin, const double *vmax, int64_t cell_offset, int64_t *idx_min,
+                         int64_t *idx_max, void *stream);
+
 /* ---- the whole path, device resident (what bench.py times) -------------------------------------- */
 typedef struct ms_rasters {
     int64_t rows, cols;

@@ -346,14 +346,21 @@ class BandPipeline(object):
         # K5/K6 bluespot labels, K8 stats
         self._labels(st)
         self._tick("labels")
-        self._stats(st)
-        self._tick("stats")
-        # K7 watersheds, K10 counts
-        self._watersheds(st)
+        if os.environ.get("MS_BAND_FUSED_TABLES", "1") == "0":
+            self._stats(st)
+            self._tick("stats")
+            # K7 watersheds, K10 counts
+            self._watersheds(st)
+            self._tick("watersheds")
+            # K8'/K8'' pour points
+            self._pour_points(st)
+            self._tick("pour_points")
+            return self
+        # K7 watersheds, then every per-label table (K8, K10, K8', K8'') in two fused passes and three all-reduces
+        self._watersheds(st, count=False)
         self._tick("watersheds")
-        # K8'/K8'' pour points
-        self._pour_points(st)
-        self._tick("pour_points")
+        self._tables(st)
+        self._tick("tables")
         return self
 
     def _noflats(self, st):
@@ -521,7 +528,39 @@ class BandPipeline(object):
         tsum.copy_(sums[:m])
         tcnt.copy_(sums[m:].round().long())
 
-    def _watersheds(self, st):
+    def _tables(self, st):
+        """label_stats(depths, labels), label_count(wsheds), label_min_index(fnf, labels), label_max_index(accum,
+        labels) (bluespots.py:160-205) for the whole raster, complete on every rank."""
+        comm, dev, n, cols, m = self.comm, self.device, self.rows * self.cols, self.cols, self.nlabels + 1
+        lohi = torch.empty(4 * m, dtype=torch.float64, device=dev)       # st_min, st_max, ppmin value, ppmax value
+        sums = torch.empty(m, dtype=torch.float64, device=dev)           # st_sum
+        cnts = torch.empty(2 * m, dtype=torch.int64, device=dev)         # st_count, ws_count
+        self._call("ms_band_tables_a_dev", _p(self.out["depths"]), _p(self.out["labels"]), _p(self.out["fnf"]),
+                   _p(self.out["accum"]), _p(self.out["wsheds"]), n, self.nlabels, _p(lohi[0:]), _p(lohi[m:]),
+                   _p(sums[0:]), _p(cnts[0:]), _p(cnts[m:]), _p(lohi[2 * m:]), _p(lohi[3 * m:]), st)
+        lohi[m:2 * m].neg_()                                 # max(x) = -min(-x): one min all-reduce for all four
+        lohi[3 * m:].neg_()
+        comm.all_reduce(lohi, "min")
+        lohi[m:2 * m].neg_()
+        lohi[3 * m:].neg_()
+        comm.all_reduce(cnts, "sum")
+        comm.all_reduce(sums, "sum")
+        idx = torch.empty(2 * m, dtype=torch.int64, device=dev)
+        self._call("ms_band_tables_b_dev", _p(self.out["labels"]), _p(self.out["fnf"]), _p(self.out["accum"]), n,
+                   self.nlabels, _p(lohi[2 * m:]), _p(lohi[3 * m:]), self.cell_offset, _p(idx[0:]), _p(idx[m:]), st)
+        comm.all_reduce(idx, "min")
+        none = idx == torch.iinfo(torch.int64).max
+        rows_ = torch.where(none, torch.full_like(idx, -1), idx // cols)
+        cols_ = torch.where(none, torch.full_like(idx, -1), idx % cols)
+        t = self.tables
+        t["st_min"], t["st_max"], t["st_sum"] = lohi[:m], lohi[m:2 * m], sums
+        t["st_count"], t["ws_count"] = cnts[:m], cnts[m:]
+        for k, key in enumerate(("ppmin", "ppmax")):
+            t[key + "_value"] = lohi[(2 + k) * m:(3 + k) * m]
+            t[key + "_row"] = rows_[k * m:(k + 1) * m]
+            t[key + "_col"] = cols_[k * m:(k + 1) * m]
+
+    def _watersheds(self, st, count=True):
         comm, dev, cols = self.comm, self.device, self.cols
         G, g = comm.size, comm.rank
         ws = self.out["wsheds"]
@@ -537,6 +576,8 @@ class BandPipeline(object):
         node, ok = exit_targets(all_to, cols, g)
         exit_label = torch.where(ok, final[node.clamp(0, arr.numel() - 1)], torch.zeros_like(final[:1])).to(torch.int32)
         self._call("ms_band_ws_finish_dev", self.h, _p(self.out["flowdir"]), _p(ws), 0, _p(exit_label.contiguous()), st)
+        if not count:
+            return
         cnt = self._table("ws_count", torch.int64)
         self._call("ms_label_count_dev", _p(ws), self.rows * cols, self.nlabels + 1, _p(cnt), st)
         comm.all_reduce(cnt, "sum")

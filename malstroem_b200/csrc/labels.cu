@@ -853,6 +853,84 @@ __global__ void __launch_bounds__(256) k_idx_global(const int *__restrict__ tidx
 
 extern "C" {
 
+/* The per-label tables of a band in two fused passes (k_tables_a / k_tables_b; see pipeline_tables_dev_impl).  Phase
+ * A: the band's partial stats, watershed histogram and extreme values (float64, +-inf where the band does not see a
+ * label) — combine across bands with min / max / sum all-reduces.  Phase B: with the GLOBAL extremes, the smallest
+ * global flat index holding each (INT64_MAX: not in this band) — combine with a min all-reduce. */
+int ms_band_tables_a_dev(const float *depths, const int32_t *labels, const double *fnf, const double *accum,
+                         const int32_t *wsheds, int64_t n, int64_t nlabels, double *st_min, double *st_max,
+                         double *st_sum, int64_t *st_count, int64_t *ws_count, double *vmin, double *vmax,
+                         void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!depths || !labels || !fnf || !accum || !wsheds || !st_min || !st_max || !st_sum || !st_count || !ws_count ||
+        !vmin || !vmax || n < 1 || nlabels < 0) {
+        set_error("band tables: bad argument");
+        return MS_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t m = nlabels + 1;
+    DevBuf<uint32_t> tmin, tmax;
+    DevBuf<unsigned long long> tcnt, kmin, kmax;
+    DevBuf<int> scratch, err;
+    MS_TRY(tmin.alloc((size_t)m, s));
+    MS_TRY(tmax.alloc((size_t)m, s));
+    MS_TRY(tcnt.alloc((size_t)m, s));
+    MS_TRY(kmin.alloc((size_t)m, s));
+    MS_TRY(kmax.alloc((size_t)m, s));
+    MS_TRY(scratch.alloc((size_t)m, s));
+    MS_TRY(err.alloc(1, s));
+    MS_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), s));
+    unsigned gm = cdiv(m, 256);
+    MS_LAUNCH(k_stats_init<uint32_t>, gm, 256, 0, s, tmin.p, tmax.p, st_sum, tcnt.p, m, 0xffffffffu);
+    MS_LAUNCH(k_fill_u64, gm, 256, 0, s, kmin.p, ~0ull, scratch.p, INT32_MAX, m);
+    MS_LAUNCH(k_fill_u64, gm, 256, 0, s, kmax.p, 0ull, scratch.p, INT32_MAX, m);
+    MS_CUDA(cudaMemsetAsync(ws_count, 0, (size_t)m * sizeof(int64_t), s));
+    int64_t want = (n + 255) / 256;
+    int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
+    prof_units(n);
+    MS_LAUNCH(k_tables_a<true>, blocks, 256, 0, s, depths, labels, fnf, accum, wsheds, n, nlabels, tmin.p, tmax.p, st_sum,
+              tcnt.p, kmin.p, kmax.p, (unsigned long long *)ws_count, err.p);
+    MS_LAUNCH(k_stats_finish<float>, gm, 256, 0, s, tmin.p, tmax.p, tcnt.p, st_min, st_max, st_count, m);
+    MS_LAUNCH(k_key_to_val, gm, 256, 0, s, kmin.p, vmin, m, 0);
+    MS_LAUNCH(k_key_to_val, gm, 256, 0, s, kmax.p, vmax, m, 1);
+    return MS_OK;
+}
+
+int ms_band_tables_b_dev(const int32_t *labels, const double *fnf, const double *accum, int64_t n, int64_t nlabels,
+                         const double *vmin, const double *vmax, int64_t cell_offset, int64_t *idx_min,
+                         int64_t *idx_max, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!labels || !fnf || !accum || !vmin || !vmax || !idx_min || !idx_max || n < 1 || nlabels < 0) {
+        set_error("band tables: bad argument");
+        return MS_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t m = nlabels + 1;
+    DevBuf<unsigned long long> kmin, kmax;
+    DevBuf<int> imin, imax;
+    MS_TRY(kmin.alloc((size_t)m, s));
+    MS_TRY(kmax.alloc((size_t)m, s));
+    MS_TRY(imin.alloc((size_t)m, s));
+    MS_TRY(imax.alloc((size_t)m, s));
+    unsigned gm = cdiv(m, 256);
+    MS_LAUNCH(k_val_to_key, gm, 256, 0, s, vmin, kmin.p, imin.p, m);
+    MS_LAUNCH(k_val_to_key, gm, 256, 0, s, vmax, kmax.p, imax.p, m);
+    int64_t want = (n + 255) / 256;
+    int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
+    prof_units(n);
+    MS_LAUNCH(k_tables_b<true>, blocks, 256, 0, s, labels, fnf, accum, n, nlabels, kmin.p, kmax.p, imin.p, imax.p);
+    MS_LAUNCH(k_idx_global, gm, 256, 0, s, imin.p, cell_offset, idx_min, m);
+    MS_LAUNCH(k_idx_global, gm, 256, 0, s, imax.p, cell_offset, idx_max, m);
+    return MS_OK;
+}
+
+}  // extern "C"
+
+
+extern "C" {
+
 int ms_band_extreme_value_dev(const double *data, const int32_t *labels, int64_t n, int64_t nlabels, int want_max,
                               double *out_value, void *stream) {
     using namespace ms;
