@@ -140,3 +140,28 @@ def test_net_error_behaviour():
     cyc = np.array([[2, 6]], np.uint8)                                  # two cells pointing at each other
     with pytest.raises(RuntimeError):
         net.next_downstream_label(cyc, np.zeros((1, 2), np.int32), (0, 0), 0)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_arbitrary_labels_and_nodir_cells_vs_oracle(seed):
+    """Function-level semantics away from the tool chain: labels that are NOT connected components (speckle, stripes:
+    paths re-enter the start cell's own label), no-direction cells in the interior, start cells anywhere, background
+    given / None, int32 / int64 labels, few (plain walk) and many (forest walk) start cells, with geometry."""
+    rng = np.random.default_rng(seed)
+    rows, cols = 120 + 17 * seed, 150 - 11 * seed
+    dem = synth.fractal_dem(rows, cols, seed=40 + seed)
+    short, diag = port.minimum_safe_short_and_diag(dem)
+    fd = port.terrain_flowdirection(port.fill_terrain_no_flats(dem, short, diag))
+    fd[rng.random(fd.shape) < 0.02] = 8                                    # interior cells without a direction
+    lab = np.where(rng.random(fd.shape) < 0.3, rng.integers(1, 6, fd.shape), 0).astype(np.int32)     # speckle
+    lab[(np.arange(rows)[:, None] // 7) % 3 == 0] = 7                      # stripes of one label
+    cells = [(int(r), int(c)) for r, c in zip(rng.integers(0, rows, 300), rng.integers(0, cols, 300))]
+    for labels in (lab, lab.astype(np.int64)):
+        for bg in (0, None, 7):
+            for sub in (cells, cells[:40]):
+                assert net.pourpoint_network(fd, labels, sub, bg) == port.pourpoint_network(fd, labels, sub, bg)
+    for cell in cells[:25]:
+        for bg in (0, None):
+            got = net.next_downstream_label(fd, lab, cell, bg, geometry=True)
+            want = port.next_downstream_label(fd, lab, cell, bg, geometry=True)
+            assert got[0] == want[0] and [tuple(map(int, c)) for c in got[1]] == want[1]
