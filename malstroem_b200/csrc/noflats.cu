@@ -1126,7 +1126,9 @@ struct RelaxIR {
 // is pipelined across tiles in the tail of the solve.  Measured at 8192^2 (round 1): 66 k -> 72 k visits, no-flats
 // stage 5.9 -> 6.3 ms — off.  IR_SWEEP 1 (the cone sweeps above) measured 6.65 ms against 5.9 ms for the dirty
 // blocks: a single warp runs a line in ~350 cycles (85 dependent instructions), so a sweep across the tile costs as
-// much as the block iteration does with all 8 warps — off as well; both are kept as measured alternatives.
+// much as the block iteration does with all 8 warps — off as well; both are kept as measured alternatives.  Also
+// measured and removed: a CTA taking the tile it has just woken directly instead of through the FIFO (always: 66 k ->
+// 90-108 k visits, 5.7-6.4 ms; only while CTAs are idle: no change) — the queue round trip is not what a hop costs.
 #ifndef IR_MIDFLUSH
 #define IR_MIDFLUSH 0
 #endif

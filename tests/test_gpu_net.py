@@ -154,7 +154,7 @@ def test_arbitrary_labels_and_nodir_cells_vs_oracle(seed):
     fd = port.terrain_flowdirection(port.fill_terrain_no_flats(dem, short, diag))
     fd[rng.random(fd.shape) < 0.02] = 8                                    # interior cells without a direction
     lab = np.where(rng.random(fd.shape) < 0.3, rng.integers(1, 6, fd.shape), 0).astype(np.int32)     # speckle
-    lab[(np.arange(rows)[:, None] // 7) % 3 == 0] = 7                      # stripes of one label
+    lab[(np.arange(rows) // 7) % 3 == 0, :] = 7                            # stripes of one label
     cells = [(int(r), int(c)) for r, c in zip(rng.integers(0, rows, 300), rng.integers(0, cols, 300))]
     for labels in (lab, lab.astype(np.int64)):
         for bg in (0, None, 7):
