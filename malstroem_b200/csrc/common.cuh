@@ -139,6 +139,38 @@ __device__ inline double okey64_inv(unsigned long long k) {
 __device__ __constant__ const int kDR[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
 __device__ __constant__ const int kDC[8] = {0, 1, 1, 1, 0, -1, -1, -1};
 
+// K3's per-cell rule (speedups/_flow.pyx:98-176): dz = z - nbr (edge) or (z - nbr) * INV_SQRT2 (diagonal), float64,
+// strict `>` against a running maximum that starts at 0, neighbours in the order above; 8 when none is lower.
+#ifdef __CUDACC__
+__device__ inline int d8_code(double z, double up, double ur, double rt, double dr, double dn, double dl, double lf,
+                              double ul, double inv_sqrt2) {
+    int code = 8;
+    double dzmax = 0.0, dz;
+    dz = __dsub_rn(z, up);                        if (dz > dzmax) { dzmax = dz; code = 0; }
+    dz = __dmul_rn(__dsub_rn(z, ur), inv_sqrt2);  if (dz > dzmax) { dzmax = dz; code = 1; }
+    dz = __dsub_rn(z, rt);                        if (dz > dzmax) { dzmax = dz; code = 2; }
+    dz = __dmul_rn(__dsub_rn(z, dr), inv_sqrt2);  if (dz > dzmax) { dzmax = dz; code = 3; }
+    dz = __dsub_rn(z, dn);                        if (dz > dzmax) { dzmax = dz; code = 4; }
+    dz = __dmul_rn(__dsub_rn(z, dl), inv_sqrt2);  if (dz > dzmax) { dzmax = dz; code = 5; }
+    dz = __dsub_rn(z, lf);                        if (dz > dzmax) { dzmax = dz; code = 6; }
+    dz = __dmul_rn(__dsub_rn(z, ul), inv_sqrt2);  if (dz > dzmax) { dzmax = dz; code = 7; }
+    return code;
+}
+// the border rule of flow.py:118-139 in the reference's assignment order (rows, then columns, then corners)
+__device__ inline int d8_border(int code, bool top, bool bot, int c, int cols) {
+    const int mc = cols - 1;
+    if (top) code = 0;
+    if (bot) code = 4;
+    if (c == 0) code = 6;
+    if (c == mc) code = 2;
+    if (top && c == 0) code = 7;
+    if (top && c == mc) code = 1;
+    if (bot && c == 0) code = 5;
+    if (bot && c == mc) code = 3;
+    return code;
+}
+#endif
+
 // ---- shared device primitives (scan.cu, forest.cu) ----------------------------------------------
 // exclusive scan of int32 flags; out may alias flags; *total_dev receives the sum (int64 on device)
 int exclusive_scan_i32(const int *flags, int *out, int64_t n, int64_t *total_dev, cudaStream_t s);

@@ -23,27 +23,10 @@ __global__ void __launch_bounds__(256) k_flowdir(const double *__restrict__ t, u
     const bool top_border = (r == 0) && !(open & 1), bot_border = (r == rows - 1) && !(open & 2);
     if (!top_border && !bot_border && c >= 1 && c <= cols - 2) {
         const double *p = t + i;
-        double z = *p, dzmax = 0.0, dz;
-        dz = __dsub_rn(z, __ldg(p - cols));                              if (dz > dzmax) { dzmax = dz; code = 0; }
-        dz = __dmul_rn(__dsub_rn(z, __ldg(p - cols + 1)), inv_sqrt2);    if (dz > dzmax) { dzmax = dz; code = 1; }
-        dz = __dsub_rn(z, __ldg(p + 1));                                 if (dz > dzmax) { dzmax = dz; code = 2; }
-        dz = __dmul_rn(__dsub_rn(z, __ldg(p + cols + 1)), inv_sqrt2);    if (dz > dzmax) { dzmax = dz; code = 3; }
-        dz = __dsub_rn(z, __ldg(p + cols));                              if (dz > dzmax) { dzmax = dz; code = 4; }
-        dz = __dmul_rn(__dsub_rn(z, __ldg(p + cols - 1)), inv_sqrt2);    if (dz > dzmax) { dzmax = dz; code = 5; }
-        dz = __dsub_rn(z, __ldg(p - 1));                                 if (dz > dzmax) { dzmax = dz; code = 6; }
-        dz = __dmul_rn(__dsub_rn(z, __ldg(p - cols - 1)), inv_sqrt2);    if (dz > dzmax) { dzmax = dz; code = 7; }
+        code = d8_code(*p, __ldg(p - cols), __ldg(p - cols + 1), __ldg(p + 1), __ldg(p + cols + 1), __ldg(p + cols),
+                       __ldg(p + cols - 1), __ldg(p - 1), __ldg(p - cols - 1), inv_sqrt2);
     }
-    if (edges) {
-        int mc = cols - 1;
-        if (top_border) code = 0;
-        if (bot_border) code = 4;
-        if (c == 0) code = 6;
-        if (c == mc) code = 2;
-        if (top_border && c == 0) code = 7;
-        if (top_border && c == mc) code = 1;
-        if (bot_border && c == 0) code = 5;
-        if (bot_border && c == mc) code = 3;
-    }
+    if (edges) code = d8_border(code, top_border, bot_border, c, cols);
     out[i] = (uint8_t)code;
 }
 

@@ -1472,10 +1472,14 @@ __global__ void __launch_bounds__(IR_NT, 1024 / IR_NT) k_nf_solve_ir(const float
 // of a 64x64 tile + apron in shared memory — lake / flat cell: W = F + D * ulp(F) (exact: one binade, D * ulp is a
 // multiple of ulp below 2^29 ulps; +inf if the solve never reached the cell), anything else: W = z — stores the
 // tile and checks W == max(z, min(min4diag W + diag, min4edge W + short)) at every interior cell (SURVEY.md A.2:
-// passing it certifies the surface, however it was computed).  Violations are counted in ctl->nviol.
+// passing it certifies the surface, however it was computed).  Violations are counted in ctl->nviol.  With the tile and
+// its apron in shared memory the D8 flow direction of every cell of the tile (K3, flow.py:142-167, edges flowing
+// outward) is one more stencil over the same data: written to `flowdir` when the caller wants it (the pipeline), which
+// saves K3's own pass over the float64 surface.  It is only valid if the verification passes.
 __global__ void __launch_bounds__(256) k_nf_finish_ir(const float *__restrict__ z, const float *__restrict__ F,
                                                       const int *__restrict__ Dg, int P, double *__restrict__ W,
-                                                      NfCtl *ctl, int rows, int cols, int tiles_x, double sh, double dg) {
+                                                      NfCtl *ctl, int rows, int cols, int tiles_x, double sh, double dg,
+                                                      uint8_t *__restrict__ flowdir, double inv_sqrt2) {
     constexpr int LD = NF_T + 2;
     __shared__ double sW[LD * LD];
     const int tile = blockIdx.x, tid = threadIdx.x;
@@ -1524,6 +1528,7 @@ __global__ void __launch_bounds__(256) k_nf_finish_ir(const float *__restrict__ 
         size_t i = (size_t)r * cols + c;
         double w = *p;
         W[i] = w;
+        int code = 8;
         if (r > 0 && c > 0 && r < rows - 1 && c < cols - 1) {
             double d4 = dmin2(p[-LD - 1], dmin2(p[-LD + 1], dmin2(p[LD - 1], p[LD + 1])));
             double e4 = dmin2(p[-LD], dmin2(p[-1], dmin2(p[1], p[LD])));
@@ -1531,7 +1536,9 @@ __global__ void __launch_bounds__(256) k_nf_finish_ir(const float *__restrict__ 
             double zc = (double)__ldg(z + i);
             double g = m >= zc ? m : zc;
             if (g != w) bad = 1;
+            if (flowdir) code = d8_code(w, p[-LD], p[-LD + 1], p[1], p[LD + 1], p[LD], p[LD - 1], p[-1], p[-LD - 1], inv_sqrt2);
         }
+        if (flowdir) flowdir[i] = (uint8_t)d8_border(code, r == 0, r == rows - 1, c, cols);
     }
     int cnt = __syncthreads_count(bad);
     if (tid == 0 && cnt) atomicAdd(&ctl->nviol, cnt);
@@ -1616,8 +1623,12 @@ static int nf_launch_solve_ir(const float *F, int *Dg, int P, int *ring, int cap
     return MS_OK;
 }
 
+// flowdir_out (optional): the D8 flow directions of the result with edges flowing outward (K3); *flowdir_done says
+// whether they were written (the integer-raster path does it in its finishing pass, the others do not).
 int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, double dg, double *out,
-                           int64_t rows, int64_t cols, int64_t *stats, cudaStream_t s) {
+                           int64_t rows, int64_t cols, int64_t *stats, cudaStream_t s, uint8_t *flowdir_out,
+                           int *flowdir_done) {
+    if (flowdir_done) *flowdir_done = 0;
     if (!dtm || !out) { set_error("fill_terrain_no_flats: null pointer"); return MS_ERR_ARG; }
     if (rows < 3 || cols < 3 || rows * cols > (1ll << 30)) {
         set_error("fill_terrain_no_flats: unsupported shape %lld x %lld", (long long)rows, (long long)cols);
@@ -1688,7 +1699,7 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
                                       (int)rows, (int)cols, tiles_x, tiles_y, ntiles, sh, dg, n, s));
             prof_units(n);
             MS_LAUNCH(k_nf_finish_ir, ntiles, 256, 0, s, dtm, filled, Dg.p, P, out, ctl.p, (int)rows, (int)cols, tiles_x, sh,
-                      dg);
+                      dg, flowdir_out, 1.0 / pow(2.0, 0.5));      // _flow.pyx:93-94: INV_SQRT2 = 1 / 2**0.5
         } else if (cap) {
             MS_TRY(nf_launch_solve<true>(filled, out, ring.p, cap_ring, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols, tiles_x,
                                          tiles_y, ntiles, sh, dg, g_nf_use_int, cap_bound, 0, n, s));
@@ -1711,7 +1722,10 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
             set_error("fill_terrain_no_flats: tile solver stopped early (done=%d, pending=%d)", h->done, h->pending);
             return MS_ERR_NOCONV;
         }
-        if (h->nviol == 0) break;
+        if (h->nviol == 0) {
+            if (ir && flowdir_out && flowdir_done) *flowdir_done = 1;
+            break;
+        }
         if (cap) {          // the heuristic cap (or a seed) was wrong somewhere: redo without it
             cap = false;
             continue;
@@ -2053,7 +2067,7 @@ int ms_fill_terrain_no_flats_dev(const float *dtm, const float *filled, double s
                                  double *out, int64_t rows, int64_t cols, int64_t *stats, void *stream) {
     MS_TRY(ms::ensure_init());
     return ms::fill_no_flats_dev_impl(dtm, filled, short_eps, diag_eps, out, rows, cols, stats,
-                                      (cudaStream_t)stream);
+                                      (cudaStream_t)stream, nullptr, nullptr);
 }
 
 int ms_fill_terrain_no_flats(const float *dtm, double short_eps, double diag_eps, double *out, int64_t rows,
@@ -2071,7 +2085,7 @@ int ms_fill_terrain_no_flats(const float *dtm, double short_eps, double diag_eps
     MS_TRY(d.alloc(n, s));
     MS_TRY(o.alloc(n, s));
     MS_CUDA(cudaMemcpyAsync(d.p, dtm, n * sizeof(float), cudaMemcpyHostToDevice, s));
-    MS_TRY(ms::fill_no_flats_dev_impl(d.p, nullptr, short_eps, diag_eps, o.p, rows, cols, nullptr, s));
+    MS_TRY(ms::fill_no_flats_dev_impl(d.p, nullptr, short_eps, diag_eps, o.p, rows, cols, nullptr, s, nullptr, nullptr));
     MS_CUDA(cudaMemcpyAsync(out, o.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
     return MS_OK;

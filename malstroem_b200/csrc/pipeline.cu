@@ -10,7 +10,7 @@
 namespace ms {
 int minmax_dev(const float *z, int64_t n, float *out2, cudaStream_t s);
 int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, double dg, double *out, int64_t rows,
-                           int64_t cols, int64_t *stats, cudaStream_t s);
+                           int64_t cols, int64_t *stats, cudaStream_t s, uint8_t *flowdir_out, int *flowdir_done);
 int flowdir_dev_impl(const double *t, uint8_t *out, int64_t rows, int64_t cols, int edges, cudaStream_t s, int open);
 int accum_dev_impl(const uint8_t *fd, double *acc, int64_t rows, int64_t cols, cudaStream_t s);
 int watersheds_dev_impl(const uint8_t *fd, void *lab, int label_bytes, int64_t rows, int64_t cols, int64_t unassigned,
@@ -86,10 +86,12 @@ extern "C" int ms_pipeline_host_dev(ms_rasters *io, const ms_host_out *host, voi
     io->diag_eps = io->short_eps * pow(2.0, 0.5);
     // dem.py:80-83
     int64_t nfstats[3] = {0, 0, 0};
-    MS_TRY(fill_no_flats_dev_impl(io->dem, io->filled, io->short_eps, io->diag_eps, io->fnf, rows, cols, nfstats, s));
+    int flowdir_done = 0;      // the integer-raster no-flats solve writes the D8 codes in its finishing pass
+    MS_TRY(fill_no_flats_dev_impl(io->dem, io->filled, io->short_eps, io->diag_eps, io->fnf, rows, cols, nfstats, s,
+                                  io->flowdir, &flowdir_done));
     io->stats[2] = nfstats[0]; io->stats[3] = nfstats[1]; io->stats[4] = nfstats[2];
     MS_TRY(ship(host->fnf, io->fnf, (size_t)n * sizeof(double), s));
-    MS_TRY(flowdir_dev_impl(io->fnf, io->flowdir, rows, cols, 1, s, 0));
+    if (!flowdir_done) MS_TRY(flowdir_dev_impl(io->fnf, io->flowdir, rows, cols, 1, s, 0));
     MS_TRY(ship(host->flowdir, io->flowdir, (size_t)n, s));
     // dem.py:87-91
     if (io->accum) {
