@@ -81,6 +81,20 @@ g["nodes_id"] = np.array([n['nodeid'] for n in nj], np.int64)
 g["events"] = np.array(EVENTS, np.float64)
 for k, v in rain_arrays(nj, EVENTS).items():
     g["nodes_" + k] = v
+# nodes.json as a graph on cells (junction ids depend on dict order, docs/cli.rst:206-208: not stable): per node its
+# type (0 pour point, 1 junction), its cell and the cell of its downstream node (-1, -1: none)
+by_id = {n['nodeid']: n for n in nj}
+g["nodes_graph"] = np.array(sorted(
+    (0 if n['nodetype'] == 'pourpoint' else 1, n['cell_row'], n['cell_col'],
+     by_id[n['dstrnodeid']]['cell_row'] if n['dstrnodeid'] is not None else -1,
+     by_id[n['dstrnodeid']]['cell_col'] if n['dstrnodeid'] is not None else -1) for n in nj), np.int64)
+# and the reference's geometric_pourpoint_network run here on the golden rasters must be that graph
+gn = net.geometric_pourpoint_network(fd, lab, [tuple(c) for c in g["pp_cells"].tolist()], 0)
+gi = {n['id']: n for n in gn}
+mine = np.array(sorted((0 if n['nodetype'] == 'pourpoint' else 1, n['pix'][0], n['pix'][1],
+                        gi[n['downstream_id']]['pix'][0] if n['downstream_id'] is not None else -1,
+                        gi[n['downstream_id']]['pix'][1] if n['downstream_id'] is not None else -1) for n in gn), np.int64)
+assert np.array_equal(mine, g["nodes_graph"]), "geometric_pourpoint_network here != nodes.json as a graph"
 np.savez_compressed(os.path.join(HERE, "net188.npz"), **g)
 
 # ------------------------------------------------------------------------------------------- small cases

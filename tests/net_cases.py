@@ -83,3 +83,23 @@ def check_rain(rain_events, z, zs, exact=True):
     assert len(keys) >= 30
     for pre in keys:
         _check_rain(rain_events, dict(zs, events=EVENTS), pre, exact)
+
+
+def check_geometric_network(net, z, dtm188):
+    """net.geometric_pourpoint_network (net.py:195-224) on the golden rasters == the reference's golden node table
+    (tests/data/nodes.json: 105 pour points + 12 junction nodes, tests/test_raster_net.py:24-30), compared as a graph
+    on cells because junction ids are not stable (docs/cli.rst:206-208)."""
+    fd, lab = dtm188["flowdir_noflats"], dtm188["labelled"]
+    nodes = net.geometric_pourpoint_network(fd, lab, [tuple(c) for c in z["pp_cells"].tolist()], 0)
+    assert len(nodes) == 117 and sum(n["nodetype"] == "junction" for n in nodes) == 12
+    by_id = {n["id"]: n for n in nodes}
+    assert len(by_id) == len(nodes)
+    graph = sorted((0 if n["nodetype"] == "pourpoint" else 1, int(n["pix"][0]), int(n["pix"][1]),
+                    int(by_id[n["downstream_id"]]["pix"][0]) if n["downstream_id"] is not None else -1,
+                    int(by_id[n["downstream_id"]]["pix"][1]) if n["downstream_id"] is not None else -1) for n in nodes)
+    assert np.array_equal(np.array(graph, np.int64), z["nodes_graph"])
+    for n in nodes:                                     # tests/test_raster_net.py:38-45
+        assert tuple(n["geometry"][0]) == tuple(n["pix"])
+        d = n["downstream_id"]
+        if d is not None and by_id[d]["nodetype"] == "junction":
+            assert tuple(n["geometry"][-1]) == tuple(by_id[d]["pix"])
