@@ -280,9 +280,11 @@ class BandPipeline(object):
         self.timing[name] = self.timing.get(name, 0.0) + (now - self._t_last) * 1e3
         self._t_last = now
 
-    def run(self):
+    def run(self, ship=None):
+        """ship(names), if given, is called after the stage that finishes the rasters `names` (run_host: D2H copies)."""
         import os
         import time
+        ship = ship or (lambda names: None)
         L, comm, dev, cols, rows, n = _lib.lib(), self.comm, self.device, self.cols, self.rows, self.rows * self.cols
         st = self._stream()
         i64 = ctypes.c_int64
@@ -322,6 +324,7 @@ class BandPipeline(object):
         self._call("ms_band_fill_finish_dev", self.h, _p(self.dem), _p(graph_x), _p(self.out["filled"]),
                    _p(self.out["depths"]), st)
         self._halo(self.ext["filled"])
+        ship(("filled", "depths"))
         self._tick("fill")
         # short / diag (fill.py:235-250)
         mm = torch.empty(2, dtype=torch.float32, device=dev)
@@ -339,18 +342,22 @@ class BandPipeline(object):
         # K3 D8
         self._call("ms_band_flowdir_dev", self.h, _p(self.out["fnf"]), _p(self.out["flowdir"]), 1, st)
         self._halo(self.ext["flowdir"])
+        ship(("flowdir",))
         self._tick("flowdir")
         # K4 accumulation
         self._accum(st)
+        ship(("accum",))
         self._tick("accum")
         # K5/K6 bluespot labels, K8 stats
         self._labels(st)
+        ship(("labels",))
         self._tick("labels")
         if os.environ.get("MS_BAND_FUSED_TABLES", "1") == "0":
             self._stats(st)
             self._tick("stats")
             # K7 watersheds, K10 counts
             self._watersheds(st)
+            ship(("wsheds",))
             self._tick("watersheds")
             # K8'/K8'' pour points
             self._pour_points(st)
@@ -358,6 +365,7 @@ class BandPipeline(object):
             return self
         # K7 watersheds, then every per-label table (K8, K10, K8', K8'') in two fused passes and three all-reduces
         self._watersheds(st, count=False)
+        ship(("wsheds",))
         self._tick("watersheds")
         self._tables(st)
         self._tick("tables")
@@ -645,16 +653,42 @@ class BandPipeline(object):
         return self._host
 
     def run_host(self, dem_host=None):
+        """Pinned host DEM rows -> H2D -> the staged run -> D2H.  Every rank brings back its own rows of the rasters,
+        each over a copy stream as soon as the stage that produces it is done (so the copies overlap the later stages,
+        as in RasterPipeline.run_host); the per-label tables are replicated on every rank, so rank 0 alone ships
+        them, into pinned buffers.  Returns the dict of pinned host tensors (`tables` only on rank 0)."""
         h = self.host_buffers()
         if dem_host is not None:
             h["dem"].copy_(torch.from_numpy(dem_host) if isinstance(dem_host, np.ndarray) else dem_host)
         self.dem.copy_(h["dem"], non_blocking=True)
-        self.run()
-        for name, t in self.out.items():
-            if name in h:
-                h[name].copy_(t, non_blocking=True)
-        tabs = {k: v.cpu() for k, v in self.tables.items()}
-        torch.cuda.current_stream(self.device).synchronize()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        side, cur = self._copy_stream, torch.cuda.current_stream(self.device)
+
+        def ship(names):
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for name in names:
+                    if name in h:
+                        h[name].copy_(self.out[name], non_blocking=True)
+
+        self.run(ship=ship)
+        tabs = {}
+        if self.comm.rank == 0:
+            m = self.nlabels + 1
+            pinned = getattr(self, "_host_tabs", None)
+            if pinned is None:
+                pinned = self._host_tabs = {}
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for k, v in self.tables.items():
+                    buf = pinned.get(k)
+                    if buf is None or buf.numel() < m or buf.dtype != v.dtype:
+                        buf = pinned[k] = torch.empty(m + m // 4 + 1, dtype=v.dtype).pin_memory()
+                    buf[:m].copy_(v[:m], non_blocking=True)
+                    tabs[k] = buf[:m]
+        side.synchronize()
+        cur.synchronize()
         h["tables"] = tabs
         return h
 
@@ -662,8 +696,9 @@ class BandPipeline(object):
         return self.rows * self.cols * 4
 
     def bytes_d2h(self):
+        """Per rank: its rows of the rasters; rank 0 also ships the (replicated) tables."""
         per_cell = sum(t.element_size() for k, t in self.out.items() if k != "fnf")
-        per_label = sum(t.element_size() for t in self.tables.values())
+        per_label = sum(t.element_size() for t in self.tables.values()) if self.comm.rank == 0 else 0
         return self.rows * self.cols * per_cell + (self.nlabels + 1) * per_label
 
 
