@@ -137,3 +137,68 @@ def test_synth_is_window_consistent_and_quantised():
     assert not np.array_equal(full, synth.fractal_dem(96, 160, seed=6))
     p = synth.pathological_dem(128, 128)
     assert p.dtype == np.float32 and (p[128 // 3] == np.float32(100000) * np.float32(0.001)).all()
+
+
+# ------------------------------------------------------------------------------------------ SURVEY 8(f) rows
+def test_net_argument_validation_before_any_device_work():
+    from malstroem_b200.algorithms import net
+    fd = np.zeros((5, 6), np.uint8)
+    lab = np.zeros((5, 6), np.int32)
+    with pytest.raises(ValueError):
+        net.pourpoint_network(fd.astype(np.int32), lab, [(1, 1)], 0)          # flowdir must be uint8
+    with pytest.raises(ValueError):
+        net.pourpoint_network(fd, lab.astype(np.float32), [(1, 1)], 0)        # labels must be integers
+    with pytest.raises(ValueError):
+        net.pourpoint_network(fd, lab[:4], [(1, 1)], 0)                       # same shape
+    with pytest.raises(IndexError):
+        net.next_downstream_label(fd, lab, (5, 0), 0)                         # labeled[cell] would raise (net.py:163)
+    # json-type pour points and plain pairs enumerate alike (net.py:21-40)
+    feats = [dict(properties=dict(bspot_id=7, cell_row=1, cell_col=2)), (3, 4)]
+    assert list(net._pourpoint_enumerator(feats)) == [(7, (1, 2)), (1, (3, 4))]
+
+
+def test_network_class_bookkeeping_matches_reference_contract():
+    from malstroem_b200 import network
+    nw = network.Network()
+    nodes = [dict(nodeid=5, dstrnodeid=2, wshed_area=10.0, bspot_vol=1.0),
+             dict(nodeid=2, dstrnodeid=None, wshed_area=20.0, bspot_vol=0.0),
+             dict(nodeid=9, dstrnodeid=77, wshed_area=5.0, bspot_vol=2.0)]
+    nw.add_nodes(nodes)                                   # network.py:43-71
+    assert nw.nodes == nodes and nw.root_nodes == [2]
+    assert nw.nodes_index[5] is nodes[0] and dict(nw.upstream_tree) == {2: [5], None: [2], 77: [9]}
+    parent, area, cap = nw._arrays()
+    assert parent.tolist() == [1, -1, -2] and area.tolist() == [10.0, 20.0, 5.0] and cap.tolist() == [1.0, 0.0, 2.0]
+    nw.add_node(dict(nodeid=5, dstrnodeid=None, wshed_area=1.0, bspot_vol=1.0))
+    with pytest.raises(ValueError):
+        nw._arrays()                                      # duplicate ids cannot be indexed
+    if _lib.lib().ms_device_count() == 0:                 # no CPU fallback for the §8(f) rows either
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            network.rain_events_arrays([-1], [1.0], [1.0], [10.0])
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            from malstroem_b200.algorithms import net
+            net.pourpoint_network(np.zeros((4, 4), np.uint8), np.zeros((4, 4), np.int32), [(1, 1)], 0)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/malstroem"), reason="reference tree not present")
+def test_enable_rebinds_net_and_network_on_the_real_reference():
+    sys.path.insert(0, "/root/reference")
+    for k in [k for k in sys.modules if k == "malstroem" or k.startswith("malstroem.")]:
+        del sys.modules[k]
+    try:
+        import malstroem.algorithms as alg          # noqa: F401
+        from malstroem.algorithms import net as rnet
+        from malstroem import network as rnetwork
+        from malstroem_b200.algorithms import net
+        orig_pp, orig_rain = rnet.pourpoint_network, rnetwork.Network.rain_event
+        speedups.enable()
+        assert rnet.pourpoint_network is net.pourpoint_network
+        assert rnet.next_downstream_label is net.next_downstream_label
+        assert rnet.geometric_pourpoint_network is net.geometric_pourpoint_network
+        assert rnetwork.Network.rain_event is not orig_rain
+        speedups.disable()
+        assert rnet.pourpoint_network is orig_pp and rnetwork.Network.rain_event is orig_rain
+    finally:
+        speedups.disable()
+        sys.path.remove("/root/reference")
+        for k in [k for k in sys.modules if k == "malstroem" or k.startswith("malstroem.")]:
+            del sys.modules[k]
