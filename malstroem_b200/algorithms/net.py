@@ -1,7 +1,7 @@
 """Mirror of malstroem/algorithms/net.py for the pour-point network: `next_downstream_label`
 (net.py:142-172) and `pourpoint_network` (net.py:175-192) run on the device for all pour points at once;
-`geometric_pourpoint_network` (net.py:195-224) takes every path from the device in one call and leaves the
-junction untangling (net.py:43-139, host-side list surgery) to the reference's own code."""
+`geometric_pourpoint_network` (net.py:195-224) takes every path from the device in one call and inserts the
+junction nodes where paths merge on the host (net.py:43-139, list surgery over the paths)."""
 import numpy as np
 
 from .. import _lib
@@ -85,25 +85,78 @@ def pourpoint_network(flowdir, labeled, pour_points, background_label=None):
                  pix=tuple(cells[k])) for k in range(len(ids))]
 
 
+def _common_flow_groups(nodes):
+    """net.py:43-66 (min_common_cells = 2): nodes whose paths share their second-to-last cell flow together for at
+    least the last two cells.  Groups in order of their first member; a path of two cells or fewer stands alone."""
+    groups, rest = [], list(nodes)
+    while rest:
+        first = rest.pop(0)
+        group = [first]
+        if len(first['geometry']) > 2:
+            key = first['geometry'][-2]
+            for other in list(rest):
+                if len(other['geometry']) > 2 and other['geometry'][-2] == key:
+                    group.append(other)
+                    rest.remove(other)
+        groups.append(group)
+    return groups
+
+
+def _insert_junction(nodes, junction_id):
+    """net.py:69-118: the cells all paths of `nodes` share at their downstream end become the path of a new junction
+    node; the nodes are cut back to end at the junction's first cell and re-pointed to it."""
+    paths = [list(n['geometry']) for n in nodes]
+    shared = []
+    while all(paths) and all(p[-1] == paths[0][-1] for p in paths):
+        shared.append(paths[0][-1])
+        for p in paths:
+            p.pop()
+    shared.reverse()                                     # back to flow order
+    junction = dict(id=junction_id, downstream_id=nodes[0]['downstream_id'], nodetype='junction',
+                    pix=tuple(shared[0]), geometry=shared)
+    for n, p in zip(nodes, paths):
+        n['downstream_id'] = junction_id
+        n['geometry'] = p + [junction['pix']]
+    return junction
+
+
+def _untangle(nodes, next_id):
+    """net.py:121-139: nodes flowing into one downstream node, with junction nodes inserted wherever their paths
+    merge before they get there.  Yields (node, next free id), junctions before the nodes that flow into them."""
+    for group in _common_flow_groups(nodes):
+        if len(group) == 1:
+            yield group[0], next_id
+            continue
+        junction = _insert_junction(group, next_id)
+        next_id += 1
+        yield junction, next_id
+        for node, next_id in _untangle(group, next_id):
+            yield node, next_id
+
+
+def untangle_network(nodes, first_free_id):
+    """The second half of net.geometric_pourpoint_network (net.py:213-224) on nodes that carry their `geometry`:
+    grouped by downstream node in first-seen order, each group untangled, ids for junctions from `first_free_id`."""
+    upstream = {}
+    for node in nodes:
+        upstream.setdefault(node['downstream_id'], []).append(node)
+    final, next_id = [], int(first_free_id)
+    for group in upstream.values():
+        for node, next_id in _untangle(group, next_id):
+            final.append(node)
+    return final
+
+
 def geometric_pourpoint_network(flowdir, labeled_bluespots, pour_points, background_label=None):
     """net.geometric_pourpoint_network (net.py:195-224).  Paths and downstream labels come from the device in one
-    call; inserting junction nodes where paths merge (net.py:43-139) is the reference's own `_untangle`, imported
-    from the installed reference package — it is host-side list work outside the hot path."""
-    from malstroem.algorithms.net import _untangle      # the reference must be importable for this one
+    call; the junction nodes where paths merge are inserted on the host (list surgery over the paths, O(total path
+    length))."""
     ids, cells = [], []
     for pid, pp in _pourpoint_enumerator(pour_points):
         ids.append(pid)
         cells.append(tuple(pp))
     down, found, paths = _downstream(flowdir, labeled_bluespots, cells, background_label, True,
                                      "geometric_pourpoint_network")
-    upstream = {}                                       # downstream label -> nodes, first-seen order (net.py:213-217)
-    for k in range(len(ids)):
-        d = int(down[k]) if found[k] else None
-        node = dict(id=ids[k], downstream_id=d, nodetype='pourpoint', pix=tuple(cells[k]), geometry=paths[k])
-        upstream.setdefault(d, []).append(node)
-    next_label = int(np.max(labeled_bluespots) + 1)     # net.py:220
-    final = []
-    for nodes in upstream.values():
-        for node, next_label in _untangle(nodes, next_label):
-            final.append(node)
-    return final
+    nodes = [dict(id=ids[k], downstream_id=(int(down[k]) if found[k] else None), nodetype='pourpoint',
+                  pix=tuple(cells[k]), geometry=paths[k]) for k in range(len(ids))]
+    return untangle_network(nodes, int(np.max(labeled_bluespots) + 1))         # net.py:220

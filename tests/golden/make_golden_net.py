@@ -95,6 +95,11 @@ mine = np.array(sorted((0 if n['nodetype'] == 'pourpoint' else 1, n['pix'][0], n
                         gi[n['downstream_id']]['pix'][0] if n['downstream_id'] is not None else -1,
                         gi[n['downstream_id']]['pix'][1] if n['downstream_id'] is not None else -1) for n in gn), np.int64)
 assert np.array_equal(mine, g["nodes_graph"]), "geometric_pourpoint_network here != nodes.json as a graph"
+# the exact output of the reference under this interpreter (insertion-ordered dicts make the junction ids deterministic)
+g["geo_nodes"] = np.array([(n['id'], -1 if n['downstream_id'] is None else n['downstream_id'],
+                            0 if n['nodetype'] == 'pourpoint' else 1, n['pix'][0], n['pix'][1], len(n['geometry']))
+                           for n in gn], np.int64)
+g["geo_paths"] = np.array([c for n in gn for c in n['geometry']], np.int64).reshape(-1, 2)
 np.savez_compressed(os.path.join(HERE, "net188.npz"), **g)
 
 # ------------------------------------------------------------------------------------------- small cases

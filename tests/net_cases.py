@@ -103,3 +103,17 @@ def check_geometric_network(net, z, dtm188):
         d = n["downstream_id"]
         if d is not None and by_id[d]["nodetype"] == "junction":
             assert tuple(n["geometry"][-1]) == tuple(by_id[d]["pix"])
+    check_untangle_exact(nodes, z)
+
+
+def check_untangle_exact(nodes, z):
+    """A geometric network (list of node dicts in output order) == the reference's own output, ids and order included
+    (fixture `geo_nodes` / `geo_paths`, generated under an insertion-ordered-dict interpreter)."""
+    want, paths = z["geo_nodes"], z["geo_paths"]
+    assert len(nodes) == len(want)
+    off = 0
+    for n, w in zip(nodes, want.tolist()):
+        assert (n["id"], -1 if n["downstream_id"] is None else n["downstream_id"],
+                0 if n["nodetype"] == "pourpoint" else 1, int(n["pix"][0]), int(n["pix"][1]), len(n["geometry"])) == tuple(w)
+        assert [list(map(int, c)) for c in n["geometry"]] == paths[off:off + w[5]].tolist()
+        off += w[5]

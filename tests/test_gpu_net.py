@@ -20,10 +20,6 @@ def test_next_downstream_label_and_pourpoint_network_golden(dtm188):
 
 
 def test_geometric_pourpoint_network_golden(dtm188):
-    import toolchain
-    if not toolchain.available():
-        pytest.skip("baseline/_ref not installed: the junction untangling is the reference's own code")
-    toolchain.import_reference()
     net_cases.check_geometric_network(net, _load("net188.npz"), dtm188)
 
 

@@ -25,3 +25,19 @@ def test_rain_plain_sum_within_tolerance():
     """sum_mode 0 (sum() before CPython 3.12) differs from the fixtures only in the last bits."""
     z, zs = _load("net188.npz"), _load("net_small.npz")
     net_cases.check_rain(lambda p, a, c, mm, _m: port.rain_events(p, a, c, mm, 0), z, zs, exact=False)
+
+
+def test_junction_untangling_on_oracle_paths(dtm188):
+    """The host half of geometric_pourpoint_network (malstroem_b200.algorithms.net.untangle_network, a restatement of
+    net.py:43-139, 213-224) on paths from the CPU oracle == the reference's own output, junction ids and order
+    included, and == the golden nodes.json as a graph."""
+    from malstroem_b200.algorithms import net
+    z = _load("net188.npz")
+    fd, lab = dtm188["flowdir_noflats"], dtm188["labelled"]
+    nodes = []
+    for k, c in enumerate(z["pp_cells"].tolist()):
+        lbl, geom = port.next_downstream_label(fd, lab, tuple(c), 0, geometry=True)
+        nodes.append(dict(id=k, downstream_id=lbl, nodetype="pourpoint", pix=tuple(c), geometry=geom))
+    out = net.untangle_network(nodes, int(lab.max()) + 1)
+    net_cases.check_untangle_exact(out, z)
+    assert len(out) == 117 and sum(n["nodetype"] == "junction" for n in out) == 12      # tests/test_raster_net.py:27-30
