@@ -73,22 +73,42 @@ class Network(object):
         cap = np.array([float(n['bspot_vol']) for n in self.nodes], dtype=np.float64)
         return parent, area, cap
 
+    def _evaluation_order(self):
+        """Node indices in the order the reference evaluates (and returns) them, network.py:100-129: per root in
+        insertion order, a stack walk upstream that visits the last-added upstream node first, evaluated in reverse."""
+        index = {n['nodeid']: k for k, n in enumerate(self.nodes)}
+        ups = {}
+        for k, n in enumerate(self.nodes):
+            ups.setdefault(n['dstrnodeid'], []).append(k)
+        order = []
+        for k, n in enumerate(self.nodes):
+            if n['dstrnodeid'] is not None:
+                continue
+            walk, stack = [], [k]
+            while stack:
+                x = stack.pop()
+                walk.append(x)
+                stack.extend(ups.get(self.nodes[x]['nodeid'], ()))
+            order.extend(reversed(walk))
+        return order, index
+
     def rain_events(self, mmrains):
         """All events in one device pass: list (per event) of lists of event dicts as `rain_event` returns them."""
         mm = [float(m) for m in mmrains]
         out = rain_events_arrays(*self._arrays(), mm)
-        keep = np.flatnonzero(out["present"])
+        order, _ = self._evaluation_order()
+        assert int(out["present"].sum()) == len(order)
         res = []
         for e in range(len(mm)):
             r, s, v, p = (out[k][e] for k in ("rainv", "spillv", "v", "pctv"))
-            res.append([dict(nodeid=self.nodes[k]['nodeid'], rainv=float(r[k]), spillv=float(s[k]), v=float(v[k]),
-                             pctv=None if np.isnan(p[k]) else float(p[k])) for k in keep])
+            # max(0, x) in the reference leaves the int 0 where nothing spills (network.py:92)
+            res.append([dict(nodeid=self.nodes[k]['nodeid'], rainv=float(r[k]), spillv=float(s[k]) if s[k] else 0,
+                             v=float(v[k]), pctv=None if np.isnan(p[k]) else float(p[k])) for k in order])
         return res
 
     def rain_event(self, mmrain):
-        """network.py:113-129.  One dict per node reachable from a root (nodeid, rainv, spillv, v, pctv).  The list is
-        in node insertion order (the reference's is in evaluation order; its callers index by nodeid, rain.py:75-79).
-        `spillv` is always a float (the reference yields the int 0 where nothing spills)."""
+        """network.py:113-129.  One dict per node reachable from a root (nodeid, rainv, spillv, v, pctv), in the
+        reference's order (its evaluation order: leaves before the nodes they drain to, root by root)."""
         events = self.rain_events([mmrain])[0]
         self._node_rain_values = {e['nodeid']: e for e in events}
         return events

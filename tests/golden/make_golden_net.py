@@ -38,13 +38,17 @@ def rain_arrays(nodes, events):
     nw.add_nodes(nodes)
     out = {k: np.full((len(events), len(nodes)), np.nan) for k in ("rainv", "spillv", "v", "pctv")}
     present = np.zeros(len(nodes), bool)
+    order = None
     for e, mm in enumerate(events):
-        for ev in nw.rain_event(mm):
+        evs = nw.rain_event(mm)
+        if order is None:      # the order in which the reference returns the nodes (its evaluation order)
+            order = np.array([index[ev['nodeid']] for ev in evs], np.int64)
+        for ev in evs:
             k = index[ev['nodeid']]
             present[k] = True
             for key in out:
                 out[key][e, k] = np.nan if ev[key] is None else ev[key]
-    return dict(parent=parent, area=area, cap=cap, present=present, **out)
+    return dict(parent=parent, area=area, cap=cap, present=present, order=order, **out)
 
 
 # ------------------------------------------------------------------------------------------------ dtm188

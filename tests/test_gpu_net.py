@@ -41,7 +41,10 @@ def test_network_class_matches_reference_values():
     nw.add_nodes(nodes)
     assert len(nw.root_nodes) == int((z["nodes_parent"] == -1).sum())
     for e, mm in enumerate(z["events"]):
-        ev = {d["nodeid"]: d for d in nw.rain_event(mm)}
+        evs = nw.rain_event(mm)
+        assert [d["nodeid"] for d in evs] == z["nodes_id"][z["nodes_order"]].tolist()      # the reference's order
+        assert all(type(d["spillv"]) is (float if d["spillv"] else int) for d in evs)      # max(0, x): the int 0
+        ev = {d["nodeid"]: d for d in evs}
         assert len(ev) == int(z["nodes_present"].sum())
         for k, nid in enumerate(z["nodes_id"]):
             d = ev[int(nid)]

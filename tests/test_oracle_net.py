@@ -41,3 +41,26 @@ def test_junction_untangling_on_oracle_paths(dtm188):
     out = net.untangle_network(nodes, int(lab.max()) + 1)
     net_cases.check_untangle_exact(out, z)
     assert len(out) == 117 and sum(n["nodetype"] == "junction" for n in out) == 12      # tests/test_raster_net.py:27-30
+
+
+def test_network_evaluation_order_matches_reference():
+    """Network.rain_event returns the nodes in the reference's evaluation order (network.py:100-129): the host-side
+    order (no device involved) against the order recorded from the reference itself for nodes.json, the synthetic
+    forests (hub, chains, unknown downstream ids) and the 40 small-case node tables."""
+    from malstroem_b200 import network
+    z, zs = _load("net188.npz"), _load("net_small.npz")
+
+    def check(g, pre, ids=None):
+        par = g[pre + "parent"]
+        ids = np.arange(len(par)) if ids is None else ids
+        nodes = [dict(nodeid=int(ids[k]), dstrnodeid=(None if par[k] == -1 else (int(ids[par[k]]) if par[k] >= 0 else 10 ** 9)),
+                      wshed_area=1.0, bspot_vol=1.0) for k in range(len(par))]
+        nw = network.Network()
+        nw.add_nodes(nodes)
+        assert nw._evaluation_order()[0] == g[pre + "order"].tolist(), pre
+
+    check(z, "nodes_", z["nodes_id"])
+    keys = ["forest%d_" % t for t in range(4)] + sorted(k[:-5] for k in zs if k.endswith("_rain_order"))
+    assert len(keys) >= 44
+    for pre in keys:
+        check(zs, pre)
