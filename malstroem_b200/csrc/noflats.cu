@@ -1106,175 +1106,22 @@ struct RelaxIR {
     }
 };
 
-// ---- in-tile relaxation by directional cone sweeps with dirty-line gating (IR_SWEEP 1; 0 = dirty 8x8 blocks) ----
-// The tile problem is a chamfer distance transform with obstacles.  A sweep computes line k from line k - 1 through
-// the three neighbours of its direction's cone (down, up: lines are rows; right, left: lines are columns),
-//      D(k, j) = min( D(k, j), D(k-1, j) + short, min(D(k-1, j-1), D(k-1, j+1)) + diag ),
-// one warp per direction, the previous line in registers (a lane owns positions `lane` and `lane + 32`, neighbours
-// by shuffle), branch-free, ~60 cycles per line.  A shortest chamfer path in open water uses two move types of one
-// octant, both of which lie in one cone, so one sweep carries a wave straight across the tile; every bend around an
-// obstacle needs another round.  Gating: per direction a 64-bit mask of lines that must be looked at (because the
-// line before them changed).  A sweep starts at its first dirty line and stops when nothing it carries forward
-// changed and no dirty line lies ahead; every change marks the lines that read the changed cell in the other
-// three directions.  The four sweeps of a round run concurrently on the shared tile (updates by atomicMin: every
-// candidate is an upper bound, stale reads only delay); rounds repeat until all masks are empty = the fixed point.
-#ifndef IR_SWEEP
-#define IR_SWEEP 0
-#endif
+// ---- alternatives to the dirty-block relaxation that were measured in round 1 and removed again -------------------
+// Directional cone sweeps with dirty-line gating (one warp per direction sweeps the tile line by line, the previous
+// line in registers, neighbours by shuffle; rounds until no line is dirty): correct, 6.65 ms against 5.9 ms for the
+// dirty blocks at 8192^2 — a single warp runs a line in ~350 cycles (85 dependent instructions), so one sweep across
+// the tile costs as much as the block iteration does with all 8 warps.  (git history: commit "K2: gated cone sweeps
+// and tail mid-flush measured ...".)
 // IR_MIDFLUSH 1: while CTAs are idle (fewer tiles queued or running than the grid has CTAs) a tile forwards its ring
 // to the neighbours after iterations 1, 2, 4, ... instead of only when it has settled, so the wave of a large lake
 // is pipelined across tiles in the tail of the solve.  Measured at 8192^2 (round 1): 66 k -> 72 k visits, no-flats
-// stage 5.9 -> 6.3 ms — off.  IR_SWEEP 1 (the cone sweeps above) measured 6.65 ms against 5.9 ms for the dirty
-// blocks: a single warp runs a line in ~350 cycles (85 dependent instructions), so a sweep across the tile costs as
-// much as the block iteration does with all 8 warps — off as well; both are kept as measured alternatives.  Also
-// measured and removed: a CTA taking the tile it has just woken directly instead of through the FIFO (always: 66 k ->
-// 90-108 k visits, 5.7-6.4 ms; only while CTAs are idle: no change) — the queue round trip is not what a hop costs.
+// stage 5.9 -> 6.3 ms — off (the switch stays: it costs nothing when off).
+// A CTA taking the tile it has just woken directly instead of through the FIFO (always: 66 k -> 90-108 k visits,
+// 5.7-6.4 ms; only while CTAs are idle: no change): the queue round trip is not what a hop costs.  128- and
+// 512-thread CTAs: 7.6 / 6.4 ms; 6 CTAs per SM (40 registers): no change.
 #ifndef IR_MIDFLUSH
 #define IR_MIDFLUSH 0
 #endif
-
-struct IrSweepState {
-    unsigned long long mA, mB;     // lines in which this lane's first / second cell changed (all rounds of a visit)
-    int vmax;                      // largest value written
-};
-
-template <int DIR, bool UNI>
-__device__ inline void ir_sweep(int *sd, const RelaxIR &rx, unsigned *ld, IrSweepState &st) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    constexpr bool ROWS = DIR < 2;
-    constexpr int STEP = (DIR & 1) ? -1 : 1;
-    constexpr int LS = ROWS ? IR_LD : 1;           // stride between lines
-    constexpr int PS = ROWS ? 1 : IR_LD;           // stride along a line
-    constexpr int OPP = DIR ^ 1, XUP = ROWS ? 2 : 0, XDN = ROWS ? 3 : 1;
-    unsigned lo = 0, hi = 0;
-    if (lane == 0) { lo = atomicExch(&ld[DIR * 2], 0u); hi = atomicExch(&ld[DIR * 2 + 1], 0u); }
-    lo = __shfl_sync(full, lo, 0);
-    hi = __shfl_sync(full, hi, 0);
-    unsigned long long m = ((unsigned long long)hi << 32) | lo;
-    if (!m) return;
-    if (STEP < 0) m = __brevll(m);                 // bit k = the k-th line in sweep order
-    const int k0 = __ffsll((long long)m) - 1;
-    const int first = STEP > 0 ? 0 : NF_T - 1;
-    int *base = sd + IR_LD + 4;                    // cell (0, 0)
-    const int up = (lane + 31) & 31, dn = (lane + 1) & 31;
-    const int2 wu = rx.wtab[0];
-    int *cur = base + (first + STEP * k0) * LS;
-    const int *prev = cur - STEP * LS;
-    int pA = prev[lane * PS], pB = prev[(lane + 32) * PS], eL = prev[-PS], eR = prev[NF_T * PS];
-    int cA = cur[lane * PS], cB = cur[(lane + 32) * PS];
-    bool carry = false;
-    unsigned long long opp = 0;
-    unsigned posA = 0, posB = 0;
-    for (int k = k0; k < NF_T; k++) {
-        if (!carry && !(m >> k)) break;            // nothing carried forward, no dirty line ahead
-        const int line = first + STEP * k;
-        int *nxt = cur + STEP * LS;
-        // what the next line needs from shared memory (the clamp keeps the last prefetch inside the apron)
-        const int nL = cur[-PS], nR = cur[NF_T * PS];
-        const int nA = nxt[lane * PS], nB = nxt[(lane + 32) * PS];
-        const int rA = __shfl_sync(full, pA, up), rB = __shfl_sync(full, pB, up);
-        const int qA = __shfl_sync(full, pA, dn), qB = __shfl_sync(full, pB, dn);
-        const int LA = lane == 0 ? eL : rA, LB = lane == 0 ? rA : rB;
-        const int RA = lane == 31 ? qB : qA, RB = lane == 31 ? eR : qB;
-        int2 wa = wu, wb = wu;
-        if (!UNI) {
-            wa = ROWS ? rx.weights(line, lane) : rx.weights(lane, line);
-            wb = ROWS ? rx.weights(line, lane + 32) : rx.weights(lane + 32, line);
-        }
-        const int mAv = min(pA + wa.x, min(LA, RA) + wa.y);
-        const int mBv = min(pB + wb.x, min(LB, RB) + wb.y);
-        const bool uA = cA <= D_INF && mAv < cA, uB = cB <= D_INF && mBv < cB;
-        if (uA) atomicMin(cur + lane * PS, mAv);
-        if (uB) atomicMin(cur + (lane + 32) * PS, mBv);
-        cA = uA ? mAv : cA;
-        cB = uB ? mBv : cB;
-        st.mA |= (unsigned long long)uA << line;
-        st.mB |= (unsigned long long)uB << line;
-        st.vmax = max(st.vmax, max(uA ? mAv : 0, uB ? mBv : 0));
-        const unsigned bA = __ballot_sync(full, uA), bB = __ballot_sync(full, uB);
-        carry = (bA | bB) != 0;
-        if (carry) {
-            // remember which lines the other sweeps must look at (kept in registers, published after the sweep:
-            // the masks are only read at the start of a sweep)
-            const int back = line - STEP;          // the opposite sweep reads this line when it computes `back`
-            if (back >= 0 && back < NF_T) opp |= 1ull << back;
-            posA |= bA;
-            posB |= bB;
-        }
-        pA = cA; pB = cB; eL = nL; eR = nR;
-        cA = nA; cB = nB;
-        cur = nxt;
-    }
-    if (lane == 0 && (opp | posA | posB)) {
-        __threadfence_block();
-        // the crossing sweeps: position j changed -> their lines j + 1 (ascending) and j - 1 (descending)
-        const unsigned ulo = posA << 1, uhi = (posB << 1) | (posA >> 31);
-        const unsigned dlo = (posA >> 1) | (posB << 31), dhi = posB >> 1;
-        if ((unsigned)opp) atomicOr(&ld[OPP * 2], (unsigned)opp);
-        if ((unsigned)(opp >> 32)) atomicOr(&ld[OPP * 2 + 1], (unsigned)(opp >> 32));
-        if (ulo) atomicOr(&ld[XUP * 2], ulo);
-        if (uhi) atomicOr(&ld[XUP * 2 + 1], uhi);
-        if (dlo) atomicOr(&ld[XDN * 2], dlo);
-        if (dhi) atomicOr(&ld[XDN * 2 + 1], dhi);
-    }
-}
-
-// All sweeps, round after round, until no line is dirty.  On return S.chgmask / S.ring say which 8x8 blocks and which
-// sides of the tile changed; S.bad is raised when a distance left the trusted range.  Called by all 256 threads
-// (warps 4-7 only keep the barriers); S.ld was set from the tile's flag word before the preceding barrier.
-__device__ inline int ir_tile_sweeps(int *sd, const RelaxIR &rx, NfTileShared &S, unsigned *ld) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    IrSweepState st{0ull, 0ull, 0};
-    int rounds = 0;
-    for (;;) {
-        if (rx.uni) {
-            if (warp == 0) ir_sweep<0, true>(sd, rx, ld, st);
-            else if (warp == 1) ir_sweep<1, true>(sd, rx, ld, st);
-            else if (warp == 2) ir_sweep<2, true>(sd, rx, ld, st);
-            else if (warp == 3) ir_sweep<3, true>(sd, rx, ld, st);
-        } else {
-            if (warp == 0) ir_sweep<0, false>(sd, rx, ld, st);
-            else if (warp == 1) ir_sweep<1, false>(sd, rx, ld, st);
-            else if (warp == 2) ir_sweep<2, false>(sd, rx, ld, st);
-            else if (warp == 3) ir_sweep<3, false>(sd, rx, ld, st);
-        }
-        rounds++;
-        __syncthreads();
-        const unsigned any = ld[0] | ld[1] | ld[2] | ld[3] | ld[4] | ld[5] | ld[6] | ld[7];
-        __syncthreads();
-        if (!any) break;
-    }
-    if (warp < 4) {
-        // lines x positions -> 8x8 blocks and ring sides
-        const bool rows = warp < 2;
-        unsigned long long chg = 0;
-        int rings = 0;
-#pragma unroll
-        for (int g = 0; g < 8; g++) {
-            const bool a = (st.mA >> (8 * g)) & 0xffull, b = (st.mB >> (8 * g)) & 0xffull;
-            // rows-type sweep: line group g = block row, position lane (+32) -> block column; columns-type: transposed
-            if (a) chg |= 1ull << (rows ? g * 8 + (lane >> 3) : (lane >> 3) * 8 + g);
-            if (b) chg |= 1ull << (rows ? g * 8 + 4 + (lane >> 3) : (4 + (lane >> 3)) * 8 + g);
-        }
-        const unsigned long long mm = st.mA | st.mB;
-        const int first_line = (int)(mm & 1ull), last_line = (int)(mm >> 63);
-        const int first_pos = (lane == 0 && st.mA) ? 1 : 0, last_pos = (lane == 31 && st.mB) ? 1 : 0;
-        if (rows) rings = first_line * 1 | last_line * 2 | first_pos * 4 | last_pos * 8;
-        else rings = first_line * 4 | last_line * 8 | first_pos * 1 | last_pos * 2;
-        unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)chg);
-        unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(chg >> 32));
-        rings = __reduce_or_sync(0xffffffffu, rings);
-        int vmax = __reduce_max_sync(0xffffffffu, st.vmax);
-        if (lane == 0) {
-            if (lo | hi) atomicOr(&S.chgmask, ((unsigned long long)hi << 32) | lo);
-            if (rings) atomicOr(&S.ring, rings);
-            if (vmax >= D_LIMIT) S.bad = 1;
-        }
-    }
-    __syncthreads();
-    return rounds;
-}
 
 __global__ void __launch_bounds__(IR_NT, 1024 / IR_NT) k_nf_solve_ir(const float *__restrict__ F, int *Dg, int P, int *ring, int cap,
                                                         int *tileflag, const int *__restrict__ tilesides,
@@ -1284,7 +1131,6 @@ __global__ void __launch_bounds__(IR_NT, 1024 / IR_NT) k_nf_solve_ir(const float
     int *sd = reinterpret_cast<int *>(smem_raw);
     unsigned char *se = smem_raw + (NF_T + 2) * IR_LD * 4;
     __shared__ NfTileShared S;
-    __shared__ unsigned s_ld[8];            // IR_SWEEP: dirty lines per direction (down, up, right, left) x 2 words
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (*(volatile unsigned *)&ctl->tail == 0 || *(volatile int *)irbad) return;      // nothing queued / not for this form
     const unsigned sd_base = (unsigned)__cvta_generic_to_shared(sd);
@@ -1365,17 +1211,6 @@ __global__ void __launch_bounds__(IR_NT, 1024 / IR_NT) k_nf_solve_ir(const float
                 S.wtab[tid] = wt;
             }
             if (tid == 0) S.dirty[0] = nf_region(S.flags);
-            if (tid < 8) {
-                // what the tile was queued for: everything, or the first line behind each side whose apron changed
-                const int f = S.flags, d = tid >> 1, w = tid & 1;
-                unsigned v = 0;
-                if (f & 16) v = 0xffffffffu;
-                else if (d == 0 && (f & 1) && w == 0) v = 1u;             // top apron -> row 0, downwards
-                else if (d == 1 && (f & 2) && w == 1) v = 0x80000000u;    // bottom apron -> row 63, upwards
-                else if (d == 2 && (f & 4) && w == 0) v = 1u;             // left apron -> column 0, rightwards
-                else if (d == 3 && (f & 8) && w == 1) v = 0x80000000u;    // right apron -> column 63, leftwards
-                s_ld[tid] = v;
-            }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
             if (!S.bad) {
@@ -1436,12 +1271,7 @@ __global__ void __launch_bounds__(IR_NT, 1024 / IR_NT) k_nf_solve_ir(const float
 #ifdef NF_STATS
                 tg1 = gtimer();
 #endif
-#if IR_SWEEP
-                int its = ir_tile_sweeps(sd, rx, S, s_ld);
-                if (S.chgmask) flush();
-#else
                 int its = nf_tile_iterate(rx, S, flush);
-#endif
 #ifdef NF_STATS
                 nit = its;
 #endif
