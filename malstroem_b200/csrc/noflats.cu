@@ -76,6 +76,15 @@ struct NfCtl {
     int reserved;
 };
 
+// wall-clock watchdog of the persistent solvers (a spin count trips under a profiler, compute-sanitizer or a
+// time-sliced GPU): a consumer that has waited this long for work gives up and stops every CTA
+constexpr unsigned long long NF_WATCHDOG_NS = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ inline unsigned long long nf_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ inline double dmin2(double a, double b) { return a <= b ? a : b; }
 __device__ inline double dmin4(double a, double b, double c, double d) { return dmin2(dmin2(a, b), dmin2(c, d)); }
 
@@ -1024,12 +1033,28 @@ __global__ void __launch_bounds__(256) k_nf_verify(const float *__restrict__ z, 
 // k_nf_solve.  Anything that does not fit the integer form (k_nf_init_tile's *irbad, a distance beyond D_LIMIT,
 // weights that are not whole ulps) raises *irbad and the caller falls back to the W-based solver.
 // =====================================================================================================
-constexpr int IR_LD = NF_T + 8;                 // shared row = columns c0 - 4 .. c0 + 67 of Dg
+// In-tile relaxation of the integer-raster solver: LINE SWEEPS.  The four warps of a CTA are the four sweep
+// directions of a chamfer distance transform (top->bottom, bottom->top, left->right, right->left); a sweep walks the
+// 64 lines of the tile in its direction and relaxes every cell of a line from the three cells of the previous line
+// that touch it (straight: + short, the two diagonals: + diag).  The previous line stays in registers (a lane owns
+// cells k = lane and lane + 32 of every line, neighbours come by shuffle), the line's current values are loaded one
+// step ahead, so the dependent chain of a step is shuffle -> add -> min -> compare (~45 cycles), and a wave crosses the
+// tile in one sweep (~1.5 us) where the dirty-block iteration of round 1 took ~15 us (8 warps, two barriers and a
+// 64-block work list per iteration: profiles/r01c_nf_solve_ir_raw.txt, 65 % of the warp samples at a barrier).
+// The shared row stride is ODD (67 words): a row and a column of the tile are both 64 consecutive banks modulo 32, so
+// all four directions read and write without bank conflicts through plain 4-byte accesses.  Rounds: a direction runs again when ANOTHER direction changed a cell in
+// the previous round; the tile is settled when a round changes nothing.  A tile queued for a changed apron side starts
+// with the one direction that reads that side.
+constexpr int IR_LD = NF_T + 3;                 // 67: odd
 constexpr int IR_SMEM = (NF_T + 2) * IR_LD * 4 + NF_T * NF_T;
-// threads per CTA of the integer-raster solver.  A visit is mostly one dependent chain (stall_barrier dominates the
-// warp samples), so more, smaller CTAs per SM keep more tiles in flight while the FIFO is full.
 #ifndef IR_NT
-#define IR_NT 256
+#define IR_NT 128
+#endif
+#ifndef IR_CTAS
+#define IR_CTAS 8
+#endif
+#ifndef IR_UNCOND
+#define IR_UNCOND 1
 #endif
 
 // the wall frame of the padded raster: row 0, the rows below the tiles, and 4 columns either side of every tile row
@@ -1048,123 +1073,169 @@ __global__ void __launch_bounds__(256) k_ir_frame(int *Dg, int P, int inner_rows
     Dg[row * P + (k < 4 ? k : P - 8 + k)] = D_WALL;
 }
 
-struct RelaxIR {
-    int *sd;
-    const unsigned char *se;   // per interior cell: low byte of the binade exponent (only read when !uni)
-    const int2 *wtab;
-    int elo8;
-    bool uni;
-    int *overflow;
-    __device__ inline int2 weights(int lr, int lc) const {
-        return uni ? wtab[0] : wtab[(se[lr * NF_T + lc] - elo8) & (NF_NBIN - 1)];
-    }
-    __device__ inline bool block(int b, unsigned *sides) const {
-        const unsigned full = 0xffffffffu;
-        int lane = threadIdx.x & 31;
-        int lr = (b >> 3) * 8 + (lane >> 2), lc = (b & 7) * 8 + (lane & 3) * 2;
-        int *p = sd + (lr + 1) * IR_LD + (lc + 4);          // even index: (p[0], p[1]) is an aligned pair
-        int2 own = *reinterpret_cast<const int2 *>(p);
-        int w0 = own.x, w1 = own.y;
-        bool live = (w0 <= D_INF) || (w1 <= D_INF);
-        *sides = 0;
-        if (!__any_sync(full, live)) return false;
-        int sq = 0, dq = 0, sq1 = 0, dq1 = 0;
-        if (live) {
-            int2 wa = weights(lr, lc), wb = weights(lr, lc + 1);
-            sq = wa.x; dq = wa.y; sq1 = wb.x; dq1 = wb.y;
-        }
-        unsigned sds = 0;
-        bool any = false;
-        for (int it = 0;; it++) {
-            bool ch = false;
-            if (live) {
-                const int2 ua = *reinterpret_cast<const int2 *>(p - IR_LD - 2), ub = *reinterpret_cast<const int2 *>(p - IR_LD);
-                const int2 uc = *reinterpret_cast<const int2 *>(p - IR_LD + 2);
-                const int2 ma = *reinterpret_cast<const int2 *>(p - 2), mc = *reinterpret_cast<const int2 *>(p + 2);
-                const int2 da = *reinterpret_cast<const int2 *>(p + IR_LD - 2), db = *reinterpret_cast<const int2 *>(p + IR_LD);
-                const int2 dc = *reinterpret_cast<const int2 *>(p + IR_LD + 2);
-                const int a0 = ua.y, a1 = ub.x, a2 = ub.y, a3 = uc.x, l = ma.y, r = mc.x;
-                const int c0 = da.y, c1 = db.x, c2 = db.y, c3 = dc.x;
-                if (w0 <= D_INF) {
-                    int m = min(imin4(a0, a2, c0, c2) + dq, imin4(a1, l, w1, c1) + sq);
-                    if (m < w0) { w0 = m; p[0] = m; ch = true; if (m >= D_LIMIT) *overflow = 1; }
-                }
-                if (w1 <= D_INF) {
-                    int m = min(imin4(a1, a3, c1, c3) + dq1, imin4(a2, w0, r, c2) + sq1);
-                    if (m < w1) { w1 = m; p[1] = m; ch = true; if (m >= D_LIMIT) *overflow = 1; }
-                }
-            }
-            __syncwarp();
-            unsigned bal = __ballot_sync(full, ch);
-            if (!bal) break;
-            any = true;
-            sds |= nf_sides(bal);
-            if (it == NF_BLOCK_ITERS - 1) { sds |= 16u; break; }
-        }
-        *sides = sds;
-        return any;
-    }
+struct IrShared {
+    int k;             // tile taken off the FIFO (-1: none)
+    int flags;         // side bits the tile was queued with
+    int e, elo;        // largest / smallest binade exponent of the tile's lake cells
+    int has;           // the tile or its apron holds a lake cell
+    int bad;           // does not fit the integer form
+    int chgdir[3];     // directions that changed a cell, per round (rotating)
+    unsigned long long crow[3], ccol[3];   // rows / columns of the tile in which a cell changed, per round (rotating)
+    unsigned long long rows, cols;         // ... during the whole visit (write-back, edges for the neighbours)
+    int ring;          // bit 0/1/2/3: the tile's top / bottom / left / right edge changed
+    int nb;            // neighbour tiles to queue: bit (dy+1)*3 + (dx+1)
+    int2 wtab[NF_NBIN];
 };
 
-// ---- alternatives to the dirty-block relaxation that were measured in round 1 and removed again -------------------
-// Directional cone sweeps with dirty-line gating (one warp per direction sweeps the tile line by line, the previous
-// line in registers, neighbours by shuffle; rounds until no line is dirty): correct, 6.65 ms against 5.9 ms for the
-// dirty blocks at 8192^2 — a single warp runs a line in ~350 cycles (85 dependent instructions), so one sweep across
-// the tile costs as much as the block iteration does with all 8 warps.  (git history: commit "K2: gated cone sweeps
-// and tail mid-flush measured ...".)
-// IR_MIDFLUSH 1: while CTAs are idle (fewer tiles queued or running than the grid has CTAs) a tile forwards its ring
-// to the neighbours after iterations 1, 2, 4, ... instead of only when it has settled, so the wave of a large lake
-// is pipelined across tiles in the tail of the solve.  Measured at 8192^2 (round 1): 66 k -> 72 k visits, no-flats
-// stage 5.9 -> 6.3 ms — off (the switch stays: it costs nothing when off).
-// A CTA taking the tile it has just woken directly instead of through the FIFO (always: 66 k -> 90-108 k visits,
-// 5.7-6.4 ms; only while CTAs are idle: no change): the queue round trip is not what a hop costs.  128- and
-// 512-thread CTAs: 7.6 / 6.4 ms; 6 CTAs per SM (40 registers): no change.
-#ifndef IR_MIDFLUSH
-#define IR_MIDFLUSH 0
-#endif
+// One sweep of the tile in direction `dir` (0 top->bottom, 1 bottom->top, 2 left->right, 3 right->left) by one warp.
+// Cell (line, k) of the sweep sits at sd[org + line * SL + k * SK]; lines and k run -1..64 (apron included).
+__device__ __forceinline__ void ir_red_min(int *p, int v, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\t@q red.shared.min.s32 [%0], %1;\n\t}"
+                 :: "r"((unsigned)__cvta_generic_to_shared(p)), "r"(v), "r"((int)pred) : "memory");
+}
 
-__global__ void __launch_bounds__(IR_NT, 1024 / IR_NT) k_nf_solve_ir(const float *__restrict__ F, int *Dg, int P, int *ring, int cap,
+// `start`: first position (in sweep order: position p is line p of a forward sweep, line 63 - p of a backward one) to
+// relax; `lastext`: from this position on the sweep stops at the first line it does not change (everything that
+// could disturb the lines beyond lies behind it).
+template <bool UNI, int dir>
+__device__ __forceinline__ void ir_sweep(int *sd, const unsigned char *se, IrShared &S, const int lane, const int rnd,
+                                         const int start, const int lastext) {
+    const unsigned full = 0xffffffffu;
+    constexpr bool rowsweep = dir < 2;
+    constexpr int SL = rowsweep ? IR_LD : 1, SK = rowsweep ? 1 : IR_LD;
+    constexpr int EL = rowsweep ? NF_T : 1, EK = rowsweep ? 1 : NF_T;      // the same walk over the binade bytes
+    constexpr int step = (dir & 1) ? -1 : 1;
+    const int first = (dir & 1) ? NF_T - 1 - start : start;                // line of position `start`
+    const int org = IR_LD + 1;
+    int *pa = sd + org + lane * SK + first * SL, *pb = pa + 32 * SK;       // the line being relaxed
+    const int *pp = sd + org + (lane == 0 ? -1 : NF_T) * SK + first * SL;
+    const unsigned char *ea = se + lane * EK + first * EL, *eb = ea + 32 * EK;
+    const int elo8 = S.elo & 0xff;
+    int2 wA = S.wtab[0], wB = wA;
+    int pA = pa[-step * SL], pB = pb[-step * SL], pP = pp[-step * SL];
+    int cA = pa[0], cB = pb[0], cP = pp[0];
+    if (!UNI) {
+        wA = S.wtab[(ea[0] - elo8) & (NF_NBIN - 1)];
+        wB = S.wtab[(eb[0] - elo8) & (NF_NBIN - 1)];
+    }
+    // change bookkeeping without branches: one bit per step shifted into `hist` (the step at position start + j ends up
+    // at bit n - 1 - j after n steps), per-lane "my cell A / B changed at some step" flags
+    unsigned long long hist = 0;
+    int everA = 0, everB = 0;
+    const int srcl = (lane + 31) & 31, srcr = (lane + 1) & 31;
+    const bool l0 = lane == 0, l31 = lane == 31;
+    int p = start;
+#pragma unroll 2
+    for (; p < NF_T; p++) {
+        // the next line's current values: independent of this step's result, in flight while it is computed
+        const int nA = pa[step * SL], nB = pb[step * SL], nP = pp[step * SL];
+        int2 nwA = wA, nwB = wB;
+        if (!UNI) {
+            const int o = p + 1 < NF_T ? step * EL : 0;
+            nwA = S.wtab[(ea[o] - elo8) & (NF_NBIN - 1)];
+            nwB = S.wtab[(eb[o] - elo8) & (NF_NBIN - 1)];
+        }
+        // a wall never moves: its candidate is pushed out of range (off the dependent chain: cA / cB were loaded a step ago)
+        const int wallA = cA > D_INF ? 0x7fffffff : 0, wallB = cB > D_INF ? 0x7fffffff : 0;
+        // neighbours of cell k on the previous line: k - 1 and k + 1 (cells 31 | 32 wrap between the two halves)
+        const int X = l0 ? pB : pA, Y = l31 ? pA : pB;
+        int lA = __shfl_sync(full, pA, srcl);
+        const int rA = __shfl_sync(full, X, srcr);
+        const int lB = __shfl_sync(full, Y, srcl);
+        int rB = __shfl_sync(full, pB, srcr);
+        lA = l0 ? pP : lA;
+        rB = l31 ? pP : rB;
+        const int candA = min(pA + wA.x, min(lA, rA) + wA.y) | wallA;
+        const int candB = min(pB + wB.x, min(lB, rB) + wB.y) | wallB;
+        const bool chA = candA < cA, chB = candB < cB;
+        // the four warps work on the same tile at once: improvements go in as shared-memory min reductions (no result),
+        // so a cell never rises and a value read one step early only costs another round.  Issued unconditionally (a
+        // lane without an improvement reduces with INT_MAX): ptxas wraps a conditional ATOMS into a divergent branch
+        // region, which costs more than the reduction (measured at 8192^2 / 32768^2: 4.03 / 41.5 ms against 4.46 / 43.8;
+        // plain predicated stores with the sweeps restarted on the first changed line: 4.07 / 42.0 and more rounds)
+#if IR_UNCOND
+        atomicMin(pa, chA ? candA : 0x7fffffff);
+        atomicMin(pb, chB ? candB : 0x7fffffff);
+#elif IR_PLAIN
+        if (chA) *pa = candA;
+        if (chB) *pb = candB;
+#else
+        ir_red_min(pa, candA, chA);
+        ir_red_min(pb, candB, chB);
+#endif
+        hist = (hist << 1) | (unsigned long long)(chA | chB);
+        everA |= chA;
+        everB |= chB;
+        pA = chA ? candA : cA;
+        pB = chB ? candB : cB;
+        pP = cP;
+        cA = nA; cB = nB; cP = nP;
+        wA = nwA; wB = nwB;
+        pa += step * SL; pb += step * SL; pp += step * SL;
+        if (!UNI) { ea += step * EL; eb += step * EL; }
+        if (p >= lastext && !__any_sync(full, chA | chB)) { p++; break; }
+    }
+    const int n = p - start;                       // steps done
+    // lines that changed (any lane), as a mask over line numbers
+    unsigned hlo = __reduce_or_sync(full, (unsigned)hist), hhi = __reduce_or_sync(full, (unsigned)(hist >> 32));
+    unsigned long long lines = ((unsigned long long)hhi << 32) | hlo;
+    if (n > 0 && lines) {
+        lines = __brevll(lines) >> (64 - n);       // bit j = step j, i.e. position start + j
+        lines <<= start;                           // bit = position
+        if (dir & 1) lines = __brevll(lines);      // position p is line 63 - p
+    }
+    const unsigned balA = __ballot_sync(full, everA), balB = __ballot_sync(full, everB);      // cells k = lane / lane + 32
+    if (lane == 0 && lines) {
+        const unsigned long long cells = ((unsigned long long)balB << 32) | balA;
+        const unsigned long long r = rowsweep ? lines : cells, c = rowsweep ? cells : lines;
+        atomicOr(&S.crow[rnd % 3], r);
+        atomicOr(&S.ccol[rnd % 3], c);
+        atomicOr(&S.chgdir[rnd % 3], 1 << dir);
+    }
+}
+
+__global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__restrict__ F, int *Dg, int P, int *ring, int cap,
                                                         int *tileflag, const int *__restrict__ tilesides,
                                                         const int *__restrict__ tmeta, NfCtl *ctl, int *irbad, int rows,
                                                         int cols, int tiles_x, int tiles_y, double sh, double dg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int *sd = reinterpret_cast<int *>(smem_raw);
     unsigned char *se = smem_raw + (NF_T + 2) * IR_LD * 4;
-    __shared__ NfTileShared S;
+    __shared__ IrShared S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (*(volatile unsigned *)&ctl->tail == 0 || *(volatile int *)irbad) return;      // nothing queued / not for this form
-    const unsigned sd_base = (unsigned)__cvta_generic_to_shared(sd);
 
     for (;;) {
-        // thread 32 takes the next tile while thread 0 still signs off the previous one (see k_nf_solve)
+        // thread 32 takes the next tile while thread 0 still signs off the previous one
         if (tid == 32) {
             unsigned my = atomicAdd(&ctl->head, 1u);
             volatile int *slot = ring + (my % (unsigned)cap);
             int t = -1;
+            const unsigned long long t_start = nf_globaltimer();
             for (unsigned spins = 0;; spins++) {
                 t = *slot;
                 if (t >= 0) break;
                 if (*(volatile int *)&ctl->done) break;
-                __nanosleep(200);
-                if (spins > (1u << 23)) { atomicExch(&ctl->done, 2); break; }      // watchdog (~2 s): never hang the GPU
+                __nanosleep(100);
+                // watchdog on the wall clock (never hang the GPU): generous, so that a profiler or a time-sliced GPU
+                // does not trip it
+                if ((spins & 1023u) == 1023u && nf_globaltimer() - t_start > NF_WATCHDOG_NS) { atomicExch(&ctl->done, 2); break; }
             }
             if (t >= 0) {
                 *slot = -1;
                 __threadfence();
                 S.flags = atomicExch(tileflag + t, NF_RUNNING) & NF_SIDES;
-                S.dirty[1] = 0;
-                S.dirty[2] = 0;
-                S.chgmask = 0;
                 S.ring = 0;
                 S.nb = 0;
-                S.grab[0] = S.grab[1] = S.grab[2] = 0;
-                S.midflush = IR_MIDFLUSH && *(volatile int *)&ctl->pending < (int)gridDim.x;
                 S.bad = 0;
-                S.any = 0;
+                S.rows = S.cols = 0;
+                S.chgdir[0] = S.chgdir[1] = S.chgdir[2] = 0;
+                S.crow[0] = S.crow[1] = S.crow[2] = 0;
+                S.ccol[0] = S.ccol[1] = S.ccol[2] = 0;
                 int meta = __ldg(tmeta + t);
                 S.elo = (int)(short)(meta & 0xffff);
                 S.e = S.elo + ((meta >> 16) & 15);
-                S.dmax = (meta >> 20) & 1;          // here: the tile or its apron holds a lake cell
+                S.has = (meta >> 20) & 1;
                 atomicAdd(&ctl->visits, 1);
             }
             S.k = t;
@@ -1172,21 +1243,43 @@ __global__ void __launch_bounds__(IR_NT, 1024 / IR_NT) k_nf_solve_ir(const float
         __syncthreads();
         const int t = S.k;
         if (t < 0) break;
-#ifdef NF_STATS
-        unsigned long long tg0 = gtimer(), tg1 = 0; int nit = 0;
-#endif
         const int ty = t / tiles_x, tx = t - ty * tiles_x;
         const int r0 = ty * NF_T, c0 = tx * NF_T;
-        if (S.dmax) {
-            // ---- tile + apron: 66 rows x 18 chunks of 16 bytes, straight from L2 / HBM into shared memory
+#ifdef NF_STATS
+        unsigned long long tg0 = gtimer(), tg1 = tg0, tg2 = tg0; int nrounds = 0;
+#endif
+        if (S.has) {
+            // ---- tile + apron: 66 rows x 18 chunks of 16 bytes (columns c0 - 4 .. c0 + 67 of the padded raster, L2 only:
+            // other SMs write these lines), the 66 x 66 cells of interest stored at the odd stride
             const int *src0 = Dg + (size_t)r0 * P + c0;        // row r0 - 1, column c0 - 4 of the padded raster
-            for (int q = tid; q < (NF_T + 2) * 18; q += IR_NT) {
-                int lr = q / 18, ch = q - lr * 18;
-                const int *src = src0 + (size_t)lr * P + ch * 4;
-                unsigned dst = sd_base + (unsigned)((lr * IR_LD + ch * 4) * 4);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            constexpr int NCH = (NF_T + 2) * 18;
+            int fin = 0;       // a finite distance somewhere in the block: without one nothing can move
+#pragma unroll 1
+            for (int q0 = tid; q0 < NCH; q0 += IR_NT * 5) {
+                int4 v[5];
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    int q = q0 + j * IR_NT;
+                    if (q < NCH) {
+                        int lr = q / 18, ch = q - lr * 18;
+                        v[j] = __ldcg(reinterpret_cast<const int4 *>(src0 + (size_t)lr * P + ch * 4));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    int q = q0 + j * IR_NT;
+                    if (q < NCH) {
+                        int lr = q / 18, ch = q - lr * 18;
+                        int *dst = sd + lr * IR_LD + ch * 4 - 3;      // column c0 - 4 + 4 ch + m -> k + 1 = 4 ch + m - 3
+                        if (ch == 0) { dst[3] = v[j].w; fin |= v[j].w < D_INF; }                       // k = -1
+                        else if (ch == 17) { dst[0] = v[j].x; fin |= v[j].x < D_INF; }                 // k = 64 (the rest lies beyond the apron)
+                        else {
+                            dst[0] = v[j].x; dst[1] = v[j].y; dst[2] = v[j].z; dst[3] = v[j].w;
+                            fin |= min(min(v[j].x, v[j].y), min(v[j].z, v[j].w)) < D_INF;
+                        }
+                    }
+                }
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
             const bool uni = S.e == S.elo;
             if (!uni) {
                 // several binades in the tile: the per-cell binade byte comes from F
@@ -1210,81 +1303,130 @@ __global__ void __launch_bounds__(IR_NT, 1024 / IR_NT) k_nf_solve_ir(const float
                 }
                 S.wtab[tid] = wt;
             }
-            if (tid == 0) S.dirty[0] = nf_region(S.flags);
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncthreads();
-            if (!S.bad) {
-                RelaxIR rx{sd, se, S.wtab, S.elo & 0xff, uni, &S.bad};
-                auto flush = [&]() {
-                    if (S.bad) return;
-                    // the blocks that changed go back as they are: a lane holds two adjacent cells (8-byte store)
-                    unsigned long long mm = S.chgmask;
-                    for (int idx = 0; mm; idx++) {
-                        int b = __ffsll((long long)mm) - 1;
-                        mm &= mm - 1;
-                        if ((idx % (IR_NT / 32)) != warp) continue;
-                        int lr = (b >> 3) * 8 + (lane >> 2), lc = (b & 7) * 8 + (lane & 3) * 2;
-                        const int2 v = *reinterpret_cast<const int2 *>(sd + (lr + 1) * IR_LD + (lc + 4));
-                        *reinterpret_cast<int2 *>(Dg + (size_t)(r0 + lr + 1) * P + (c0 + lc + 4)) = v;
+            fin = __syncthreads_or(fin);
+#ifdef NF_STATS
+            tg1 = tg2 = gtimer();
+#endif
+            if (!S.bad && fin) {
+                // round 0: everything (first visit), or the one direction that reads the apron side that changed
+                int dirs = (S.flags & 16) ? 15 : (S.flags & 15);
+                bool whole = (S.flags & 16) != 0;
+                unsigned long long mrow = 0, mcol = 0;       // rows / columns changed in the previous round
+                for (int rnd = 0;; rnd++) {
+                    if (tid == 0) { S.chgdir[(rnd + 1) % 3] = 0; S.crow[(rnd + 1) % 3] = 0; S.ccol[(rnd + 1) % 3] = 0; }
+                    if ((dirs >> warp) & 1) {
+                        // positions (sweep order) this direction has to look at: the line after the first changed one ...
+                        int start = 0, lastext = rnd == 0 && whole ? NF_T : 0;
+                        if (rnd > 0) {
+                            unsigned long long m = warp < 2 ? mrow : mcol;
+                            if (warp & 1) m = __brevll(m);
+#if IR_PLAIN
+                            start = __ffsll((long long)m) - 1;           // the first changed position itself (see ir_sweep)
+#else
+                            start = __ffsll((long long)m);               // first changed position + 1 (m != 0 here)
+#endif
+                            lastext = 64 - __clzll((long long)m);        // ... up to the one after the last changed one
+                        }
+                        if (start < NF_T) {
+                            if (uni) {
+                                if (warp == 0) ir_sweep<true, 0>(sd, se, S, lane, rnd, start, lastext);
+                                else if (warp == 1) ir_sweep<true, 1>(sd, se, S, lane, rnd, start, lastext);
+                                else if (warp == 2) ir_sweep<true, 2>(sd, se, S, lane, rnd, start, lastext);
+                                else ir_sweep<true, 3>(sd, se, S, lane, rnd, start, lastext);
+                            } else {
+                                if (warp == 0) ir_sweep<false, 0>(sd, se, S, lane, rnd, start, lastext);
+                                else if (warp == 1) ir_sweep<false, 1>(sd, se, S, lane, rnd, start, lastext);
+                                else if (warp == 2) ir_sweep<false, 2>(sd, se, S, lane, rnd, start, lastext);
+                                else ir_sweep<false, 3>(sd, se, S, lane, rnd, start, lastext);
+                            }
+                        }
                     }
-                    // neighbours that can gain from the new ring (see k_nf_solve)
-                    for (int sidx = tid; sidx < 4 * NF_T; sidx += IR_NT) {
-                        const int side = sidx >> 6, k = sidx & 63;      // 0 top, 1 bottom, 2 left, 3 right (warp-uniform)
-                        if (!(S.ring & (1 << side))) continue;
+                    __syncthreads();
+                    const int cd = S.chgdir[rnd % 3];
+                    mrow = S.crow[rnd % 3];
+                    mcol = S.ccol[rnd % 3];
+                    if (tid == 0) { S.rows |= mrow; S.cols |= mcol; }
+                    if (cd == 0 || S.bad) {
+                        if (tid == 0) atomicAdd(&ctl->reserved, rnd + 1);
+#ifdef NF_STATS
+                        nrounds = rnd + 1; tg2 = gtimer();
+#endif
+                        break;
+                    }
+                    dirs = (cd & (cd - 1)) ? 15 : (15 & ~cd);
+                }
+                __syncthreads();
+            }
+            if (!S.bad && S.rows) {
+                // ---- the rows that changed go back (two coalesced 128-byte stores per row)
+                unsigned long long mm = S.rows;
+                const int ringbits = ((mm & 1ull) ? 1 : 0) | ((mm >> 63) ? 2 : 0) | ((S.cols & 1ull) ? 4 : 0) | ((S.cols >> 63) ? 8 : 0);
+                for (int idx = 0; mm; idx++) {
+                    int lr = __ffsll((long long)mm) - 1;
+                    mm &= mm - 1;
+                    if ((idx & (IR_NT / 32 - 1)) != warp) continue;
+                    const int *srow = sd + (lr + 1) * IR_LD + 1;
+                    int *drow = Dg + (size_t)(r0 + lr + 1) * P + (c0 + 4);
+                    const int va = srow[lane], vb = srow[lane + 32];
+                    __stcg(drow + lane, va);
+                    __stcg(drow + lane + 32, vb);
+                    // a distance beyond what the integer form is trusted for: the float64 form takes over
+                    if ((va >= D_LIMIT && va < D_INF) || (vb >= D_LIMIT && vb < D_INF)) S.bad = 1;
+                }
+                // ---- neighbours that can gain from the new edge cells: a lake cell of their side of the apron that
+                // lies above (edge cell + weight)
+                const bool uni2 = uni;
+                for (int sidx = tid; sidx < 4 * NF_T; sidx += IR_NT) {
+                    const int side = sidx >> 6, k = sidx & 63;      // 0 top, 1 bottom, 2 left, 3 right (warp-uniform)
+                    int nbm = 0;
+                    if (ringbits & (1 << side)) {
                         int lr = side == 0 ? 0 : (side == 1 ? NF_T - 1 : k);
                         int lc = side == 2 ? 0 : (side == 3 ? NF_T - 1 : k);
-                        int d = sd[(lr + 1) * IR_LD + (lc + 4)];
-                        int nbm = 0;
+                        int d = sd[(lr + 1) * IR_LD + (lc + 1)];
                         if (d < D_INF) {
-                            int2 wt = rx.weights(lr, lc);
 #pragma unroll
                             for (int o = -1; o <= 1; o++) {
                                 int ar = side == 0 ? -1 : (side == 1 ? NF_T : lr + o);
                                 int ac = side == 2 ? -1 : (side == 3 ? NF_T : lc + o);
-                                int da = sd[(ar + 1) * IR_LD + (ac + 4)];
-                                int w = (o == 0) ? wt.x : wt.y;
-                                if (da <= D_INF && d + w < da) {
-                                    int dy = ar < 0 ? -1 : (ar >= NF_T ? 1 : 0), dx = ac < 0 ? -1 : (ac >= NF_T ? 1 : 0);
-                                    nbm |= 1 << ((dy + 1) * 3 + (dx + 1));
+                                int da = sd[(ar + 1) * IR_LD + (ac + 1)];
+                                if (da <= D_INF) {
+                                    // the weight is the TARGET cell's (adjacent lake cells share their binade)
+                                    int2 wt = uni2 ? S.wtab[0] : S.wtab[(se[lr * NF_T + lc] - (S.elo & 0xff)) & (NF_NBIN - 1)];
+                                    int w = (o == 0) ? wt.x : wt.y;
+                                    if (d + w < da) {
+                                        int dy = ar < 0 ? -1 : (ar >= NF_T ? 1 : 0), dx = ac < 0 ? -1 : (ac >= NF_T ? 1 : 0);
+                                        nbm |= 1 << ((dy + 1) * 3 + (dx + 1));
+                                    }
                                 }
                             }
                         }
-                        nbm = __reduce_or_sync(0xffffffffu, nbm);
-                        if (lane == 0 && nbm) atomicOr(&S.nb, nbm);
                     }
-                    __threadfence();
-                    __syncthreads();
-                    if (tid < 9 && tid != 4) {
-                        const int dy = tid / 3 - 1, dx = tid % 3 - 1;
-                        const int y = ty + dy, x = tx + dx;
-                        if ((S.nb & (1 << tid)) && x >= 0 && x < tiles_x && y >= 0 && y < tiles_y) {
-                            int bits = (dy < 0 ? 2 : 0) | (dy > 0 ? 1 : 0) | (dx < 0 ? 8 : 0) | (dx > 0 ? 4 : 0);
-                            if (dy && dx) bits = dy < 0 ? 2 : 1;      // a corner: one block of that side is enough
-                            int nb = y * tiles_x + x;
-                            if ((__ldg(tilesides + nb) & bits) && atomicOr(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb);
-                        }
+                    nbm = __reduce_or_sync(0xffffffffu, nbm);
+                    if (lane == 0 && nbm) atomicOr(&S.nb, nbm);
+                }
+                __threadfence();
+                __syncthreads();
+                if (tid < 9 && tid != 4) {
+                    const int dy = tid / 3 - 1, dx = tid % 3 - 1;
+                    const int y = ty + dy, x = tx + dx;
+                    if ((S.nb & (1 << tid)) && x >= 0 && x < tiles_x && y >= 0 && y < tiles_y) {
+                        int bits = (dy < 0 ? 2 : 0) | (dy > 0 ? 1 : 0) | (dx < 0 ? 8 : 0) | (dx > 0 ? 4 : 0);
+                        if (dy && dx) bits = dy < 0 ? 2 : 1;      // a corner: the row sweep from that side reads it
+                        int nb = y * tiles_x + x;
+                        if ((__ldg(tilesides + nb) & bits) && atomicOr(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb);
                     }
-                    __syncthreads();
-                    if (tid == 0) { S.nb = 0; S.ring = 0; S.chgmask = 0; }
-                    __syncthreads();
-                };
-#ifdef NF_STATS
-                tg1 = gtimer();
-#endif
-                int its = nf_tile_iterate(rx, S, flush);
-#ifdef NF_STATS
-                nit = its;
-#endif
-                (void)its;
+                }
             }
+            __syncthreads();
             if (S.bad && tid == 0) atomicExch(irbad, 1);
         }
 #ifdef NF_STATS
         if (tid == 0) {
             unsigned k = atomicAdd(&g_nf_nlog, 1u);
             if (k < 262144u) {
+                unsigned long long rel = tg2 - tg1; if (rel > 0xffffffull) rel = 0xffffffull;
                 g_nf_log[4 * k] = tg0; g_nf_log[4 * k + 1] = tg1; g_nf_log[4 * k + 2] = gtimer();
-                g_nf_log[4 * k + 3] = (unsigned long long)t | ((unsigned long long)nit << 32) | ((unsigned long long)blockIdx.x << 48);
+                g_nf_log[4 * k + 3] = (unsigned long long)(unsigned)t | ((unsigned long long)(nrounds & 0xff) << 32) | (rel << 40);
             }
         }
 #endif
@@ -1504,7 +1646,7 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
     }
     dim3 g2(cdiv(cols, 64), cdiv(rows, 4));
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
-    int64_t visits = 0, tries = 0;
+    int64_t visits = 0, tries = 0, rounds = 0;
     for (;;) {
         tries++;
         MS_CUDA(cudaMemsetAsync(tileflag.p, 0, (size_t)ntiles * sizeof(int), s));
@@ -1544,6 +1686,7 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
         if (ir) MS_CUDA(cudaMemcpyAsync(h_irbad, irbad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
         MS_TRY(ms::stream_sync(s));
         visits += h->visits;
+        rounds += h->reserved;
         if (ir && *h_irbad) {       // something does not fit the integer form: the W-based solver takes over
             use_ir = false;
             continue;
@@ -1571,7 +1714,7 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
             return MS_ERR_NOCONV;
         }
     }
-    if (stats) { stats[0] = tries; stats[1] = visits; stats[2] = tries - 1; }
+    if (stats) { stats[0] = tries; stats[1] = visits; stats[2] = tries - 1; stats[3] = rounds; }
     return MS_OK;
 }
 
@@ -1896,8 +2039,11 @@ int ms_band_nf_verify_dev(ms_band *B, const float *dem, const double *fnf, doubl
 int ms_fill_terrain_no_flats_dev(const float *dtm, const float *filled, double short_eps, double diag_eps,
                                  double *out, int64_t rows, int64_t cols, int64_t *stats, void *stream) {
     MS_TRY(ms::ensure_init());
-    return ms::fill_no_flats_dev_impl(dtm, filled, short_eps, diag_eps, out, rows, cols, stats,
-                                      (cudaStream_t)stream, nullptr, nullptr);
+    int64_t st[4] = {0, 0, 0, 0};       // the internal form also counts sweep rounds; the ABI documents three entries
+    int rc = ms::fill_no_flats_dev_impl(dtm, filled, short_eps, diag_eps, out, rows, cols, st, (cudaStream_t)stream,
+                                        nullptr, nullptr);
+    if (stats) { stats[0] = st[0]; stats[1] = st[1]; stats[2] = st[2]; }
+    return rc;
 }
 
 int ms_fill_terrain_no_flats(const float *dtm, double short_eps, double diag_eps, double *out, int64_t rows,

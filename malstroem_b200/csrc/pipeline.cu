@@ -85,11 +85,11 @@ extern "C" int ms_pipeline_host_dev(ms_rasters *io, const ms_host_out *host, voi
     io->short_eps = (nextafter(maxval, (double)INFINITY) - maxval) * 1024.0;
     io->diag_eps = io->short_eps * pow(2.0, 0.5);
     // dem.py:80-83
-    int64_t nfstats[3] = {0, 0, 0};
+    int64_t nfstats[4] = {0, 0, 0, 0};
     int flowdir_done = 0;      // the integer-raster no-flats solve writes the D8 codes in its finishing pass
     MS_TRY(fill_no_flats_dev_impl(io->dem, io->filled, io->short_eps, io->diag_eps, io->fnf, rows, cols, nfstats, s,
                                   io->flowdir, &flowdir_done));
-    io->stats[2] = nfstats[0]; io->stats[3] = nfstats[1]; io->stats[4] = nfstats[2];
+    io->stats[2] = nfstats[0]; io->stats[3] = nfstats[1]; io->stats[4] = nfstats[2]; io->stats[7] = nfstats[3];
     MS_TRY(ship(host->fnf, io->fnf, (size_t)n * sizeof(double), s));
     if (!flowdir_done) MS_TRY(flowdir_dev_impl(io->fnf, io->flowdir, rows, cols, 1, s, 0));
     MS_TRY(ship(host->flowdir, io->flowdir, (size_t)n, s));

@@ -18,7 +18,7 @@ TABLES = (("st_min", torch.float64), ("st_max", torch.float64), ("st_sum", torch
           ("ppmin_col", torch.int64), ("ppmax_value", torch.float64), ("ppmax_row", torch.int64),
           ("ppmax_col", torch.int64))
 STAT_NAMES = ("boruvka_rounds", "catchments", "noflat_rounds", "noflat_tile_visits", "noflat_reverify",
-              "fill_jump_rounds", "wshed_jump_rounds", "reserved")
+              "fill_jump_rounds", "wshed_jump_rounds", "noflat_sweep_rounds")
 
 
 class RasterPipeline(object):
