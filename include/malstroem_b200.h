@@ -193,6 +193,24 @@ int ms_band_nf_p2p_arm_dev(ms_band *band, void *stream);
 int ms_band_nf_p2p_solve_dev(ms_band *band, const float *filled, double *fnf, double short_eps, double diag_eps,
                              double cap_bound, int64_t *tile_visits, void *stream);
 
+/* The same fused solve on the INTEGER RASTER of the single-GPU path (fill.py:174-232 / _fill.pyx:72-124 as above; the
+ * W-based form above stays as the fall-back for rasters that do not fit the integer form).  edgefix: fixed flags
+ * (seed or raster border) of the band's first / last own row (cols bytes each) - the caller hands them to the
+ * neighbours, whose halo rows they describe.  prepare: the band's padded int32 distance raster, its edge rows stored
+ * into the neighbours' mailboxes (peer memory), FIFO := tiles holding lake cells; *queued, *irbad (the band does not
+ * fit the integer form).  All ranks synchronise, ms_band_nf_p2p_arm_dev, synchronise, solve (all ranks at once).
+ * finish: the float64 surface written once and verified against the fixed-point equation with the halo rows
+ * (*nviol), the D8 codes of the band's rows (flow.py:142-167, edges of the raster flowing outward) on the way. */
+int ms_band_nf_ir_edgefix_dev(ms_band *band, const float *dem, const float *filled, uint8_t *fix_top, uint8_t *fix_bot,
+                              void *stream);
+int ms_band_nf_ir_prepare_dev(ms_band *band, const float *dem, const float *filled, double short_eps, double diag_eps,
+                              double cap_bound, const uint8_t *fix_top, const uint8_t *fix_bot, int64_t *queued,
+                              int *irbad, void *stream);
+int ms_band_nf_ir_solve_dev(ms_band *band, const float *filled, double short_eps, double diag_eps, int64_t *tile_visits,
+                            int *irbad, void *stream);
+int ms_band_nf_ir_finish_dev(ms_band *band, const float *dem, const float *filled, double *fnf, uint8_t *flowdir,
+                             double short_eps, double diag_eps, int64_t *nviol, void *stream);
+
 /* flow.terrain_flowdirection (flow.py:142-167) on a band (needs the halo rows of the terrain) */
 int ms_band_flowdir_dev(ms_band *band, const double *terrain, uint8_t *flowdir, int edges_flow_outward, void *stream);
 

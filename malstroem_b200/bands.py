@@ -229,6 +229,7 @@ class BandPipeline(object):
                 self.out[name] = torch.empty((self.rows, self.cols), dtype=dt, device=dev)
         self.dem = self.dem_ext[1:1 + self.rows]
         self.tables, self.nlabels, self.stats = {}, 0, {}
+        self._flowdir_done = False
         self.p2p = self._p2p_setup()
 
     def _p2p_setup(self):
@@ -339,8 +340,9 @@ class BandPipeline(object):
         # K2 no-flats fill
         self._noflats(st)
         self._tick("noflats")
-        # K3 D8
-        self._call("ms_band_flowdir_dev", self.h, _p(self.out["fnf"]), _p(self.out["flowdir"]), 1, st)
+        # K3 D8 (written by the no-flats finishing pass when the integer-raster solve ran)
+        if not self._flowdir_done:
+            self._call("ms_band_flowdir_dev", self.h, _p(self.out["fnf"]), _p(self.out["flowdir"]), 1, st)
         self._halo(self.ext["flowdir"])
         ship(("flowdir",))
         self._tick("flowdir")
@@ -372,9 +374,13 @@ class BandPipeline(object):
         return self
 
     def _noflats(self, st):
+        import os
         comm, dev, cols = self.comm, self.device, self.cols
         fnf = self.ext["fnf"]
         i64 = ctypes.c_int64
+        self._flowdir_done = False
+        if self.p2p and os.environ.get("MS_BAND_IR", "1") != "0" and self._noflats_ir(st):
+            return
         if self.p2p and self._noflats_p2p(st):
             return
         for cap in (1, 0):
@@ -417,6 +423,54 @@ class BandPipeline(object):
                 return
         raise RuntimeError("band no-flats fill: the fixed-point verification failed (seed repair is not available in "
                            "band mode)")
+
+    def _noflats_ir(self, st):
+        """The capped solve on the integer raster (the single-GPU solver k_nf_solve_ir), every band's kernel running
+        at once and exchanging edge rows and tile activations over NVLink peer memory; the finishing pass writes the
+        surface once, verifies it with the halo rows and writes the D8 codes on the way.  Every decision is taken on
+        values all ranks share (gathered / reduced), so the ranks stay in step; returns False when the raster does
+        not fit the integer form or the verification rejects the result (the W-based paths take over)."""
+        comm, dev, cols = self.comm, self.device, self.cols
+        i64, cint = ctypes.c_int64, ctypes.c_int
+        cap_bound = float(_lib.lib().ms_nf_cap_bound(self.R, self.cols, self.diag))
+        dem, filled = self.dem, self.out["filled"]
+        fix = torch.empty((2, cols), dtype=torch.uint8, device=dev)
+        self._call("ms_band_nf_ir_edgefix_dev", self.h, _p(dem), _p(filled), _p(fix[0]), _p(fix[1]), st)
+        halo_top, halo_bot = comm.exchange(fix[0], fix[1])
+        q, bad, err = i64(0), cint(0), 0
+        try:
+            self._call("ms_band_nf_ir_prepare_dev", self.h, _p(dem), _p(filled), self.short, self.diag, cap_bound,
+                       _p(halo_top), _p(halo_bot), ctypes.byref(q), ctypes.byref(bad), st)
+        except RuntimeError:
+            err = 1
+        self._tick("nf_init")
+        # one gather: also the barrier after which every band's edge rows are in its neighbours' mailboxes
+        allq = comm.all_gather(torch.tensor([q.value, bad.value + err], dtype=torch.int64, device=dev)).cpu()
+        if int(allq[:, 1].sum()) > 0:
+            return False
+        visits = i64(0)
+        if int(allq[:, 0].sum()) > 0:
+            self._call("ms_band_nf_p2p_arm_dev", self.h, st)
+            comm.all_reduce(torch.zeros(1, dtype=torch.int32, device=dev), "sum").cpu()           # barrier
+            try:
+                self._call("ms_band_nf_ir_solve_dev", self.h, _p(filled), self.short, self.diag, ctypes.byref(visits),
+                           ctypes.byref(bad), st)
+            except RuntimeError:
+                err = 1
+        self._tick("nf_p2p_solve")
+        nv = i64(0)
+        if not err and not bad.value:
+            self._call("ms_band_nf_ir_finish_dev", self.h, _p(dem), _p(filled), _p(self.out["fnf"]),
+                       _p(self.out["flowdir"]), self.short, self.diag, ctypes.byref(nv), st)
+        res = comm.all_reduce(torch.tensor([nv.value, bad.value + err], dtype=torch.int64, device=dev), "sum").cpu()
+        self._tick("nf_verify")
+        ok = int(res[0]) == 0 and int(res[1]) == 0
+        self.stats.update(noflat_exchanges=0, noflat_tile_visits=visits.value, noflat_capped=1, noflat_p2p=1,
+                          noflat_ir=1 if ok else 0, noflat_p2p_violations=int(res[0]),
+                          noflat_p2p_queued=allq[:, 0].tolist())
+        if ok:
+            self._flowdir_done = True
+        return ok
 
     def _noflats_p2p(self, st):
         """The capped solve with all bands' solver kernels running at once and exchanging over NVLink peer memory.

@@ -188,7 +188,8 @@ int forest_resolve(int *ptr, int64_t n, int64_t *rounds_out, cudaStream_t s);
 enum BandBuf {
     BB_LAB, BB_COMP, BB_E, BB_FROZEN, BB_FRANK, BB_HASHK, BB_HASHV,
     BB_ACC_X, BB_ACC_X0, BB_ACC_ENTRY_NEXT, BB_ACC_NEXT, BB_ACC_INDEG, BB_ACC_INDEG0, BB_ACC_ISEXIT, BB_ACC_LOC16,
-    BB_CC_PARENT, BB_CC_RANK, BB_WS_PTR, BB_NF_FLAG, BB_NF_SIDES, BB_NF_RING, BB_NF_CTL, BB_MISC, BB_COUNT
+    BB_CC_PARENT, BB_CC_RANK, BB_WS_PTR, BB_NF_FLAG, BB_NF_SIDES, BB_NF_RING, BB_NF_CTL, BB_MISC, BB_NF_DG, BB_NF_TMETA,
+    BB_NF_IRBAD, BB_COUNT
 };
 }  // namespace ms
 struct ms_band {

@@ -414,12 +414,12 @@ struct NfPeer {
     int *tileflag;     // the neighbour band's tile flag words
     int *ring;         // ... its FIFO
     NfCtl *ctl;
-    double *mail;      // ... its mailbox row facing this band
+    void *mail;        // ... its mailbox row facing this band (float64 surface row, or padded int32 distance row)
     int tiles_y, cap;
 };
 struct NfP2P {
     NfPeer up, down;                // null pointers where the band is not open
-    double *mail_top, *mail_bot;    // this band's own halo rows of the surface (written by the neighbours)
+    void *mail_top, *mail_bot;      // this band's own halo rows of the surface (written by the neighbours)
     int *gactive;                   // rank 0: bands with queued or running tiles
     int *done_all[NF_MAXRANKS];     // every rank's ctl->done
     int world;
@@ -468,8 +468,8 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
     const int rlo = (open & 1) ? -1 : 0, rhi = rows + ((open & 2) ? 1 : 0);
     const bool p2p = pp != nullptr;
     // halo rows of the surface: the ext rows of W, or (P2P) the mailboxes the neighbours write
-    const double *halo_top = p2p ? pp->mail_top : W - (long long)cols;
-    const double *halo_bot = p2p ? pp->mail_bot : W + (long long)rows * cols;
+    const double *halo_top = p2p ? (const double *)pp->mail_top : W - (long long)cols;
+    const double *halo_bot = p2p ? (const double *)pp->mail_bot : W + (long long)rows * cols;
     if (!p2p && *(volatile unsigned *)&ctl->tail == 0) return;      // nothing was queued (tail only grows)
 
     for (;;) {
@@ -706,10 +706,10 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                         __threadfence();
                         __syncthreads();
                         if (ty == 0 && pp->up.mail && (S.ring & 1) && tid < NF_T && c0 + tid < cols)
-                            pp->up.mail[c0 + tid] = __ldcg(W + c0 + tid);
+                            ((double *)pp->up.mail)[c0 + tid] = __ldcg(W + c0 + tid);
                         if (ty == tiles_y - 1 && pp->down.mail && (S.ring & 2) && tid >= NF_T && tid < 2 * NF_T &&
                             c0 + tid - NF_T < cols)
-                            pp->down.mail[c0 + tid - NF_T] = __ldcg(W + (long long)(rows - 1) * cols + c0 + tid - NF_T);
+                            ((double *)pp->down.mail)[c0 + tid - NF_T] = __ldcg(W + (long long)(rows - 1) * cols + c0 + tid - NF_T);
                         __threadfence_system();
                     }
                     __threadfence();
@@ -790,10 +790,10 @@ __global__ void __launch_bounds__(256, 4) k_nf_solve(const float *__restrict__ z
                     __threadfence();
                     __syncthreads();
                     if (ty == 0 && pp->up.mail && (S.ring & 1) && tid < NF_T && c0 + tid < cols)
-                        pp->up.mail[c0 + tid] = __ldcg(W + c0 + tid);
+                        ((double *)pp->up.mail)[c0 + tid] = __ldcg(W + c0 + tid);
                     if (ty == tiles_y - 1 && pp->down.mail && (S.ring & 2) && tid >= NF_T && tid < 2 * NF_T &&
                         c0 + tid - NF_T < cols)
-                        pp->down.mail[c0 + tid - NF_T] = __ldcg(W + (long long)(rows - 1) * cols + c0 + tid - NF_T);
+                        ((double *)pp->down.mail)[c0 + tid - NF_T] = __ldcg(W + (long long)(rows - 1) * cols + c0 + tid - NF_T);
                     __threadfence_system();
                 }
                 __threadfence();
@@ -873,7 +873,12 @@ constexpr int NI_A = NF_T + 4;          // tile + 2-cell apron
 __global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ z, const float *__restrict__ F,
                                                       double *__restrict__ W, int *tileflag, int *tilesides, NfCtl *ctl,
                                                       int rows, int cols, int tiles_x, double sh, double dg, double capB,
-                                                      int *__restrict__ Dg, int P, int *tmeta, int *irbad) {
+                                                      int *__restrict__ Dg, int P, int *tmeta, int *irbad, int open,
+                                                      const uint8_t *__restrict__ fix_top,
+                                                      const uint8_t *__restrict__ fix_bot) {
+    // Row band (open != 0): z and F have a halo row above / below the band where it is open; whether a cell of a
+    // halo row is fixed would need a second halo row, so the neighbour says (fix_top / fix_bot, k_band_edgefix).
+    const int rlo = (open & 1) ? -1 : 0, rhi = rows + ((open & 2) ? 1 : 0);
     __shared__ float sz[NI_A * NI_A], sf[NI_A * NI_A];
     __shared__ unsigned char fixedc[(NF_T + 2) * (NF_T + 2)];      // 1: W = z there for good (seed or raster border)
     __shared__ int s_sides, s_elo, s_ehi, s_bad;
@@ -884,17 +889,19 @@ __global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ 
     for (int k = tid; k < NI_A * NI_A; k += 256) {
         int lr = k / NI_A, lc = k - lr * NI_A;
         int r = r0 + lr - 2, c = c0 + lc - 2;
-        bool in = r >= 0 && r < rows && c >= 0 && c < cols;
-        sz[k] = in ? z[(size_t)r * cols + c] : INFINITY;
-        sf[k] = in ? F[(size_t)r * cols + c] : INFINITY;
+        bool in = r >= rlo && r < rhi && c >= 0 && c < cols;
+        sz[k] = in ? z[(long long)r * cols + c] : INFINITY;
+        sf[k] = in ? F[(long long)r * cols + c] : INFINITY;
     }
     __syncthreads();
     for (int k = tid; k < (NF_T + 2) * (NF_T + 2); k += 256) {
         int lr = k / (NF_T + 2), lc = k - lr * (NF_T + 2);          // ring coordinates: cell (r0 + lr - 1, c0 + lc - 1)
         int r = r0 + lr - 1, c = c0 + lc - 1;
         unsigned char fx = 0;
-        if (r >= 0 && r < rows && c >= 0 && c < cols) {
-            if (r == 0 || c == 0 || r == rows - 1 || c == cols - 1) fx = 1;
+        if (r >= rlo && r < rhi && c >= 0 && c < cols) {
+            if (r < 0) fx = fix_top[c];
+            else if (r >= rows) fx = fix_bot[c];
+            else if ((r == 0 && !(open & 1)) || c == 0 || (r == rows - 1 && !(open & 2)) || c == cols - 1) fx = 1;
             else {
                 const float *pf = sf + (lr + 1) * NI_A + (lc + 1);
                 float f = *pf;
@@ -904,7 +911,7 @@ __global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ 
             }
         }
         fixedc[k] = fx;
-        if (Dg && !fx && r >= 0 && r < rows && c >= 0 && c < cols) {
+        if (Dg && !fx && r >= rlo && r < rhi && c >= 0 && c < cols) {
             // a lake cell of the tile or its apron: its binade counts for the tile's weight table
             float f = sf[(lr + 1) * NI_A + (lc + 1)];
             if (f == 0.f) atomicOr(&s_bad, 1);
@@ -1051,7 +1058,7 @@ constexpr int IR_SMEM = (NF_T + 2) * IR_LD * 4 + NF_T * NF_T;
 #define IR_NT 128
 #endif
 #ifndef IR_CTAS
-#define IR_CTAS 8
+#define IR_CTAS 6
 #endif
 #ifndef IR_UNCOND
 #define IR_UNCOND 1
@@ -1197,13 +1204,21 @@ __device__ __forceinline__ void ir_sweep(int *sd, const unsigned char *se, IrSha
 __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__restrict__ F, int *Dg, int P, int *ring, int cap,
                                                         int *tileflag, const int *__restrict__ tilesides,
                                                         const int *__restrict__ tmeta, NfCtl *ctl, int *irbad, int rows,
-                                                        int cols, int tiles_x, int tiles_y, double sh, double dg) {
+                                                        int cols, int tiles_x, int tiles_y, double sh, double dg,
+                                                        const NfP2P *pp) {
+    // pp != nullptr: one band of a raster split across GPUs, every band's kernel running at the same time (see "row
+    // bands fused over NVLink peer memory" above).  The rows above / below the band are mailbox rows (padded like a row
+    // of Dg) the neighbours store their edge rows into; an edge tile whose edge row changed stores it into the
+    // neighbour's mailbox and queues the neighbour's tiles with system-scope atomics.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int *sd = reinterpret_cast<int *>(smem_raw);
     unsigned char *se = smem_raw + (NF_T + 2) * IR_LD * 4;
     __shared__ IrShared S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (*(volatile unsigned *)&ctl->tail == 0 || *(volatile int *)irbad) return;      // nothing queued / not for this form
+    const bool p2p = pp != nullptr;
+    if (!p2p && (*(volatile unsigned *)&ctl->tail == 0 || *(volatile int *)irbad)) return;      // nothing queued / not for this form
+    const int *mail_top = p2p ? (const int *)pp->mail_top : nullptr, *mail_bot = p2p ? (const int *)pp->mail_bot : nullptr;
+    const bool open_top = p2p && pp->up.tileflag, open_bot = p2p && pp->down.tileflag;
 
     for (;;) {
         // thread 32 takes the next tile while thread 0 still signs off the previous one
@@ -1219,12 +1234,16 @@ __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__r
                 __nanosleep(100);
                 // watchdog on the wall clock (never hang the GPU): generous, so that a profiler or a time-sliced GPU
                 // does not trip it
-                if ((spins & 1023u) == 1023u && nf_globaltimer() - t_start > NF_WATCHDOG_NS) { atomicExch(&ctl->done, 2); break; }
+                if ((spins & 1023u) == 1023u && nf_globaltimer() - t_start > NF_WATCHDOG_NS) {
+                    if (p2p) for (int k = 0; k < pp->world; k++) *(volatile int *)pp->done_all[k] = 2;      // every rank stops
+                    atomicExch(&ctl->done, 2);
+                    break;
+                }
             }
             if (t >= 0) {
                 *slot = -1;
                 __threadfence();
-                S.flags = atomicExch(tileflag + t, NF_RUNNING) & NF_SIDES;
+                S.flags = (p2p ? atomicExch_system(tileflag + t, NF_RUNNING) : atomicExch(tileflag + t, NF_RUNNING)) & NF_SIDES;
                 S.ring = 0;
                 S.nb = 0;
                 S.bad = 0;
@@ -1262,7 +1281,11 @@ __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__r
                     int q = q0 + j * IR_NT;
                     if (q < NCH) {
                         int lr = q / 18, ch = q - lr * 18;
-                        v[j] = __ldcg(reinterpret_cast<const int4 *>(src0 + (size_t)lr * P + ch * 4));
+                        const int *src = src0 + (size_t)lr * P + ch * 4;
+                        // the row above the first / below the last tile row of an open band: the neighbour's edge row
+                        if (lr == 0 && ty == 0 && open_top) src = mail_top + c0 + ch * 4;
+                        if (lr == NF_T + 1 && ty == tiles_y - 1 && open_bot) src = mail_bot + c0 + ch * 4;
+                        v[j] = __ldcg(reinterpret_cast<const int4 *>(src));
                     }
                 }
 #pragma unroll
@@ -1372,6 +1395,13 @@ __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__r
                     __stcg(drow + lane + 32, vb);
                     // a distance beyond what the integer form is trusted for: the float64 form takes over
                     if ((va >= D_LIMIT && va < D_INF) || (vb >= D_LIMIT && vb < D_INF)) S.bad = 1;
+                    // an edge row of the band also goes into the neighbour's mailbox (peer memory over NVLink)
+                    if (p2p) {
+                        int *peer = nullptr;
+                        if (lr == 0 && ty == 0 && open_top) peer = (int *)pp->up.mail;
+                        if (lr == NF_T - 1 && ty == tiles_y - 1 && open_bot) peer = (int *)pp->down.mail;
+                        if (peer) { peer[c0 + 4 + lane] = va; peer[c0 + 4 + lane + 32] = vb; }
+                    }
                 }
                 // ---- neighbours that can gain from the new edge cells: a lake cell of their side of the apron that
                 // lies above (edge cell + weight)
@@ -1404,16 +1434,28 @@ __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__r
                     nbm = __reduce_or_sync(0xffffffffu, nbm);
                     if (lane == 0 && nbm) atomicOr(&S.nb, nbm);
                 }
-                __threadfence();
+                if (p2p) __threadfence_system(); else __threadfence();
                 __syncthreads();
                 if (tid < 9 && tid != 4) {
                     const int dy = tid / 3 - 1, dx = tid % 3 - 1;
                     const int y = ty + dy, x = tx + dx;
-                    if ((S.nb & (1 << tid)) && x >= 0 && x < tiles_x && y >= 0 && y < tiles_y) {
+                    if ((S.nb & (1 << tid)) && x >= 0 && x < tiles_x) {
                         int bits = (dy < 0 ? 2 : 0) | (dy > 0 ? 1 : 0) | (dx < 0 ? 8 : 0) | (dx > 0 ? 4 : 0);
                         if (dy && dx) bits = dy < 0 ? 2 : 1;      // a corner: the row sweep from that side reads it
-                        int nb = y * tiles_x + x;
-                        if ((__ldg(tilesides + nb) & bits) && atomicOr(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb);
+                        if (y >= 0 && y < tiles_y) {
+                            int nb = y * tiles_x + x;
+                            if (__ldg(tilesides + nb) & bits) {
+                                if (p2p) { if (atomicOr_system(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb, true, pp->gactive); }
+                                else if (atomicOr(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb);
+                            }
+                        } else if (p2p) {
+                            // the tile lies in the neighbouring band: its flag word and FIFO are on another GPU
+                            const NfPeer &q = y < 0 ? pp->up : pp->down;
+                            if (q.tileflag) {
+                                int nbq = (y < 0 ? q.tiles_y - 1 : 0) * tiles_x + x;
+                                if (atomicOr_system(q.tileflag + nbq, bits) == 0) nf_push(q.ring, q.cap, q.ctl, nbq, true, pp->gactive);
+                            }
+                        }
                     }
                 }
             }
@@ -1433,11 +1475,52 @@ __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__r
         __syncthreads();
         if (tid == 0) {
             // side bits that arrived while the tile ran mean it has to run again
-            if (atomicAnd(tileflag + t, ~NF_RUNNING) & NF_SIDES) nf_push(ring, cap, ctl, t);
-            __threadfence();
-            if (atomicSub(&ctl->pending, 1) == 1) atomicExch(&ctl->done, 1);
+            if (p2p) {
+                if (atomicAnd_system(tileflag + t, ~NF_RUNNING) & NF_SIDES) nf_push(ring, cap, ctl, t, true, pp->gactive);
+                __threadfence_system();
+                // the band runs dry: one band less is active; the last one ends every rank's kernel
+                if (atomicSub_system(&ctl->pending, 1) == 1 && atomicSub_system(pp->gactive, 1) == 1)
+                    for (int k = 0; k < pp->world; k++) *(volatile int *)pp->done_all[k] = 1;
+            } else {
+                if (atomicAnd(tileflag + t, ~NF_RUNNING) & NF_SIDES) nf_push(ring, cap, ctl, t);
+                __threadfence();
+                if (atomicSub(&ctl->pending, 1) == 1) atomicExch(&ctl->done, 1);
+            }
         }
     }
+}
+
+// Row band: the fixed flags (seed or raster border: W = z for good) of the band's first and last own row, for the
+// neighbours' k_nf_init_tile.  blockIdx.y = 0: first row -> ftop, 1: last row -> fbot.
+__global__ void __launch_bounds__(256) k_band_edgefix(const float *__restrict__ z, const float *__restrict__ F,
+                                                      uint8_t *ftop, uint8_t *fbot, int rows, int cols, int open) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    int r = blockIdx.y ? rows - 1 : 0;
+    long long i = (long long)r * cols + c;
+    unsigned char fx;
+    if ((r == 0 && !(open & 1)) || c == 0 || (r == rows - 1 && !(open & 2)) || c == cols - 1) fx = 1;
+    else {
+        float f = F[i], m = INFINITY;
+#pragma unroll
+        for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+            for (int dc = -1; dc <= 1; dc++) {
+                if (dr == 0 && dc == 0) continue;
+                m = fminf(m, __ldg(F + i + (long long)dr * cols + dc));
+            }
+        fx = (f == z[i]) && (m < f);
+    }
+    (blockIdx.y ? fbot : ftop)[c] = fx;
+}
+
+// Row band: the band's first / last own row of the integer raster (whole padded rows) -> the neighbours' mailboxes
+__global__ void __launch_bounds__(256) k_band_ir_publish(const int *__restrict__ Dg, int P, int rows, const NfP2P *pp) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P) return;
+    int *peer = blockIdx.y ? (int *)pp->down.mail : (int *)pp->up.mail;
+    if (!peer) return;
+    peer[k] = Dg[(size_t)(blockIdx.y ? rows : 1) * P + k];
 }
 
 // End of the integer-raster solve: W is written once, and verified on the way.  A CTA rebuilds the float64 surface
@@ -1451,7 +1534,11 @@ __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__r
 __global__ void __launch_bounds__(256) k_nf_finish_ir(const float *__restrict__ z, const float *__restrict__ F,
                                                       const int *__restrict__ Dg, int P, double *__restrict__ W,
                                                       NfCtl *ctl, int rows, int cols, int tiles_x, double sh, double dg,
-                                                      uint8_t *__restrict__ flowdir, double inv_sqrt2) {
+                                                      uint8_t *__restrict__ flowdir, double inv_sqrt2, int open,
+                                                      const int *__restrict__ mail_top, const int *__restrict__ mail_bot) {
+    // Row band (open != 0): the rows above / below the band are the neighbours' edge rows - z and F from the halo rows
+    // of the band's rasters, the distances from the mailbox rows the neighbours wrote (padded like a row of Dg).
+    const int rlo = (open & 1) ? -1 : 0, rhi = rows + ((open & 2) ? 1 : 0);
     constexpr int LD = NF_T + 2;
     __shared__ double sW[LD * LD];
     const int tile = blockIdx.x, tid = threadIdx.x;
@@ -1469,9 +1556,9 @@ __global__ void __launch_bounds__(256) k_nf_finish_ir(const float *__restrict__ 
             int lr = k / LD, lc = k - lr * LD;
             int r = r0 + lr - 1, c = c0 + lc - 1;
             dv[j] = D_WALL; zv[j] = INFINITY; fv[j] = 0.f;
-            if (k < LD * LD && r >= 0 && r < rows && c >= 0 && c < cols) {
-                size_t i = (size_t)r * cols + c;
-                dv[j] = __ldg(Dg + (size_t)(r + 1) * P + (c + 4));
+            if (k < LD * LD && r >= rlo && r < rhi && c >= 0 && c < cols) {
+                long long i = (long long)r * cols + c;
+                dv[j] = r < 0 ? __ldg(mail_top + c + 4) : (r >= rows ? __ldg(mail_bot + c + 4) : __ldg(Dg + (size_t)(r + 1) * P + (c + 4)));
                 zv[j] = __ldg(z + i);
                 fv[j] = __ldg(F + i);
             }
@@ -1501,7 +1588,7 @@ __global__ void __launch_bounds__(256) k_nf_finish_ir(const float *__restrict__ 
         double w = *p;
         W[i] = w;
         int code = 8;
-        if (r > 0 && c > 0 && r < rows - 1 && c < cols - 1) {
+        if ((r > 0 || (open & 1)) && c > 0 && (r < rows - 1 || (open & 2)) && c < cols - 1) {
             double d4 = dmin2(p[-LD - 1], dmin2(p[-LD + 1], dmin2(p[LD - 1], p[LD + 1])));
             double e4 = dmin2(p[-LD], dmin2(p[-1], dmin2(p[1], p[LD])));
             double m = dmin2(__dadd_rn(d4, dg), __dadd_rn(e4, sh));
@@ -1510,7 +1597,7 @@ __global__ void __launch_bounds__(256) k_nf_finish_ir(const float *__restrict__ 
             if (g != w) bad = 1;
             if (flowdir) code = d8_code(w, p[-LD], p[-LD + 1], p[1], p[LD + 1], p[LD], p[LD - 1], p[-1], p[-LD - 1], inv_sqrt2);
         }
-        if (flowdir) flowdir[i] = (uint8_t)d8_border(code, r == 0, r == rows - 1, c, cols);
+        if (flowdir) flowdir[i] = (uint8_t)d8_border(code, r == 0 && !(open & 1), r == rows - 1 && !(open & 2), c, cols);
     }
     int cnt = __syncthreads_count(bad);
     if (tid == 0 && cnt) atomicAdd(&ctl->nviol, cnt);
@@ -1568,7 +1655,7 @@ int g_nf_ir = 1;           // MS_NF_IR=0 keeps the W-based solver (k_nf_solve) o
 
 static int nf_launch_solve_ir(const float *F, int *Dg, int P, int *ring, int cap, int *tileflag, const int *tilesides,
                               const int *tmeta, NfCtl *ctl, int *irbad, int rows, int cols, int tiles_x, int tiles_y,
-                              int ntiles, double sh, double dg, int64_t units, cudaStream_t s) {
+                              int ntiles, double sh, double dg, int64_t units, cudaStream_t s, const NfP2P *pp = nullptr) {
     static int grid_blocks = 0;
     if (!grid_blocks) {
         MS_CUDA(cudaFuncSetAttribute(k_nf_solve_ir, cudaFuncAttributeMaxDynamicSharedMemorySize, IR_SMEM));
@@ -1581,8 +1668,8 @@ static int nf_launch_solve_ir(const float *F, int *Dg, int P, int *ring, int cap
     }
     void *args[] = {(void *)&F, (void *)&Dg, (void *)&P, (void *)&ring, (void *)&cap, (void *)&tileflag,
                     (void *)&tilesides, (void *)&tmeta, (void *)&ctl, (void *)&irbad, (void *)&rows, (void *)&cols,
-                    (void *)&tiles_x, (void *)&tiles_y, (void *)&sh, (void *)&dg};
-    int g = grid_blocks < ntiles ? grid_blocks : ntiles;
+                    (void *)&tiles_x, (void *)&tiles_y, (void *)&sh, (void *)&dg, (void *)&pp};
+    int g = (grid_blocks < ntiles || pp) ? grid_blocks : ntiles;
     prof_units(units);
     if (g_prof) prof_begin("k_nf_solve_ir", s);
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_nf_solve_ir, dim3(g), dim3(IR_NT), args, IR_SMEM, s);
@@ -1661,7 +1748,8 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
         }
         if (cap)
             MS_LAUNCH(k_nf_init_tile, ntiles, 256, 0, s, dtm, filled, out, tileflag.p, tilesides.p, ctl.p, (int)rows,
-                      (int)cols, tiles_x, sh, dg, cap_bound, ir ? Dg.p : (int *)nullptr, P, tmeta.p, irbad.p);
+                      (int)cols, tiles_x, sh, dg, cap_bound, ir ? Dg.p : (int *)nullptr, P, tmeta.p, irbad.p, 0,
+                      (const uint8_t *)nullptr, (const uint8_t *)nullptr);
         else
             MS_LAUNCH(k_nf_init, g2, 256, 0, s, dtm, filled, out, banned.p, tileflag.p, tilesides.p, ctl.p, (int)rows,
                       (int)cols, tiles_x, 0);
@@ -1671,7 +1759,7 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
                                       (int)rows, (int)cols, tiles_x, tiles_y, ntiles, sh, dg, n, s));
             prof_units(n);
             MS_LAUNCH(k_nf_finish_ir, ntiles, 256, 0, s, dtm, filled, Dg.p, P, out, ctl.p, (int)rows, (int)cols, tiles_x, sh,
-                      dg, flowdir_out, 1.0 / pow(2.0, 0.5));      // _flow.pyx:93-94: INV_SQRT2 = 1 / 2**0.5
+                      dg, flowdir_out, 1.0 / pow(2.0, 0.5), 0, (const int *)nullptr, (const int *)nullptr);      // _flow.pyx:93-94: INV_SQRT2 = 1 / 2**0.5
         } else if (cap) {
             MS_TRY(nf_launch_solve<true>(filled, out, ring.p, cap_ring, tileflag.p, tilesides.p, ctl.p, (int)rows, (int)cols, tiles_x,
                                          tiles_y, ntiles, sh, dg, g_nf_use_int, cap_bound, 0, n, s));
@@ -1842,8 +1930,11 @@ static NfSharedLayout nf_layout(int64_t rows, int64_t cols) {
     L.off_flag = take((size_t)L.ntiles * sizeof(int));
     L.off_sides = take((size_t)L.ntiles * sizeof(int));
     L.off_ring = take((size_t)L.cap * sizeof(int));
-    L.off_mtop = take((size_t)cols * sizeof(double));
-    L.off_mbot = take((size_t)cols * sizeof(double));
+    // a mailbox row holds cols float64 (W-based solver) or the padded int32 row of the integer raster
+    size_t mail = (size_t)cols * sizeof(double), mail_ir = ((size_t)L.tiles_x * NF_T + 8) * sizeof(int);
+    if (mail_ir > mail) mail = mail_ir;
+    L.off_mtop = take(mail);
+    L.off_mbot = take(mail);
     L.total = o;
     return L;
 }
@@ -1917,8 +2008,8 @@ int ms_band_nf_shared_open(ms_band *B, int rank, int world, const void *infos, c
     NfP2P pp;
     memset(&pp, 0, sizeof(pp));
     NfSharedLayout me = nf_layout(B->rows, B->cols);
-    pp.mail_top = (double *)((char *)B->nf_shared + me.off_mtop);
-    pp.mail_bot = (double *)((char *)B->nf_shared + me.off_mbot);
+    pp.mail_top = (void *)((char *)B->nf_shared + me.off_mtop);
+    pp.mail_bot = (void *)((char *)B->nf_shared + me.off_mbot);
     pp.world = world;
     pp.gactive = (int *)((char *)B->nf_peer[0] + nf_layout(rows_all[0], B->cols).off_gactive);
     for (int k = 0; k < world; k++) pp.done_all[k] = &((NfCtl *)B->nf_peer[k])->done;
@@ -1931,7 +2022,7 @@ int ms_band_nf_shared_open(ms_band *B, int rank, int world, const void *infos, c
         q.tileflag = (int *)(base + L.off_flag);
         q.ring = (int *)(base + L.off_ring);
         q.ctl = (NfCtl *)base;
-        q.mail = (double *)(base + (side ? L.off_mtop : L.off_mbot));      // the row of theirs that faces this band
+        q.mail = (void *)(base + (side ? L.off_mtop : L.off_mbot));      // the row of theirs that faces this band
         q.tiles_y = L.tiles_y;
         q.cap = L.cap;
         if (side) pp.down = q; else pp.up = q;
@@ -2014,6 +2105,124 @@ int ms_band_nf_p2p_solve_dev(ms_band *B, const float *filled, double *fnf, doubl
         return MS_ERR_NOCONV;
     }
     if (tile_visits) *tile_visits = h->visits;
+    return MS_OK;
+}
+
+/* ---- integer-raster form of the P2P solve (the single-GPU solver k_nf_solve_ir across bands) -------------------
+ * 1. ms_band_nf_ir_edgefix_dev: fixed flags of the band's first / last own row; the caller hands them to the
+ *    neighbours (they are the flags of the neighbours' halo rows).
+ * 2. ms_band_nf_ir_prepare_dev: padded int32 raster of the band (k_nf_init_tile with the halo rows), the band's edge
+ *    rows stored into the neighbours' mailboxes, FIFO := tiles with lake cells.  *queued = tiles queued, *irbad = the
+ *    band does not fit the integer form.  The caller synchronises all ranks, then ms_band_nf_p2p_arm_dev, synchronises
+ *    again, then
+ * 3. ms_band_nf_ir_solve_dev: every band's k_nf_solve_ir at once; ends when no band has work left.
+ * 4. ms_band_nf_ir_finish_dev: W = F + D ulp(F) written once, verified against the fixed-point equation with the
+ *    halo rows (*nviol), D8 codes of the band's rows written on the way (K3 fused, edges of the RASTER flow outward). */
+int ms_band_nf_ir_edgefix_dev(ms_band *B, const float *dem, const float *filled, uint8_t *fix_top, uint8_t *fix_bot,
+                              void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !dem || !filled || !fix_top || !fix_bot) { set_error("band no-flats: null pointer"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    MS_LAUNCH(k_band_edgefix, dim3(cdiv(B->cols, 256), 2), 256, 0, s, dem, filled, fix_top, fix_bot, (int)B->rows,
+              (int)B->cols, B->open);
+    return MS_OK;
+}
+
+int ms_band_nf_ir_prepare_dev(ms_band *B, const float *dem, const float *filled, double short_eps, double diag_eps,
+                              double cap_bound, const uint8_t *fix_top, const uint8_t *fix_bot, int64_t *queued,
+                              int *irbad_out, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !B->nf_pp_dev || !dem || !filled || !queued || !irbad_out) {
+        set_error("band no-flats P2P: not set up");
+        return MS_ERR_ARG;
+    }
+    if (((B->open & 1) && !fix_top) || ((B->open & 2) && !fix_bot)) { set_error("band no-flats: halo flags missing"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NfBandBufs nb;
+    MS_TRY(nf_band_bufs(B, &nb));
+    const int P = nb.tiles_x * NF_T + 8;
+    const int inner_rows = nb.tiles_y * NF_T;
+    int *Dg = (int *)band_buf(B, BB_NF_DG, (size_t)P * ((size_t)inner_rows + 2) * sizeof(int));
+    int *tmeta = (int *)band_buf(B, BB_NF_TMETA, (size_t)nb.ntiles * sizeof(int));
+    int *irbad = (int *)band_buf(B, BB_NF_IRBAD, sizeof(int));
+    if (!Dg || !tmeta || !irbad) return MS_ERR_CUDA;
+    NfSharedLayout L = nf_layout(B->rows, B->cols);
+    char *base = (char *)B->nf_shared;
+    MS_CUDA(cudaMemsetAsync(nb.tileflag, 0, (size_t)nb.ntiles * sizeof(int), s));
+    MS_CUDA(cudaMemsetAsync(nb.tilesides, 0, (size_t)nb.ntiles * sizeof(int), s));
+    MS_CUDA(cudaMemsetAsync(nb.ring, 0xff, (size_t)nb.cap_ring * sizeof(int), s));
+    MS_CUDA(cudaMemsetAsync(nb.ctl, 0, sizeof(NfCtl), s));
+    MS_CUDA(cudaMemsetAsync(irbad, 0, sizeof(int), s));
+    if (B->nf_rank == 0) MS_CUDA(cudaMemsetAsync(base + L.off_gactive, 0, sizeof(int), s));
+    MS_LAUNCH(k_ir_frame, cdiv(2 * (int64_t)P + 8 * (int64_t)inner_rows, 256), 256, 0, s, Dg, P, inner_rows);
+    prof_units(B->rows * B->cols);
+    MS_LAUNCH(k_nf_init_tile, nb.ntiles, 256, 0, s, dem, filled, (double *)nullptr, nb.tileflag, nb.tilesides, nb.ctl,
+              (int)B->rows, (int)B->cols, nb.tiles_x, short_eps, diag_eps, cap_bound, Dg, P, tmeta, irbad, B->open, fix_top,
+              fix_bot);
+    MS_LAUNCH(k_band_ir_publish, dim3(cdiv(P, 256), 2), 256, 0, s, Dg, P, (int)B->rows, (const NfP2P *)B->nf_pp_dev);
+    MS_LAUNCH(k_nf_compact, cdiv(nb.ntiles, 256), 256, 0, s, nb.tileflag, nb.ring, nb.ctl, nb.ntiles);
+    NfCtl *h = (NfCtl *)(host_flags().h + 32);
+    int *h_irbad = (int *)(h + 1);
+    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaMemcpyAsync(h_irbad, irbad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    *queued = h->pending;
+    *irbad_out = *h_irbad;
+    return MS_OK;
+}
+
+int ms_band_nf_ir_solve_dev(ms_band *B, const float *filled, double short_eps, double diag_eps, int64_t *tile_visits,
+                            int *irbad_out, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !B->nf_pp_dev || !filled || !irbad_out) { set_error("band no-flats P2P: not set up"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NfBandBufs nb;
+    MS_TRY(nf_band_bufs(B, &nb));
+    const int P = nb.tiles_x * NF_T + 8;
+    int *Dg = (int *)B->buf[BB_NF_DG], *tmeta = (int *)B->buf[BB_NF_TMETA], *irbad = (int *)B->buf[BB_NF_IRBAD];
+    if (!Dg || !tmeta || !irbad) { set_error("band no-flats P2P: ms_band_nf_ir_prepare_dev first"); return MS_ERR_ARG; }
+    MS_TRY(nf_launch_solve_ir(filled, Dg, P, nb.ring, nb.cap_ring, nb.tileflag, nb.tilesides, tmeta, nb.ctl, irbad,
+                              (int)B->rows, (int)B->cols, nb.tiles_x, nb.tiles_y, nb.ntiles, short_eps, diag_eps,
+                              B->rows * B->cols, s, (const NfP2P *)B->nf_pp_dev));
+    NfCtl *h = (NfCtl *)(host_flags().h + 32);
+    int *h_irbad = (int *)(h + 1);
+    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaMemcpyAsync(h_irbad, irbad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    if (tile_visits) *tile_visits = h->visits;
+    *irbad_out = *h_irbad;
+    if (h->done != 1) {
+        set_error("band no-flats P2P: solver stopped early (done=%d, pending=%d)", h->done, h->pending);
+        return MS_ERR_NOCONV;
+    }
+    return MS_OK;
+}
+
+int ms_band_nf_ir_finish_dev(ms_band *B, const float *dem, const float *filled, double *fnf, uint8_t *flowdir,
+                             double short_eps, double diag_eps, int64_t *nviol, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !B->nf_pp_dev || !dem || !filled || !fnf || !nviol) { set_error("band no-flats P2P: null pointer"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NfBandBufs nb;
+    MS_TRY(nf_band_bufs(B, &nb));
+    const int P = nb.tiles_x * NF_T + 8;
+    int *Dg = (int *)B->buf[BB_NF_DG];
+    if (!Dg) { set_error("band no-flats P2P: ms_band_nf_ir_prepare_dev first"); return MS_ERR_ARG; }
+    NfSharedLayout L = nf_layout(B->rows, B->cols);
+    char *base = (char *)B->nf_shared;
+    MS_CUDA(cudaMemsetAsync(&nb.ctl->nviol, 0, sizeof(int), s));
+    prof_units(B->rows * B->cols);
+    MS_LAUNCH(k_nf_finish_ir, nb.ntiles, 256, 0, s, dem, filled, Dg, P, fnf, nb.ctl, (int)B->rows, (int)B->cols, nb.tiles_x,
+              short_eps, diag_eps, flowdir, 1.0 / pow(2.0, 0.5), B->open, (const int *)(base + L.off_mtop),
+              (const int *)(base + L.off_mbot));
+    NfCtl *h = (NfCtl *)(host_flags().h + 32);
+    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    *nviol = h->nviol;
     return MS_OK;
 }
 

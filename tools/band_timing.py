@@ -23,4 +23,19 @@ if rank == 0:
     for k, v in p.timing.items():
         print("%-12s %7.2f ms" % (k, v / reps)); tot += v / reps
     print("total        %7.2f ms" % tot, p.stats)
+# the same run without the per-stage synchronisations: wall clock per step
+import time
+os.environ["MS_BAND_TIMING"] = "0"
+torch.cuda.synchronize(); dist.barrier()
+for mode in ("plain", "profiled"):
+    from malstroem_b200 import _lib
+    if mode == "profiled":
+        _lib.lib().ms_profile(20000)
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    for _ in range(3):
+        p.run()
+    torch.cuda.synchronize(); dist.barrier(); dt = (time.perf_counter() - t0) / 3
+    _lib.lib().ms_profile(0)
+    if rank == 0:
+        print("%s: %.2f ms per step without per-stage synchronisation" % (mode, dt * 1e3))
 dist.destroy_process_group()
