@@ -426,14 +426,17 @@ struct NfP2P {
 };
 
 // queue `tile` on the FIFO (ring, ctl); with `sys` the FIFO may be another GPU's (or be fed by another GPU)
-__device__ inline void nf_push(int *ring, int cap, NfCtl *ctl, int tile, bool sys = false, int *gactive = nullptr) {
+// (`remote`: the FIFO lives on another GPU - the entry is pushed out with a system-scope fence; a FIFO of this GPU that
+// other GPUs also feed only needs the system-scope atomics)
+__device__ inline void nf_push(int *ring, int cap, NfCtl *ctl, int tile, bool sys = false, int *gactive = nullptr,
+                               bool remote = true) {
     if (sys) {
         if (atomicAdd_system(&ctl->pending, 1) == 0) atomicAdd_system(gactive, 1);      // the band wakes up
         unsigned idx = atomicAdd_system(&ctl->tail, 1u);
         volatile int *slot = ring + (idx % (unsigned)cap);
         for (unsigned spins = 0; *slot != -1 && spins < (1u << 23); spins++) __nanosleep(100);
         *slot = tile;
-        __threadfence_system();
+        if (remote) __threadfence_system();
         return;
     }
     atomicAdd(&ctl->pending, 1);
@@ -1063,6 +1066,9 @@ constexpr int IR_SMEM = (NF_T + 2) * IR_LD * 4 + NF_T * NF_T;
 #ifndef IR_UNCOND
 #define IR_UNCOND 1
 #endif
+#ifndef IR_MIDFLUSH
+#define IR_MIDFLUSH 1
+#endif
 
 // the wall frame of the padded raster: row 0, the rows below the tiles, and 4 columns either side of every tile row
 // (k_nf_init_tile writes everything inside, including the cells of edge tiles that lie beyond the raster)
@@ -1091,6 +1097,7 @@ struct IrShared {
     unsigned long long rows, cols;         // ... during the whole visit (write-back, edges for the neighbours)
     int ring;          // bit 0/1/2/3: the tile's top / bottom / left / right edge changed
     int nb;            // neighbour tiles to queue: bit (dy+1)*3 + (dx+1)
+    int mid;           // tail of the solve: forward the edges after the first round already
     int2 wtab[NF_NBIN];
 };
 
@@ -1201,6 +1208,7 @@ __device__ __forceinline__ void ir_sweep(int *sd, const unsigned char *se, IrSha
     }
 }
 
+template <bool P2P>
 __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__restrict__ F, int *Dg, int P, int *ring, int cap,
                                                         int *tileflag, const int *__restrict__ tilesides,
                                                         const int *__restrict__ tmeta, NfCtl *ctl, int *irbad, int rows,
@@ -1215,7 +1223,7 @@ __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__r
     unsigned char *se = smem_raw + (NF_T + 2) * IR_LD * 4;
     __shared__ IrShared S;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool p2p = pp != nullptr;
+    constexpr bool p2p = P2P;       // compiled twice: the single-GPU form carries none of the peer code
     if (!p2p && (*(volatile unsigned *)&ctl->tail == 0 || *(volatile int *)irbad)) return;      // nothing queued / not for this form
     const int *mail_top = p2p ? (const int *)pp->mail_top : nullptr, *mail_bot = p2p ? (const int *)pp->mail_bot : nullptr;
     const bool open_top = p2p && pp->up.tileflag, open_bot = p2p && pp->down.tileflag;
@@ -1255,6 +1263,7 @@ __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__r
                 S.elo = (int)(short)(meta & 0xffff);
                 S.e = S.elo + ((meta >> 16) & 15);
                 S.has = (meta >> 20) & 1;
+                S.mid = IR_MIDFLUSH && *(volatile int *)&ctl->pending < (int)(gridDim.x >> 2);
                 atomicAdd(&ctl->visits, 1);
             }
             S.k = t;
@@ -1330,6 +1339,97 @@ __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__r
 #ifdef NF_STATS
             tg1 = tg2 = gtimer();
 #endif
+            // Write-back + neighbour activation: the rows that changed since the last flush go back to the raster, the
+            // neighbours that can gain from the changed edges are queued.  Called by all threads, at the end of the visit
+            // and - while the solve is in its tail (few tiles queued or running: the time is a chain of visits along
+            // the biggest lakes) - once after the first round, which carries the wave across the tile: the next tile of
+            // the chain starts while this one is still checking itself.
+            auto flush = [&]() {
+            // ---- the rows that changed go back (two coalesced 128-byte stores per row)
+            unsigned long long mm = S.rows;
+            const int ringbits = ((mm & 1ull) ? 1 : 0) | ((mm >> 63) ? 2 : 0) | ((S.cols & 1ull) ? 4 : 0) | ((S.cols >> 63) ? 8 : 0);
+            for (int idx = 0; mm; idx++) {
+                int lr = __ffsll((long long)mm) - 1;
+                mm &= mm - 1;
+                if ((idx & (IR_NT / 32 - 1)) != warp) continue;
+                const int *srow = sd + (lr + 1) * IR_LD + 1;
+                int *drow = Dg + (size_t)(r0 + lr + 1) * P + (c0 + 4);
+                const int va = srow[lane], vb = srow[lane + 32];
+                __stcg(drow + lane, va);
+                __stcg(drow + lane + 32, vb);
+                // a distance beyond what the integer form is trusted for: the float64 form takes over
+                if ((va >= D_LIMIT && va < D_INF) || (vb >= D_LIMIT && vb < D_INF)) S.bad = 1;
+                // an edge row of the band also goes into the neighbour's mailbox (peer memory over NVLink)
+                if (p2p) {
+                    int *peer = nullptr;
+                    if (lr == 0 && ty == 0 && open_top) peer = (int *)pp->up.mail;
+                    if (lr == NF_T - 1 && ty == tiles_y - 1 && open_bot) peer = (int *)pp->down.mail;
+                    if (peer) { peer[c0 + 4 + lane] = va; peer[c0 + 4 + lane + 32] = vb; }
+                }
+            }
+            // ---- neighbours that can gain from the new edge cells: a lake cell of their side of the apron that
+            // lies above (edge cell + weight)
+            const bool uni2 = uni;
+            for (int sidx = tid; sidx < 4 * NF_T; sidx += IR_NT) {
+                const int side = sidx >> 6, k = sidx & 63;      // 0 top, 1 bottom, 2 left, 3 right (warp-uniform)
+                int nbm = 0;
+                if (ringbits & (1 << side)) {
+                    int lr = side == 0 ? 0 : (side == 1 ? NF_T - 1 : k);
+                    int lc = side == 2 ? 0 : (side == 3 ? NF_T - 1 : k);
+                    int d = sd[(lr + 1) * IR_LD + (lc + 1)];
+                    if (d < D_INF) {
+#pragma unroll
+                        for (int o = -1; o <= 1; o++) {
+                            int ar = side == 0 ? -1 : (side == 1 ? NF_T : lr + o);
+                            int ac = side == 2 ? -1 : (side == 3 ? NF_T : lc + o);
+                            int da = sd[(ar + 1) * IR_LD + (ac + 1)];
+                            if (da <= D_INF) {
+                                // the weight is the TARGET cell's (adjacent lake cells share their binade)
+                                int2 wt = uni2 ? S.wtab[0] : S.wtab[(se[lr * NF_T + lc] - (S.elo & 0xff)) & (NF_NBIN - 1)];
+                                int w = (o == 0) ? wt.x : wt.y;
+                                if (d + w < da) {
+                                    int dy = ar < 0 ? -1 : (ar >= NF_T ? 1 : 0), dx = ac < 0 ? -1 : (ac >= NF_T ? 1 : 0);
+                                    nbm |= 1 << ((dy + 1) * 3 + (dx + 1));
+                                }
+                            }
+                        }
+                    }
+                }
+                nbm = __reduce_or_sync(0xffffffffu, nbm);
+                if (lane == 0 && nbm) atomicOr(&S.nb, nbm);
+            }
+            // order the tile's stores before the flags / FIFO entries that announce them.  Only a tile on an open
+            // band edge has stored into (or will queue a tile of) another GPU: everything else stays on this GPU,
+            // where the device-scope fence is enough (a system-scope fence per visit cost 3x in the banded solve)
+            const bool peer_touch = p2p && ((ty == 0 && open_top) || (ty == tiles_y - 1 && open_bot));
+            if (peer_touch) __threadfence_system(); else __threadfence();
+            __syncthreads();
+            if (tid < 9 && tid != 4) {
+                const int dy = tid / 3 - 1, dx = tid % 3 - 1;
+                const int y = ty + dy, x = tx + dx;
+                if ((S.nb & (1 << tid)) && x >= 0 && x < tiles_x) {
+                    int bits = (dy < 0 ? 2 : 0) | (dy > 0 ? 1 : 0) | (dx < 0 ? 8 : 0) | (dx > 0 ? 4 : 0);
+                    if (dy && dx) bits = dy < 0 ? 2 : 1;      // a corner: the row sweep from that side reads it
+                    if (y >= 0 && y < tiles_y) {
+                        int nb = y * tiles_x + x;
+                        if (__ldg(tilesides + nb) & bits) {
+                            if (p2p) { if (atomicOr_system(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb, true, pp->gactive, false); }
+                            else if (atomicOr(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb);
+                        }
+                    } else if (p2p) {
+                        // the tile lies in the neighbouring band: its flag word and FIFO are on another GPU
+                        const NfPeer &q = y < 0 ? pp->up : pp->down;
+                        if (q.tileflag) {
+                            int nbq = (y < 0 ? q.tiles_y - 1 : 0) * tiles_x + x;
+                            if (atomicOr_system(q.tileflag + nbq, bits) == 0) nf_push(q.ring, q.cap, q.ctl, nbq, true, pp->gactive);
+                        }
+                    }
+                }
+            }
+                __syncthreads();
+                if (tid == 0) { S.rows = 0; S.cols = 0; S.nb = 0; }
+                __syncthreads();
+            };
             if (!S.bad && fin) {
                 // round 0: everything (first visit), or the one direction that reads the apron side that changed
                 int dirs = (S.flags & 16) ? 15 : (S.flags & 15);
@@ -1377,93 +1477,23 @@ __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__r
                         break;
                     }
                     dirs = (cd & (cd - 1)) ? 15 : (15 & ~cd);
+                    if (rnd == 0 && S.mid) {
+                        __syncthreads();           // S.rows / S.cols of round 0 are in place
+                        if (S.rows) flush();
+                    }
                 }
                 __syncthreads();
             }
-            if (!S.bad && S.rows) {
-                // ---- the rows that changed go back (two coalesced 128-byte stores per row)
-                unsigned long long mm = S.rows;
-                const int ringbits = ((mm & 1ull) ? 1 : 0) | ((mm >> 63) ? 2 : 0) | ((S.cols & 1ull) ? 4 : 0) | ((S.cols >> 63) ? 8 : 0);
-                for (int idx = 0; mm; idx++) {
-                    int lr = __ffsll((long long)mm) - 1;
-                    mm &= mm - 1;
-                    if ((idx & (IR_NT / 32 - 1)) != warp) continue;
-                    const int *srow = sd + (lr + 1) * IR_LD + 1;
-                    int *drow = Dg + (size_t)(r0 + lr + 1) * P + (c0 + 4);
-                    const int va = srow[lane], vb = srow[lane + 32];
-                    __stcg(drow + lane, va);
-                    __stcg(drow + lane + 32, vb);
-                    // a distance beyond what the integer form is trusted for: the float64 form takes over
-                    if ((va >= D_LIMIT && va < D_INF) || (vb >= D_LIMIT && vb < D_INF)) S.bad = 1;
-                    // an edge row of the band also goes into the neighbour's mailbox (peer memory over NVLink)
-                    if (p2p) {
-                        int *peer = nullptr;
-                        if (lr == 0 && ty == 0 && open_top) peer = (int *)pp->up.mail;
-                        if (lr == NF_T - 1 && ty == tiles_y - 1 && open_bot) peer = (int *)pp->down.mail;
-                        if (peer) { peer[c0 + 4 + lane] = va; peer[c0 + 4 + lane + 32] = vb; }
-                    }
-                }
-                // ---- neighbours that can gain from the new edge cells: a lake cell of their side of the apron that
-                // lies above (edge cell + weight)
-                const bool uni2 = uni;
-                for (int sidx = tid; sidx < 4 * NF_T; sidx += IR_NT) {
-                    const int side = sidx >> 6, k = sidx & 63;      // 0 top, 1 bottom, 2 left, 3 right (warp-uniform)
-                    int nbm = 0;
-                    if (ringbits & (1 << side)) {
-                        int lr = side == 0 ? 0 : (side == 1 ? NF_T - 1 : k);
-                        int lc = side == 2 ? 0 : (side == 3 ? NF_T - 1 : k);
-                        int d = sd[(lr + 1) * IR_LD + (lc + 1)];
-                        if (d < D_INF) {
-#pragma unroll
-                            for (int o = -1; o <= 1; o++) {
-                                int ar = side == 0 ? -1 : (side == 1 ? NF_T : lr + o);
-                                int ac = side == 2 ? -1 : (side == 3 ? NF_T : lc + o);
-                                int da = sd[(ar + 1) * IR_LD + (ac + 1)];
-                                if (da <= D_INF) {
-                                    // the weight is the TARGET cell's (adjacent lake cells share their binade)
-                                    int2 wt = uni2 ? S.wtab[0] : S.wtab[(se[lr * NF_T + lc] - (S.elo & 0xff)) & (NF_NBIN - 1)];
-                                    int w = (o == 0) ? wt.x : wt.y;
-                                    if (d + w < da) {
-                                        int dy = ar < 0 ? -1 : (ar >= NF_T ? 1 : 0), dx = ac < 0 ? -1 : (ac >= NF_T ? 1 : 0);
-                                        nbm |= 1 << ((dy + 1) * 3 + (dx + 1));
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    nbm = __reduce_or_sync(0xffffffffu, nbm);
-                    if (lane == 0 && nbm) atomicOr(&S.nb, nbm);
-                }
-                if (p2p) __threadfence_system(); else __threadfence();
-                __syncthreads();
-                if (tid < 9 && tid != 4) {
-                    const int dy = tid / 3 - 1, dx = tid % 3 - 1;
-                    const int y = ty + dy, x = tx + dx;
-                    if ((S.nb & (1 << tid)) && x >= 0 && x < tiles_x) {
-                        int bits = (dy < 0 ? 2 : 0) | (dy > 0 ? 1 : 0) | (dx < 0 ? 8 : 0) | (dx > 0 ? 4 : 0);
-                        if (dy && dx) bits = dy < 0 ? 2 : 1;      // a corner: the row sweep from that side reads it
-                        if (y >= 0 && y < tiles_y) {
-                            int nb = y * tiles_x + x;
-                            if (__ldg(tilesides + nb) & bits) {
-                                if (p2p) { if (atomicOr_system(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb, true, pp->gactive); }
-                                else if (atomicOr(tileflag + nb, bits) == 0) nf_push(ring, cap, ctl, nb);
-                            }
-                        } else if (p2p) {
-                            // the tile lies in the neighbouring band: its flag word and FIFO are on another GPU
-                            const NfPeer &q = y < 0 ? pp->up : pp->down;
-                            if (q.tileflag) {
-                                int nbq = (y < 0 ? q.tiles_y - 1 : 0) * tiles_x + x;
-                                if (atomicOr_system(q.tileflag + nbq, bits) == 0) nf_push(q.ring, q.cap, q.ctl, nbq, true, pp->gactive);
-                            }
-                        }
-                    }
-                }
-            }
+            if (!S.bad && S.rows) flush();
             __syncthreads();
             if (S.bad && tid == 0) atomicExch(irbad, 1);
         }
 #ifdef NF_STATS
+#ifdef NF_STATS_TAIL
+        if (tid == 0 && S.mid) {        // only the visits of the tail (a raster with more visits than log entries)
+#else
         if (tid == 0) {
+#endif
             unsigned k = atomicAdd(&g_nf_nlog, 1u);
             if (k < 262144u) {
                 unsigned long long rel = tg2 - tg1; if (rel > 0xffffffull) rel = 0xffffffull;
@@ -1476,11 +1506,15 @@ __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__r
         if (tid == 0) {
             // side bits that arrived while the tile ran mean it has to run again
             if (p2p) {
-                if (atomicAnd_system(tileflag + t, ~NF_RUNNING) & NF_SIDES) nf_push(ring, cap, ctl, t, true, pp->gactive);
-                __threadfence_system();
-                // the band runs dry: one band less is active; the last one ends every rank's kernel
-                if (atomicSub_system(&ctl->pending, 1) == 1 && atomicSub_system(pp->gactive, 1) == 1)
-                    for (int k = 0; k < pp->world; k++) *(volatile int *)pp->done_all[k] = 1;
+                if (atomicAnd_system(tileflag + t, ~NF_RUNNING) & NF_SIDES) nf_push(ring, cap, ctl, t, true, pp->gactive, false);
+                // the band runs dry: one band less is active; the last one ends every rank's kernel (system-scope fence:
+                // this is the point at which another GPU may conclude that everything this band wrote is in place)
+                __threadfence();
+                if (atomicSub_system(&ctl->pending, 1) == 1) {
+                    __threadfence_system();
+                    if (atomicSub_system(pp->gactive, 1) == 1)
+                        for (int k = 0; k < pp->world; k++) *(volatile int *)pp->done_all[k] = 1;
+                }
             } else {
                 if (atomicAnd(tileflag + t, ~NF_RUNNING) & NF_SIDES) nf_push(ring, cap, ctl, t);
                 __threadfence();
@@ -1656,13 +1690,15 @@ int g_nf_ir = 1;           // MS_NF_IR=0 keeps the W-based solver (k_nf_solve) o
 static int nf_launch_solve_ir(const float *F, int *Dg, int P, int *ring, int cap, int *tileflag, const int *tilesides,
                               const int *tmeta, NfCtl *ctl, int *irbad, int rows, int cols, int tiles_x, int tiles_y,
                               int ntiles, double sh, double dg, int64_t units, cudaStream_t s, const NfP2P *pp = nullptr) {
-    static int grid_blocks = 0;
+    static int grid_blocks_of[2] = {0, 0};
+    const void *kern = pp ? (const void *)k_nf_solve_ir<true> : (const void *)k_nf_solve_ir<false>;
+    int &grid_blocks = grid_blocks_of[pp ? 1 : 0];
     if (!grid_blocks) {
-        MS_CUDA(cudaFuncSetAttribute(k_nf_solve_ir, cudaFuncAttributeMaxDynamicSharedMemorySize, IR_SMEM));
+        MS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, IR_SMEM));
         int dev = 0, sms = 0, per_sm = 0;
         MS_CUDA(cudaGetDevice(&dev));
         MS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        MS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_nf_solve_ir, IR_NT, IR_SMEM));
+        MS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, IR_NT, IR_SMEM));
         if (per_sm < 1) { set_error("fill_terrain_no_flats: solver kernel does not fit on an SM"); return MS_ERR_CUDA; }
         grid_blocks = sms * per_sm;
     }
@@ -1672,7 +1708,7 @@ static int nf_launch_solve_ir(const float *F, int *Dg, int P, int *ring, int cap
     int g = (grid_blocks < ntiles || pp) ? grid_blocks : ntiles;
     prof_units(units);
     if (g_prof) prof_begin("k_nf_solve_ir", s);
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_nf_solve_ir, dim3(g), dim3(IR_NT), args, IR_SMEM, s);
+    cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3(g), dim3(IR_NT), args, IR_SMEM, s);
     if (g_prof) prof_end(s);
     g_launches++;
     if (e != cudaSuccess) {
