@@ -42,6 +42,16 @@ extern "C" {
 int ms_version(void);
 int ms_init(int device);                 /* select device, create the memory pool; idempotent */
 int ms_shutdown(void);
+/* Device twins of host rasters (csrc/cache.cu): the host-pointer entry points below keep the device buffer of every
+ * raster they upload or return, keyed on (host address, size, sampled fingerprint of the host bytes), so that the
+ * call sequence of DemTool.process / BluespotTool.process (dem.py:67-91, bluespots.py:158-206) uploads each array
+ * once, fill_terrain_no_flats reuses fill_terrain's result, and its second call (bluespots.py:203-205) is a copy.
+ * An array rewritten IN PLACE between two calls must be followed by ms_cache_clear() (the fingerprint samples ~2000
+ * words); MS_CACHE=0 in the environment switches the cache off.  stats: out5 = inputs found on the device, inputs
+ * uploaded, derived results reused, evictions, bytes held. */
+int ms_cache_clear(void);
+int ms_cache_forget(const void *host);      /* the host array at this address is gone: drop its twin */
+int ms_cache_stats(int64_t *out5);
 const char *ms_last_error(void);
 int ms_device_count(void);
 /* launches of this library's own kernels since the last reset (bench.py's `gpu_launches`) */

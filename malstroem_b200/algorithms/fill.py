@@ -25,31 +25,34 @@ def _dtm2d(dtm, what):
 def fill_terrain(dtm):
     """fill.fill_terrain (fill.py:112-171): depressionless float32 DEM, same shape."""
     dtm = _dtm2d(dtm, "fill_terrain")
-    out = np.empty(dtm.shape, DTYPE_FILL)
+    out = _lib.result_array(dtm.shape, DTYPE_FILL)
     with _lib.lock:
         _lib.check(_lib.lib().ms_fill_terrain(_lib.ptr(dtm), _lib.ptr(out), None, dtm.shape[0], dtm.shape[1]),
                    "fill_terrain")
+    _lib.track(dtm, out)
     return out
 
 
 def fill_terrain_and_depths(dtm):
     """fill_terrain plus `filled - dtm` (dem.py:67-71) in one device pass."""
     dtm = _dtm2d(dtm, "fill_terrain")
-    out = np.empty(dtm.shape, DTYPE_FILL)
-    dep = np.empty(dtm.shape, DTYPE_FILL)
+    out = _lib.result_array(dtm.shape, DTYPE_FILL)
+    dep = _lib.result_array(dtm.shape, DTYPE_FILL)
     with _lib.lock:
         _lib.check(_lib.lib().ms_fill_terrain(_lib.ptr(dtm), _lib.ptr(out), _lib.ptr(dep), dtm.shape[0], dtm.shape[1]),
                    "fill_terrain")
+    _lib.track(dtm, out, dep)
     return out, dep
 
 
 def fill_terrain_no_flats(dtm, short=0, diag=0):
     """fill.fill_terrain_no_flats (fill.py:174-232): float64 surface with a strictly descending path."""
     dtm = _dtm2d(dtm, "fill_terrain_no_flats")
-    out = np.empty(dtm.shape, DTYPE_FILLNOFLAT)
+    out = _lib.result_array(dtm.shape, DTYPE_FILLNOFLAT)
     with _lib.lock:
         _lib.check(_lib.lib().ms_fill_terrain_no_flats(_lib.ptr(dtm), float(short), float(diag), _lib.ptr(out),
                                                        dtm.shape[0], dtm.shape[1]), "fill_terrain_no_flats")
+    _lib.track(dtm, out)
     return out
 
 
@@ -63,6 +66,7 @@ def minimum_safe_short_and_diag(dem):
         with _lib.lock:
             _lib.check(_lib.lib().ms_minmax_f32(_lib.ptr(d), d.size, _lib.ptr(lo), _lib.ptr(hi)),
                        "minimum_safe_short_and_diag")
+        _lib.track(d)
         amax, amin = hi[0], lo[0]
     else:
         amax, amin = np.amax(dem), np.amin(dem)

@@ -26,20 +26,22 @@ def _arr2d(a, dtype, what):
 def terrain_flowdirection(terrain, edges_flow_outward=True):
     """flow.terrain_flowdirection (flow.py:142-167): uint8 D8 codes 0..7, 8 = no direction."""
     t = _arr2d(terrain, np.float64, "terrain_flowdirection")
-    out = np.empty(t.shape, DTYPE_FLOWDIR)
+    out = _lib.result_array(t.shape, DTYPE_FLOWDIR)
     with _lib.lock:
         _lib.check(_lib.lib().ms_flowdir(_lib.ptr(t), _lib.ptr(out), t.shape[0], t.shape[1],
                                          1 if edges_flow_outward else 0), "terrain_flowdirection")
+    _lib.track(t, out)
     return out
 
 
 def accumulated_flow(flowdir):
     """flow.accumulated_flow (flow.py:344-364): float64 upstream cell counts (including the cell)."""
     fd = _arr2d(flowdir, np.uint8, "accumulated_flow")
-    out = np.empty(fd.shape, DTYPE_ACCUM)
+    out = _lib.result_array(fd.shape, DTYPE_ACCUM)
     with _lib.lock:
         _lib.check(_lib.lib().ms_accumulated_flow(_lib.ptr(fd), _lib.ptr(out), fd.shape[0], fd.shape[1]),
                    "accumulated_flow")
+    _lib.track(fd, out)
     return out
 
 
@@ -61,6 +63,7 @@ def watersheds_from_labels(flowdir, labelled, unassigned):
         _lib.check(_lib.lib().ms_watersheds_from_labels(_lib.ptr(fd), _lib.ptr(work), work.dtype.itemsize,
                                                         fd.shape[0], fd.shape[1], int(unassigned)),
                    "watersheds_from_labels")
+    _lib.track(fd, work)
     if work is not labelled:
         labelled[...] = work.astype(labelled.dtype)
     return None

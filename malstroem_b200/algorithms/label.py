@@ -25,6 +25,7 @@ def _nlabels(lab, nlabels, what):
         lo = np.zeros(1, np.int32)
         with _lib.lock:
             _lib.check(_lib.lib().ms_label_range(_lib.ptr(lab), lab.size, _lib.ptr(lo), _lib.ptr(hi)), what)
+        _lib.track(lab)
         nlabels = int(hi[0])
     nlabels = int(nlabels)
     if nlabels < 0:
@@ -41,12 +42,13 @@ def connected_components(data):
     if data.dtype not in _lib.DTYPE_CODE:
         data = data != 0                 # any other dtype: the foreground mask is all scipy looks at
     d = np.ascontiguousarray(data)
-    out = np.empty(d.shape, np.int32)
+    out = _lib.result_array(d.shape, np.int32)
     n = np.zeros(1, np.int64)
     with _lib.lock:
         _lib.check(_lib.lib().ms_connected_components(_lib.ptr(d.view(np.uint8) if d.dtype == np.bool_ else d),
                                                       _lib.DTYPE_CODE[d.dtype], _lib.ptr(out), d.shape[0],
                                                       d.shape[1], _lib.ptr(n)), "connected_components")
+    _lib.track(d, out)
     return out, int(n[0])
 
 
@@ -66,6 +68,7 @@ def label_stats(data, labelled, nlabels=None):
     with _lib.lock:
         _lib.check(_lib.lib().ms_label_stats(_lib.ptr(d), _lib.DTYPE_CODE[d.dtype], _lib.ptr(lab), d.size, nlabels,
                                              _lib.ptr(mn), _lib.ptr(mx), _lib.ptr(sm), _lib.ptr(cnt)), "label_stats")
+    _lib.track(d, lab)
     stats['min'], stats['max'], stats['sum'], stats['count'] = mn, mx, sm, cnt
     return stats
 
@@ -77,10 +80,11 @@ def keep_labels(labelled, keep_label, background=0):
     lab = _labels32(labelled, "keep_labels")
     if lab.size == 0:
         return np.zeros(lab.shape, bool)
-    out = np.empty(lab.shape, np.uint8)
+    out = _lib.result_array(lab.shape, np.uint8)
     with _lib.lock:
         _lib.check(_lib.lib().ms_keep_labels(_lib.ptr(lab), lab.size, _lib.ptr(keep), keep.size, _lib.ptr(out)),
                    "keep_labels")
+    _lib.track(lab, out)
     return out.view(np.bool_)
 
 
@@ -99,6 +103,7 @@ def _extreme(data, labelled, nlabels, want_max, what):
         _lib.check(_lib.lib().ms_label_extreme_index(_lib.ptr(d), _lib.ptr(lab), d.shape[0], d.shape[1], nlabels,
                                                      1 if want_max else 0, _lib.ptr(val), _lib.ptr(row),
                                                      _lib.ptr(col)), what)
+    _lib.track(d, lab)
     out['value'], out['row'], out['col'] = val, row, col
     return out
 
@@ -126,4 +131,5 @@ def label_count(labelled):
         nb = int(hi[0]) + 1
         out = np.empty(nb, np.int64)
         _lib.check(_lib.lib().ms_label_count(_lib.ptr(lab), lab.size, nb, _lib.ptr(out)), "label_count")
+    _lib.track(lab)
     return out

@@ -255,6 +255,34 @@ __device__ inline int block_append_pos(int cnt, int *n_out) {
 }
 #endif
 
+// ---- device twins of host rasters (cache.cu): used by the host-pointer entry points -----------------------------
+void cache_begin_call();
+void cache_end_call();
+int cache_input(const void *host, size_t bytes, cudaStream_t s, void **dev_out);
+int cache_output(size_t bytes, void **dev_out);
+void cache_bind_host(void *dev, const void *host, size_t bytes);
+void cache_bind_derived(void *dev, const void *src, int kind, double a, double b);
+void *cache_find_derived(const void *src, int kind, double a, double b);
+void cache_clear_all();
+enum { CK_FILLED = 1, CK_DEPTHS = 2, CK_NOFLATS = 3 };
+// one host-pointer call: inputs come from the cache (or are uploaded into it), results live in it afterwards
+struct HostCall {
+    HostCall() { cache_begin_call(); }
+    ~HostCall() { cache_end_call(); }
+    template <class T> int in(const T *host, size_t count, cudaStream_t s, T **dev) {
+        void *p = nullptr;
+        int rc = cache_input(host, count * sizeof(T), s, &p);
+        *dev = (T *)p;
+        return rc;
+    }
+    template <class T> int out(size_t count, T **dev) {
+        void *p = nullptr;
+        int rc = cache_output(count * sizeof(T), &p);
+        *dev = (T *)p;
+        return rc;
+    }
+};
+
 // internal device-pointer stage entry points used by the pipeline (pipeline.cu)
 int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_t rows, int64_t cols,
                           int64_t *stats, cudaStream_t s);

@@ -277,18 +277,27 @@ int ms_band_destroy(ms_band *b) {
 
 int ms_init(int device) {
     if (ms::g_device == device) return MS_OK;
+    if (ms::g_device >= 0) {
+        // the scratch arena, the pinned flags, the copy stream and the raster cache belong to the first device: a
+        // second device in the same process would run on the first one's memory.  Multi-GPU = one process per GPU.
+        ms::set_error("ms_init(%d): the library of this process is bound to device %d (one process per GPU; "
+                      "ms_shutdown() first to rebind)", device, ms::g_device);
+        return MS_ERR_ARG;
+    }
     return ms::init_device(device);
 }
 
 int ms_shutdown(void) {
     if (ms::g_device < 0) return MS_OK;
     cudaDeviceSynchronize();
+    ms::cache_clear_all();
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, ms::g_device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     if (ms::g_blocks.empty() && ms::g_arena) {
         cudaFree(ms::g_arena);
         ms::g_arena = nullptr;
         ms::g_arena_cap = ms::g_arena_top = 0;
+        ms::g_device = -1;          // nothing of the old device is left: ms_init may bind another one
     }
     return MS_OK;
 }

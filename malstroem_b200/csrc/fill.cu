@@ -742,11 +742,12 @@ int ms_minmax_f32(const float *dem, int64_t n, float *out_min, float *out_max) {
     MS_TRY(ms::ensure_init());
     if (!dem || n <= 0) { ms::set_error("minmax: bad argument"); return MS_ERR_ARG; }
     cudaStream_t s = nullptr;
-    ms::DevBuf<float> d, o;
-    MS_TRY(d.alloc((size_t)n, s));
+    ms::HostCall hc;
+    float *d = nullptr;
+    ms::DevBuf<float> o;
+    MS_TRY(hc.in(dem, (size_t)n, s, &d));
     MS_TRY(o.alloc(2, s));
-    MS_CUDA(cudaMemcpyAsync(d.p, dem, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s));
-    MS_TRY(ms::minmax_dev(d.p, n, o.p, s));
+    MS_TRY(ms::minmax_dev(d, n, o.p, s));
     float r[2];
     MS_CUDA(cudaMemcpyAsync(r, o.p, sizeof(r), cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
@@ -770,15 +771,24 @@ int ms_fill_terrain(const float *dtm, float *filled, float *depths, int64_t rows
     }
     cudaStream_t s = nullptr;
     size_t n = (size_t)(rows * cols);
-    ms::DevBuf<float> d, f, dp;
-    MS_TRY(d.alloc(n, s));
-    MS_TRY(f.alloc(n, s));
-    if (depths) MS_TRY(dp.alloc(n, s));
-    MS_CUDA(cudaMemcpyAsync(d.p, dtm, n * sizeof(float), cudaMemcpyHostToDevice, s));
-    MS_TRY(ms::fill_terrain_dev_impl(d.p, f.p, depths ? dp.p : nullptr, rows, cols, nullptr, s));
-    MS_CUDA(cudaMemcpyAsync(filled, f.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (depths) MS_CUDA(cudaMemcpyAsync(depths, dp.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    ms::HostCall hc;
+    float *d = nullptr;
+    MS_TRY(hc.in(dtm, n, s, &d));
+    // the plain fill (and the depths) of this DEM may still be on the device (an earlier call on the same array)
+    float *f = (float *)ms::cache_find_derived(d, ms::CK_FILLED, 0, 0);
+    float *dp = (float *)ms::cache_find_derived(d, ms::CK_DEPTHS, 0, 0);
+    if (!f || (depths && !dp)) {
+        MS_TRY(hc.out(n, &f));
+        MS_TRY(hc.out(n, &dp));
+        MS_TRY(ms::fill_terrain_dev_impl(d, f, dp, rows, cols, nullptr, s));
+        ms::cache_bind_derived(f, d, ms::CK_FILLED, 0, 0);
+        ms::cache_bind_derived(dp, d, ms::CK_DEPTHS, 0, 0);
+    }
+    MS_CUDA(cudaMemcpyAsync(filled, f, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (depths) MS_CUDA(cudaMemcpyAsync(depths, dp, n * sizeof(float), cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
+    ms::cache_bind_host(f, filled, n * sizeof(float));
+    if (depths) ms::cache_bind_host(dp, depths, n * sizeof(float));
     return MS_OK;
 }
 

@@ -338,14 +338,15 @@ int ms_flowdir(const double *terrain, uint8_t *flowdir, int64_t rows, int64_t co
     if (!terrain || !flowdir || rows < 1 || cols < 1) { ms::set_error("terrain_flowdirection: bad argument"); return MS_ERR_ARG; }
     cudaStream_t s = nullptr;
     size_t n = (size_t)(rows * cols);
-    ms::DevBuf<double> t;
-    ms::DevBuf<uint8_t> o;
-    MS_TRY(t.alloc(n, s));
-    MS_TRY(o.alloc(n, s));
-    MS_CUDA(cudaMemcpyAsync(t.p, terrain, n * sizeof(double), cudaMemcpyHostToDevice, s));
-    MS_TRY(ms::flowdir_dev_impl(t.p, o.p, rows, cols, edges_flow_outward, s, 0));
-    MS_CUDA(cudaMemcpyAsync(flowdir, o.p, n, cudaMemcpyDeviceToHost, s));
+    ms::HostCall hc;
+    double *t = nullptr;
+    uint8_t *o = nullptr;
+    MS_TRY(hc.in(terrain, n, s, &t));
+    MS_TRY(hc.out(n, &o));
+    MS_TRY(ms::flowdir_dev_impl(t, o, rows, cols, edges_flow_outward, s, 0));
+    MS_CUDA(cudaMemcpyAsync(flowdir, o, n, cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
+    ms::cache_bind_host(o, flowdir, n);
     return MS_OK;
 }
 
@@ -359,14 +360,15 @@ int ms_accumulated_flow(const uint8_t *flowdir, double *accum, int64_t rows, int
     if (!flowdir || !accum || rows < 1 || cols < 1) { ms::set_error("accumulated_flow: bad argument"); return MS_ERR_ARG; }
     cudaStream_t s = nullptr;
     size_t n = (size_t)(rows * cols);
-    ms::DevBuf<uint8_t> f;
-    ms::DevBuf<double> a;
-    MS_TRY(f.alloc(n, s));
-    MS_TRY(a.alloc(n, s));
-    MS_CUDA(cudaMemcpyAsync(f.p, flowdir, n, cudaMemcpyHostToDevice, s));
-    MS_TRY(ms::accum_dev_impl(f.p, a.p, rows, cols, s));
-    MS_CUDA(cudaMemcpyAsync(accum, a.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    ms::HostCall hc;
+    uint8_t *f = nullptr;
+    double *a = nullptr;
+    MS_TRY(hc.in(flowdir, n, s, &f));
+    MS_TRY(hc.out(n, &a));
+    MS_TRY(ms::accum_dev_impl(f, a, rows, cols, s));
+    MS_CUDA(cudaMemcpyAsync(accum, a, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
+    ms::cache_bind_host(a, accum, n * sizeof(double));
     return MS_OK;
 }
 
@@ -386,14 +388,15 @@ int ms_watersheds_from_labels(const uint8_t *flowdir, void *labelled, int label_
     }
     cudaStream_t s = nullptr;
     size_t n = (size_t)(rows * cols);
-    ms::DevBuf<uint8_t> f, l;
-    MS_TRY(f.alloc(n, s));
-    MS_TRY(l.alloc(n * label_bytes, s));
-    MS_CUDA(cudaMemcpyAsync(f.p, flowdir, n, cudaMemcpyHostToDevice, s));
-    MS_CUDA(cudaMemcpyAsync(l.p, labelled, n * label_bytes, cudaMemcpyHostToDevice, s));
-    MS_TRY(ms::watersheds_dev_impl(f.p, l.p, label_bytes, rows, cols, unassigned, nullptr, s));
-    MS_CUDA(cudaMemcpyAsync(labelled, l.p, n * label_bytes, cudaMemcpyDeviceToHost, s));
+    ms::HostCall hc;
+    uint8_t *f = nullptr, *l = nullptr;
+    MS_TRY(hc.in(flowdir, n, s, &f));
+    MS_TRY(hc.in((const uint8_t *)labelled, n * label_bytes, s, &l));
+    // in place, on the device twin as on the host array (flow.py:398-412 mutates `labelled`)
+    MS_TRY(ms::watersheds_dev_impl(f, l, label_bytes, rows, cols, unassigned, nullptr, s));
+    MS_CUDA(cudaMemcpyAsync(labelled, l, n * label_bytes, cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
+    ms::cache_bind_host(l, labelled, n * label_bytes);
     return MS_OK;
 }
 

@@ -1100,14 +1100,15 @@ int ms_connected_components(const void *data, int dtype, int32_t *labels, int64_
     if (!data || !labels || !es || rows < 1 || cols < 1) { ms::set_error("connected_components: bad argument"); return MS_ERR_ARG; }
     cudaStream_t s = nullptr;
     size_t n = (size_t)(rows * cols);
-    ms::DevBuf<uint8_t> d;
-    ms::DevBuf<int32_t> l;
-    MS_TRY(d.alloc(n * es, s));
-    MS_TRY(l.alloc(n, s));
-    MS_CUDA(cudaMemcpyAsync(d.p, data, n * es, cudaMemcpyHostToDevice, s));
-    MS_TRY(ms_connected_components_dev(d.p, dtype, l.p, rows, cols, nlabels, s));
-    MS_CUDA(cudaMemcpyAsync(labels, l.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    ms::HostCall hc;
+    uint8_t *d = nullptr;
+    int32_t *l = nullptr;
+    MS_TRY(hc.in((const uint8_t *)data, n * es, s, &d));
+    MS_TRY(hc.out(n, &l));
+    MS_TRY(ms_connected_components_dev(d, dtype, l, rows, cols, nlabels, s));
+    MS_CUDA(cudaMemcpyAsync(labels, l, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
+    ms::cache_bind_host(l, labels, n * sizeof(int32_t));
     return MS_OK;
 }
 
@@ -1121,11 +1122,12 @@ int ms_label_range(const int32_t *labels, int64_t n, int32_t *out_min, int32_t *
     MS_TRY(ms::ensure_init());
     if (!labels || n < 1) { ms::set_error("label_range: bad argument"); return MS_ERR_ARG; }
     cudaStream_t s = nullptr;
-    ms::DevBuf<int32_t> l, o;
-    MS_TRY(l.alloc((size_t)n, s));
+    ms::HostCall hc;
+    int32_t *l = nullptr;
+    ms::DevBuf<int32_t> o;
+    MS_TRY(hc.in(labels, (size_t)n, s, &l));
     MS_TRY(o.alloc(2, s));
-    MS_CUDA(cudaMemcpyAsync(l.p, labels, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    MS_TRY(ms::label_range_dev_impl(l.p, n, o.p, s));
+    MS_TRY(ms::label_range_dev_impl(l, n, o.p, s));
     int32_t r[2];
     MS_CUDA(cudaMemcpyAsync(r, o.p, sizeof(r), cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
@@ -1153,18 +1155,17 @@ int ms_label_stats(const void *data, int dtype, const int32_t *labels, int64_t n
     }
     cudaStream_t s = nullptr;
     size_t m = (size_t)nlabels + 1;
-    ms::DevBuf<uint8_t> d;
-    ms::DevBuf<int32_t> l;
+    ms::HostCall hc;
+    uint8_t *d = nullptr;
+    int32_t *l = nullptr;
     ms::DevBuf<double> a, b, c;
     ms::DevBuf<int64_t> k;
-    MS_TRY(d.alloc((size_t)n * es, s));
-    MS_TRY(l.alloc((size_t)n, s));
+    MS_TRY(hc.in((const uint8_t *)data, (size_t)n * es, s, &d));
+    MS_TRY(hc.in(labels, (size_t)n, s, &l));
     MS_TRY(a.alloc(m, s)); MS_TRY(b.alloc(m, s)); MS_TRY(c.alloc(m, s)); MS_TRY(k.alloc(m, s));
-    MS_CUDA(cudaMemcpyAsync(d.p, data, (size_t)n * es, cudaMemcpyHostToDevice, s));
-    MS_CUDA(cudaMemcpyAsync(l.p, labels, (size_t)n * 4, cudaMemcpyHostToDevice, s));
     ErrFlag ef;
     MS_TRY(ef.init(s));
-    MS_TRY(ms::label_stats_dev_impl(d.p, dtype, l.p, n, nlabels, a.p, b.p, c.p, k.p, ef.d.p, s));
+    MS_TRY(ms::label_stats_dev_impl(d, dtype, l, n, nlabels, a.p, b.p, c.p, k.p, ef.d.p, s));
     MS_TRY(ef.check("label_stats"));
     MS_CUDA(cudaMemcpyAsync(out_min, a.p, m * 8, cudaMemcpyDeviceToHost, s));
     MS_CUDA(cudaMemcpyAsync(out_max, b.p, m * 8, cudaMemcpyDeviceToHost, s));
@@ -1190,16 +1191,17 @@ int ms_label_extreme_index(const double *data, const int32_t *labels, int64_t ro
     if (!data || !labels || rows < 1 || cols < 1 || nlabels < 0) { ms::set_error("label_min/max_index: bad argument"); return MS_ERR_ARG; }
     cudaStream_t s = nullptr;
     size_t n = (size_t)(rows * cols), m = (size_t)nlabels + 1;
-    ms::DevBuf<double> d, v;
-    ms::DevBuf<int32_t> l;
+    ms::HostCall hc;
+    double *d = nullptr;
+    int32_t *l = nullptr;
+    ms::DevBuf<double> v;
     ms::DevBuf<int64_t> r, c;
-    MS_TRY(d.alloc(n, s)); MS_TRY(l.alloc(n, s));
+    MS_TRY(hc.in(data, n, s, &d));
+    MS_TRY(hc.in(labels, n, s, &l));
     MS_TRY(v.alloc(m, s)); MS_TRY(r.alloc(m, s)); MS_TRY(c.alloc(m, s));
-    MS_CUDA(cudaMemcpyAsync(d.p, data, n * 8, cudaMemcpyHostToDevice, s));
-    MS_CUDA(cudaMemcpyAsync(l.p, labels, n * 4, cudaMemcpyHostToDevice, s));
     ErrFlag ef;
     MS_TRY(ef.init(s));
-    MS_TRY(ms::label_extreme_dev_impl(d.p, l.p, rows, cols, nlabels, want_max, v.p, r.p, c.p, ef.d.p, s));
+    MS_TRY(ms::label_extreme_dev_impl(d, l, rows, cols, nlabels, want_max, v.p, r.p, c.p, ef.d.p, s));
     MS_TRY(ef.check("label_min/max_index"));
     MS_CUDA(cudaMemcpyAsync(out_value, v.p, m * 8, cudaMemcpyDeviceToHost, s));
     MS_CUDA(cudaMemcpyAsync(out_row, r.p, m * 8, cudaMemcpyDeviceToHost, s));
@@ -1219,14 +1221,14 @@ int ms_label_count(const int32_t *labels, int64_t n, int64_t nbins, int64_t *out
     MS_TRY(ms::ensure_init());
     if (!labels || !out_count || n < 1 || nbins < 1) { ms::set_error("label_count: bad argument"); return MS_ERR_ARG; }
     cudaStream_t s = nullptr;
-    ms::DevBuf<int32_t> l;
+    ms::HostCall hc;
+    int32_t *l = nullptr;
     ms::DevBuf<int64_t> c;
-    MS_TRY(l.alloc((size_t)n, s));
+    MS_TRY(hc.in(labels, (size_t)n, s, &l));
     MS_TRY(c.alloc((size_t)nbins, s));
-    MS_CUDA(cudaMemcpyAsync(l.p, labels, (size_t)n * 4, cudaMemcpyHostToDevice, s));
     ErrFlag ef;
     MS_TRY(ef.init(s));
-    MS_TRY(ms::label_count_dev_impl(l.p, n, nbins, c.p, ef.d.p, s));
+    MS_TRY(ms::label_count_dev_impl(l, n, nbins, c.p, ef.d.p, s));
     MS_TRY(ef.check("label_count"));
     MS_CUDA(cudaMemcpyAsync(out_count, c.p, (size_t)nbins * 8, cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
@@ -1245,19 +1247,21 @@ int ms_keep_labels(const int32_t *labels, int64_t n, const uint8_t *keep, int64_
     MS_TRY(ms::ensure_init());
     if (!labels || !keep || !out || n < 1 || nkeep < 1) { ms::set_error("keep_labels: bad argument"); return MS_ERR_ARG; }
     cudaStream_t s = nullptr;
-    ms::DevBuf<int32_t> l;
-    ms::DevBuf<uint8_t> k, o;
-    MS_TRY(l.alloc((size_t)n, s));
+    ms::HostCall hc;
+    int32_t *l = nullptr;
+    uint8_t *o = nullptr;
+    ms::DevBuf<uint8_t> k;
+    MS_TRY(hc.in(labels, (size_t)n, s, &l));
+    MS_TRY(hc.out((size_t)n, &o));
     MS_TRY(k.alloc((size_t)nkeep, s));
-    MS_TRY(o.alloc((size_t)n, s));
-    MS_CUDA(cudaMemcpyAsync(l.p, labels, (size_t)n * 4, cudaMemcpyHostToDevice, s));
     MS_CUDA(cudaMemcpyAsync(k.p, keep, (size_t)nkeep, cudaMemcpyHostToDevice, s));
     ErrFlag ef;
     MS_TRY(ef.init(s));
-    MS_TRY(ms::keep_labels_dev_impl(l.p, n, k.p, nkeep, o.p, ef.d.p, s));
+    MS_TRY(ms::keep_labels_dev_impl(l, n, k.p, nkeep, o, ef.d.p, s));
     MS_TRY(ef.check("keep_labels"));
-    MS_CUDA(cudaMemcpyAsync(out, o.p, (size_t)n, cudaMemcpyDeviceToHost, s));
+    MS_CUDA(cudaMemcpyAsync(out, o, (size_t)n, cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
+    ms::cache_bind_host(o, out, (size_t)n);
     return MS_OK;
 }
 

@@ -2301,14 +2301,21 @@ int ms_fill_terrain_no_flats(const float *dtm, double short_eps, double diag_eps
     }
     cudaStream_t s = nullptr;
     size_t n = (size_t)(rows * cols);
-    ms::DevBuf<float> d;
-    ms::DevBuf<double> o;
-    MS_TRY(d.alloc(n, s));
-    MS_TRY(o.alloc(n, s));
-    MS_CUDA(cudaMemcpyAsync(d.p, dtm, n * sizeof(float), cudaMemcpyHostToDevice, s));
-    MS_TRY(ms::fill_no_flats_dev_impl(d.p, nullptr, short_eps, diag_eps, o.p, rows, cols, nullptr, s, nullptr, nullptr));
-    MS_CUDA(cudaMemcpyAsync(out, o.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    ms::HostCall hc;
+    float *d = nullptr;
+    MS_TRY(hc.in(dtm, n, s, &d));
+    // asked for twice by the tool layer (dem.py:80, bluespots.py:203-205): the second time it is still on the device
+    double *o = (double *)ms::cache_find_derived(d, ms::CK_NOFLATS, short_eps, diag_eps);
+    if (!o) {
+        // the plain fill of this DEM, if fill_terrain has just computed it (dem.py:67)
+        const float *f = (const float *)ms::cache_find_derived(d, ms::CK_FILLED, 0, 0);
+        MS_TRY(hc.out(n, &o));
+        MS_TRY(ms::fill_no_flats_dev_impl(d, f, short_eps, diag_eps, o, rows, cols, nullptr, s, nullptr, nullptr));
+        ms::cache_bind_derived(o, d, ms::CK_NOFLATS, short_eps, diag_eps);
+    }
+    MS_CUDA(cudaMemcpyAsync(out, o, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
+    ms::cache_bind_host(o, out, n * sizeof(double));
     return MS_OK;
 }
 
