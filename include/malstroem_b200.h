@@ -381,6 +381,26 @@ int ms_band_pp_parent_dev(const uint8_t *flowdir, const int32_t *wsheds, const i
 int ms_synth_fractal_dev(float *dem, int64_t rows, int64_t cols, int64_t row0, int64_t col0, int seed,
                          void *stream);
 
+/* ---- the raster codec of malstroem/io.py (GeoTIFF: tiled, deflate, predictor 2) on the device.
+ * The container (header, tag directory) is host-side bookkeeping (malstroem_b200/io.py); these touch every byte.
+ * ms_tiff_encode_dev replaces the compression inside RasterWriter.write (io.py:112-139): the raster (device, row
+ * major, sample_bytes 1 / 2 / 4 / 8) becomes one zlib stream (RFC 1950 / 1951, what TIFF compression 8 holds) per
+ * 256 x 256 tile in row-major tile order, tile k at out + k * slot (slot >= ms_tiff_tile_slot(sample_bytes)),
+ * sizes[k] bytes long; predictor 1 = none, 2 = horizontal differencing.  ms_tiff_pack_dev lines the streams up.
+ * ms_tiff_decode_dev replaces RasterReader.read (io.py:52-72): nblocks zlib streams (tiles, or strips with
+ * block_w = cols; any conforming deflate stream) are inflated into `scratch`, the predictor is undone, the blocks are
+ * cropped into the rows x cols raster, and samples equal to the file's nodata value (subst_mode 1: np.isclose, 2:
+ * np.isnan, 0: no substitution - io.py:69-71) become `subst`.  compressed = 0: `scratch` already holds the raw blocks. */
+int64_t ms_tiff_tile_slot(int sample_bytes);
+int ms_tiff_encode_dev(const void *raster, int sample_bytes, int64_t rows, int64_t cols, int predictor, void *out,
+                       int64_t slot, uint32_t *sizes, void *stream);
+int ms_tiff_pack_dev(const void *slots, int64_t slot, const uint32_t *sizes, const uint64_t *offs, int64_t ntiles,
+                     void *packed, void *stream);
+int ms_tiff_decode_dev(const void *in, const uint64_t *in_off, const uint32_t *in_len, int64_t nblocks, int block_w,
+                       int block_h, int sample_bytes, int sample_format, int predictor, void *scratch, void *raster,
+                       int64_t rows, int64_t cols, int subst_mode, double nodata, double subst, int compressed,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,11 @@ SIGNATURES = {
     "ms_rain_events": (c_int, [c_i64, c_p, c_p, c_p, c_i64, c_p, c_int, c_p, c_p, c_p, c_p, c_p]),
     "ms_rain_events_dev": (c_int, [c_i64, c_p, c_p, c_p, c_i64, c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ms_band_pp_parent_dev": (c_int, [c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_p]),
+    "ms_tiff_tile_slot": (c_i64, [c_int]),
+    "ms_tiff_encode_dev": (c_int, [c_p, c_int, c_i64, c_i64, c_int, c_p, c_i64, c_p, c_p]),
+    "ms_tiff_pack_dev": (c_int, [c_p, c_i64, c_p, c_p, c_i64, c_p, c_p]),
+    "ms_tiff_decode_dev": (c_int, [c_p, c_p, c_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_i64, c_i64,
+                                   c_int, c_dbl, c_dbl, c_int, c_p]),
     "ms_bluespot_network_dev": (c_int, [c_p, c_dbl, c_int, c_i64, c_p, c_int, c_p, c_p, c_p, c_p, c_p, c_p]),
 }
 
