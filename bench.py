@@ -481,6 +481,57 @@ def plugin_record(size, reps=3):
             "host_memory": "pageable numpy arrays (what the tools hold)", "cache": st}
 
 
+def config5_record(job, lib, bc, size, banded):
+    """BASELINE configs[4]: the pathological DEM (5 m plateaus = large exact flats, nested square craters centred on
+    the k * rows / 8 band edges, a raster-wide flat strip) through the whole path, whole on one GPU or as row bands,
+    certified, then the bluespot network and the 10 / 30 / 100 mm rain events on the device (SURVEY.md 8(f1, f2))."""
+    import torch
+    spec = importlib.util.spec_from_file_location("c5_check", os.path.join(ROOT, "tools", "c5_check.py"))
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    c5 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(c5)
+    if banded:
+        from malstroem_b200 import bands
+        pipe = bands.BandPipeline(size, size, bands.DistComm(), device=job.local)
+        pipe.dem.copy_(c5.pathological_dem_device(size, row0=pipe.r0, nrows=pipe.rows, device=job.local))
+    else:
+        from malstroem_b200.pipeline import RasterPipeline
+        pipe = RasterPipeline(size, size, device=job.local, with_accum=True)
+        pipe.dem.copy_(c5.pathological_dem_device(size, device=job.local))
+    torch.cuda.synchronize()
+    ms, _, _, _ = timed_steps(job, lib, pipe, 2, 3, profile=False)
+    par = parity_record(job, pipe, banded, size, size, bc, single_compare=False)
+    events = [10.0, 30.0, 100.0]
+    pipe.network(cell_area=0.16, events_mm=events)       # warm-up
+    job.barrier()
+    t0 = time.perf_counter()
+    net = pipe.network(cell_area=0.16, events_mm=events)
+    job.barrier()
+    net_ms = job.max_over_ranks([(time.perf_counter() - t0) * 1e3])[0]
+    tabs = pipe.tables if banded else {k: pipe.table(k) for k in pipe.tables}
+    cap = tabs["st_sum"] * 0.16
+    roots = net["parent"] < 0
+    rain = []
+    for e, mm_ in enumerate(events):
+        r, sp, v = net["rainv"][e], net["spillv"][e], net["v"][e]
+        lhs, rhs = float(r.sum()), float(v.sum() + sp[roots].sum())
+        rain.append({"mm": mm_, "conservation_rel_error": abs(lhs - rhs) / max(lhs, 1e-300),
+                     "bound_violations": int(((v < 0) | (v > cap) | (sp < 0) | ((sp > 0) & (v < cap))).sum()),
+                     "full_bluespots": int(((v >= cap) & (cap > 0)).sum())})
+    rec = {"workload": "pathological DEM %dx%d float32 (5 m plateaus, nested craters on the k*rows/8 band edges, a "
+                       "raster-wide flat) + bluespot network + rain events 10/30/100 mm" % (size, size),
+           "baseline_config": "BASELINE.json configs[4]",
+           "parallelism": ("%d row bands, one per GPU" % job.world) if banded else "1 GPU",
+           "ms_per_step": round(ms / 2, 3), "value": round(size * size * 2 / (ms * 1e-3) / 1e6, 2), "unit": UNIT,
+           "network_and_rain_ms": round(net_ms, 2), "nodes": int(net["parent"].numel()), "roots": int(roots.sum()),
+           "rain_events": rain, "parity": par, "stats": dict(pipe.stats)}
+    if banded:
+        pipe.close()
+    del pipe, net
+    torch.cuda.empty_cache()
+    return rec
+
+
 def sub_record(job, lib, size, steps, warmup, e2e_steps=2):
     """One more single-GPU size on the same line (rank 0's GPU): device-resident value and e2e."""
     import torch
@@ -542,6 +593,8 @@ def run_ours(args):
             sub["same_config"] = sub_record(job, lib, w, max(5, args.steps), 3)
             sub["same_config"]["note"] = ("the window `bench.py --impl reference --steps %d --warmup %d` times "
                                           "(%dx%d): GPU arm on the same DEM window" % (args.steps, args.warmup, w, w))
+        if not args.no_config5 and (world == 1 or world == 8 or args.config5_size):
+            sub["config5"] = config5_record(job, lib, bc, args.config5_size or S, banded)
         big = args.config4_size or (65536 if world == 8 and not args.no_config4 else 0)
         if big and world > 1:
             p4 = make_pipe(job, big, big, True)
@@ -646,6 +699,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the certificates / single-GPU comparison")
     ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (config2, same_config, config4)")
     ap.add_argument("--no-config4", action="store_true", help="N = 8: skip the 65536^2 sub-record")
+    ap.add_argument("--no-config5", action="store_true", help="skip the pathological-DEM sub-record (N = 1 and N = 8)")
+    ap.add_argument("--config5-size", type=int, default=0, help="edge of the `config5` sub-record (default: --size)")
     ap.add_argument("--config4-size", type=int, default=0, help="N > 1: edge of the `config4` sub-record (default: 65536 at N = 8, none otherwise)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != "reference":

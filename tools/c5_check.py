@@ -17,15 +17,18 @@ from malstroem_b200.pipeline import RasterPipeline, synth_fractal
 from big_check import certify
 
 
-def pathological_dem_device(S, seed=1):
-    """synth.pathological_dem(S, S, seed) with torch on the device (same integer-millimetre arithmetic)."""
-    dem = synth_fractal(S, S, seed=seed)
+def pathological_dem_device(S, seed=1, row0=0, nrows=None, device=0):
+    """synth.pathological_dem(S, S, seed) with torch on the device (same integer-millimetre arithmetic); with
+    row0 / nrows only the rows [row0, row0 + nrows) of it (one band of a row-band run)."""
+    nrows = S if nrows is None else nrows
+    dem = synth_fractal(nrows, S, seed=seed, row0=row0, device=device)
     out = torch.empty_like(dem)
     xs = torch.arange(S, device=dem.device, dtype=torch.int64).view(1, -1)
     CH = 2048
-    for r0 in range(0, S, CH):
-        r1 = min(S, r0 + CH)
-        y = torch.arange(r0, r1, device=dem.device, dtype=torch.int64).view(-1, 1)
+    for q0 in range(0, nrows, CH):
+        q1 = min(nrows, q0 + CH)
+        r0, r1 = q0, q1
+        y = torch.arange(row0 + q0, row0 + q1, device=dem.device, dtype=torch.int64).view(-1, 1)
         mm = torch.round(dem[r0:r1].double() * 1000.0).long()
         mm = (mm // 5000) * 5000
         for k in range(1, 8):
