@@ -218,6 +218,9 @@ int ms_band_nf_ir_prepare_dev(ms_band *band, const float *dem, const float *fill
                               int *irbad, void *stream);
 int ms_band_nf_ir_solve_dev(ms_band *band, const float *filled, double short_eps, double diag_eps, int64_t *tile_visits,
                             int *irbad, void *stream);
+/* solve = launch + wait; between the two the host is free for CPU work (no library call on this band) */
+int ms_band_nf_ir_solve_launch_dev(ms_band *band, const float *filled, double short_eps, double diag_eps, void *stream);
+int ms_band_nf_ir_solve_wait_dev(ms_band *band, int64_t *tile_visits, int *irbad, void *stream);
 int ms_band_nf_ir_finish_dev(ms_band *band, const float *dem, const float *filled, double *fnf, uint8_t *flowdir,
                              double short_eps, double diag_eps, int64_t *nviol, void *stream);
 

@@ -83,6 +83,8 @@ SIGNATURES = {
     "ms_band_nf_ir_edgefix_dev": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p]),
     "ms_band_nf_ir_prepare_dev": (c_int, [c_p, c_p, c_p, c_dbl, c_dbl, c_dbl, c_p, c_p, c_p, c_p, c_p]),
     "ms_band_nf_ir_solve_dev": (c_int, [c_p, c_p, c_dbl, c_dbl, c_p, c_p, c_p]),
+    "ms_band_nf_ir_solve_launch_dev": (c_int, [c_p, c_p, c_dbl, c_dbl, c_p]),
+    "ms_band_nf_ir_solve_wait_dev": (c_int, [c_p, c_p, c_p, c_p]),
     "ms_band_nf_ir_finish_dev": (c_int, [c_p, c_p, c_p, c_p, c_p, c_dbl, c_dbl, c_p, c_p]),
     "ms_band_flowdir_dev": (c_int, [c_p, c_p, c_p, c_int, c_p]),
     "ms_band_accum_local_dev": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p]),

@@ -230,6 +230,7 @@ class BandPipeline(object):
         self.dem = self.dem_ext[1:1 + self.rows]
         self.tables, self.nlabels, self.stats = {}, 0, {}
         self._flowdir_done = False
+        self._cc_allr = self._cc_plan = None
         self.p2p = self._p2p_setup()
 
     def _p2p_setup(self):
@@ -337,6 +338,11 @@ class BandPipeline(object):
         self.short = float((np.nextafter(maxval, np.inf) - maxval) * 1024.0)
         self.diag = float(self.short * 2 ** 0.5)
         self._tick("minmax")
+        # K5/K6 phase 1 (needs the depths only): its host-side merge then overlaps the no-flats solver kernel
+        self._cc_allr = None
+        if self.p2p and os.environ.get("MS_BAND_OVERLAP", "1") != "0":
+            self._labels_local(st)
+            self._tick("labels_local")
         # K2 no-flats fill
         self._noflats(st)
         self._tick("noflats")
@@ -453,8 +459,10 @@ class BandPipeline(object):
             self._call("ms_band_nf_p2p_arm_dev", self.h, st)
             comm.all_reduce(torch.zeros(1, dtype=torch.int32, device=dev), "sum").cpu()           # barrier
             try:
-                self._call("ms_band_nf_ir_solve_dev", self.h, _p(filled), self.short, self.diag, ctypes.byref(visits),
-                           ctypes.byref(bad), st)
+                self._call("ms_band_nf_ir_solve_launch_dev", self.h, _p(filled), self.short, self.diag, st)
+                if self._cc_allr is not None:
+                    self._labels_merge()          # CPU work while the solver kernels of all bands run
+                self._call("ms_band_nf_ir_solve_wait_dev", self.h, ctypes.byref(visits), ctypes.byref(bad), st)
             except RuntimeError:
                 err = 1
         self._tick("nf_p2p_solve")
@@ -528,14 +536,23 @@ class BandPipeline(object):
         self._call("ms_band_accum_finish_dev", self.h, _p(self.out["flowdir"]), _p(top), _p(bot), _p(self.out["accum"]),
                    st)
 
-    def _labels(self, st):
+    def _labels_local(self, st):
+        """K5/K6 phase 1: the band's own components (kernels) and the roots of every band's edge rows on the host."""
         comm, dev, cols = self.comm, self.device, self.cols
-        G = comm.size
-        L = _lib.lib()
         roots_tb = torch.empty((2, cols), dtype=torch.int64, device=dev)
         self._call("ms_band_cc_local_dev", self.h, _p(self.out["depths"]), _lib.MS_F32, self.cell_offset,
                    _p(roots_tb[0]), _p(roots_tb[1]), st)
-        allr = comm.all_gather(roots_tb).cpu().numpy()              # [G, 2, cols]
+        self._cc_allr = comm.all_gather(roots_tb).cpu().numpy()              # [G, 2, cols]
+        self._cc_plan = None
+
+    def _labels_merge(self):
+        """K5/K6 phase 2, host only (O(G * cols)): components that touch across band edges.  Runs while the no-flats
+        solver kernel is busy on the device when the integer-raster path is taken."""
+        if self._cc_plan is not None:
+            return
+        G, cols = self.comm.size, self.cols
+        L = _lib.lib()
+        allr = self._cc_allr
         top = np.ascontiguousarray(allr[:, 0, :])
         bot = np.ascontiguousarray(allr[:, 1, :])
         capn = 2 * G * cols
@@ -545,7 +562,18 @@ class BandPipeline(object):
         with _lib.lock:
             _lib.check(L.ms_cc_boundary_merge(G, cols, _lib.ptr(top), _lib.ptr(bot), _lib.ptr(out_root),
                                               _lib.ptr(out_glob), capn, ctypes.byref(k)), "ms_cc_boundary_merge")
-        plan = cc_plan(out_root[: k.value], out_glob[: k.value], self.cell_offset, self.cell_offset + self.rows * cols)
+        self._cc_plan = cc_plan(out_root[: k.value], out_glob[: k.value], self.cell_offset,
+                                self.cell_offset + self.rows * cols)
+        self._cc_nroots = int(k.value)
+
+    def _labels(self, st):
+        comm, dev, cols = self.comm, self.device, self.cols
+        if self._cc_allr is None:
+            self._labels_local(st)
+        self._labels_merge()
+        plan = self._cc_plan
+        k = ctypes.c_int64(self._cc_nroots)
+        self._cc_allr = None
         rer = torch.from_numpy(plan["rerooted_local"]).to(dev)
         cnt = ctypes.c_int64(0)
         self._call("ms_band_cc_count_dev", self.h, _p(rer) if rer.numel() else None, rer.numel(), ctypes.byref(cnt), st)

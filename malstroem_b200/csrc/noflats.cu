@@ -2209,11 +2209,12 @@ int ms_band_nf_ir_prepare_dev(ms_band *B, const float *dem, const float *filled,
     return MS_OK;
 }
 
-int ms_band_nf_ir_solve_dev(ms_band *B, const float *filled, double short_eps, double diag_eps, int64_t *tile_visits,
-                            int *irbad_out, void *stream) {
+/* launch: returns as soon as the solver kernel and the read-back of its control block are queued (the host may do
+ * CPU work meanwhile; no other library call on this band until wait); wait: the result. */
+int ms_band_nf_ir_solve_launch_dev(ms_band *B, const float *filled, double short_eps, double diag_eps, void *stream) {
     using namespace ms;
     MS_TRY(ensure_init());
-    if (!B || !B->nf_pp_dev || !filled || !irbad_out) { set_error("band no-flats P2P: not set up"); return MS_ERR_ARG; }
+    if (!B || !B->nf_pp_dev || !filled) { set_error("band no-flats P2P: not set up"); return MS_ERR_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
     NfBandBufs nb;
     MS_TRY(nf_band_bufs(B, &nb));
@@ -2227,7 +2228,16 @@ int ms_band_nf_ir_solve_dev(ms_band *B, const float *filled, double short_eps, d
     int *h_irbad = (int *)(h + 1);
     MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
     MS_CUDA(cudaMemcpyAsync(h_irbad, irbad, sizeof(int), cudaMemcpyDeviceToHost, s));
-    MS_TRY(ms::stream_sync(s));
+    return MS_OK;
+}
+
+int ms_band_nf_ir_solve_wait_dev(ms_band *B, int64_t *tile_visits, int *irbad_out, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B || !irbad_out) { set_error("band no-flats P2P: null pointer"); return MS_ERR_ARG; }
+    NfCtl *h = (NfCtl *)(host_flags().h + 32);
+    int *h_irbad = (int *)(h + 1);
+    MS_TRY(ms::stream_sync((cudaStream_t)stream));
     if (tile_visits) *tile_visits = h->visits;
     *irbad_out = *h_irbad;
     if (h->done != 1) {
@@ -2235,6 +2245,12 @@ int ms_band_nf_ir_solve_dev(ms_band *B, const float *filled, double short_eps, d
         return MS_ERR_NOCONV;
     }
     return MS_OK;
+}
+
+int ms_band_nf_ir_solve_dev(ms_band *B, const float *filled, double short_eps, double diag_eps, int64_t *tile_visits,
+                            int *irbad_out, void *stream) {
+    MS_TRY(ms_band_nf_ir_solve_launch_dev(B, filled, short_eps, diag_eps, stream));
+    return ms_band_nf_ir_solve_wait_dev(B, tile_visits, irbad_out, stream);
 }
 
 int ms_band_nf_ir_finish_dev(ms_band *B, const float *dem, const float *filled, double *fnf, uint8_t *flowdir,
