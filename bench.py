@@ -43,7 +43,7 @@ STAGE_BYTES = {
     "k_cc_tile<T>": 8, "k_cc_border": 8, "k_cc_flatten": 8, "k_cc_number": 8,
     "k_label_stats<T>": 8, "k_ws_ptr<L>": 9, "k_ws_assign<L>": 9, "k_label_count": 9,
     "k_extreme_key<true>": 12, "k_extreme_key<false>": 12, "k_extreme_index": 12, "k_minmax": 4,
-    "k_tables_a<true>": 28, "k_tables_a<false>": 20, "k_tables_b<true>": 20, "k_tables_b<false>": 12,
+    "k_tables_a<true>": 28, "k_tables_a<false>": 20, "k_tables_a2<true>": 28, "k_tables_a2<false>": 20, "k_tables_b<true>": 20, "k_tables_b<false>": 12,
 }
 WORKLOAD = ("synthetic fractal DEM %dx%d float32 (seed 1, 1 mm quantised): fill+depths, no-flats fill, D8, accum, "
             "bluespot labels, stats, watersheds, pour points")

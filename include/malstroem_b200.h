@@ -277,7 +277,7 @@ int ms_band_extreme_index_dev(const double *data, const int32_t *labels, int64_t
  * a label: combine across bands with min / max / sum all-reduces.  Phase B: with the GLOBAL extremes, the smallest
  * global flat index holding each (INT64_MAX: not in this band): combine with a min all-reduce. */
 int ms_band_tables_a_dev(const float *depths, const int32_t *labels, const double *fnf, const double *accum,
-                         const int32_t *wsheds, int64_t n, int64_t nlabels, double *st_min, double *st_max,
+                         const int32_t *wsheds, int64_t n, int64_t cols, int64_t nlabels, double *st_min, double *st_max,
                          double *st_sum, int64_t *st_count, int64_t *ws_count, double *vmin, double *vmax,
                          void *stream);
 int ms_band_tables_b_dev(const int32_t *labels, const double *fnf, const double *accum, int64_t n, int64_t nlabels,

@@ -100,7 +100,7 @@ SIGNATURES = {
     "ms_band_ws_finish_dev": (c_int, [c_p, c_p, c_p, ctypes.c_int32, c_p, c_p]),
     "ms_band_extreme_value_dev": (c_int, [c_p, c_p, c_i64, c_i64, c_int, c_p, c_p]),
     "ms_band_extreme_index_dev": (c_int, [c_p, c_p, c_i64, c_i64, c_p, c_i64, c_p, c_p]),
-    "ms_band_tables_a_dev": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "ms_band_tables_a_dev": (c_int, [c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "ms_band_tables_b_dev": (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_p, c_p, c_i64, c_p, c_p, c_p]),
     "ms_pipeline_dev": (c_int, [c_p, c_p]),
     "ms_pipeline_host_dev": (c_int, [c_p, c_p, c_p]),

@@ -626,7 +626,7 @@ class BandPipeline(object):
         sums = torch.empty(m, dtype=torch.float64, device=dev)           # st_sum
         cnts = torch.empty(2 * m, dtype=torch.int64, device=dev)         # st_count, ws_count
         self._call("ms_band_tables_a_dev", _p(self.out["depths"]), _p(self.out["labels"]), _p(self.out["fnf"]),
-                   _p(self.out["accum"]), _p(self.out["wsheds"]), n, self.nlabels, _p(lohi[0:]), _p(lohi[m:]),
+                   _p(self.out["accum"]), _p(self.out["wsheds"]), n, cols, self.nlabels, _p(lohi[0:]), _p(lohi[m:]),
                    _p(sums[0:]), _p(cnts[0:]), _p(cnts[m:]), _p(lohi[2 * m:]), _p(lohi[3 * m:]), st)
         lohi[m:2 * m].neg_()                                 # max(x) = -min(-x): one min all-reduce for all four
         lohi[3 * m:].neg_()

@@ -765,6 +765,195 @@ __global__ void __launch_bounds__(256) k_tables_a(const float *__restrict__ dept
     }
 }
 
+// Pass A, tile form: one CTA per 64 x 64 tile, a thread walks 16 consecutive cells of a tile row.  Bluespots and
+// watersheds are blobs, so a thread sees runs of one label: it keeps the run's partial results in registers and folds
+// a finished run into a small shared-memory table keyed by label (open addressing, 256 slots; a tile holds a few dozen
+// labels), and the table goes to the global per-label tables with one set of atomics per label and tile - instead of
+// one warp-aggregated set per label and 32 cells (k_tables_a above: 21.6 ms at 32768^2, 54 % issue-bound on the
+// match / group-reduction instructions).  Label 0 stays in registers as before.
+constexpr int TA_SLOTS = 256;
+template <bool ACC>
+__global__ void __launch_bounds__(256) k_tables_a2(const float *__restrict__ depths, const int32_t *__restrict__ lab,
+                                                   const double *__restrict__ fnf, const double *__restrict__ accum,
+                                                   const int32_t *__restrict__ ws, int rows, int cols, int tiles_x,
+                                                   int64_t nlabels, uint32_t *tmin, uint32_t *tmax, double *tsum,
+                                                   unsigned long long *tcnt, unsigned long long *kmin,
+                                                   unsigned long long *kmax, unsigned long long *wcnt, int *err) {
+    __shared__ int s_key[TA_SLOTS], s_wkey[TA_SLOTS];
+    __shared__ uint32_t s_min[TA_SLOTS], s_max[TA_SLOTS], s_cnt[TA_SLOTS], s_wcnt[TA_SLOTS];
+    __shared__ double s_sum[TA_SLOTS];
+    __shared__ unsigned long long s_kmin[TA_SLOTS], s_kmax[TA_SLOTS];
+    const unsigned full = 0xffffffffu;
+    const int tid = threadIdx.x;
+    {
+        s_key[tid] = 0; s_wkey[tid] = 0; s_min[tid] = 0xffffffffu; s_max[tid] = 0; s_cnt[tid] = 0; s_wcnt[tid] = 0;
+        s_sum[tid] = 0.0; s_kmin[tid] = ~0ull; s_kmax[tid] = 0ull;
+    }
+    __syncthreads();
+    const int tile = blockIdx.x, ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int r = ty * 64 + (tid >> 2), c0 = tx * 64 + (tid & 3) * 16;
+    // label-0 accumulators (registers, reduced over the CTA at the end)
+    uint32_t bmin = 0xffffffffu, bmax = 0;
+    double bsum = 0.0;
+    unsigned long long bcnt = 0, bwz = 0, bkmin = ~0ull, bkmax = 0ull;
+    // the current run of one bluespot label, and of one watershed label
+    int cur = -1, wcur = -1;
+    uint32_t rmin = 0xffffffffu, rmax = 0, rcnt = 0, wn = 0;
+    double rsum = 0.0;
+    unsigned long long rkmin = ~0ull, rkmax = 0ull;
+    auto slot_of = [&](int *keys, int lbl) {
+        unsigned h = ((unsigned)lbl * 2654435761u) >> 24;
+        for (int probe = 0; probe < 32; probe++) {
+            int old = atomicCAS(keys + h, 0, lbl);
+            if (old == 0 || old == lbl) return (int)h;
+            h = (h + 1) & (TA_SLOTS - 1);
+        }
+        return -1;
+    };
+    auto flush_run = [&]() {
+        if (cur == 0) {
+            bmin = rmin < bmin ? rmin : bmin; bmax = rmax > bmax ? rmax : bmax;
+            bsum += rsum; bcnt += rcnt;
+            bkmin = rkmin < bkmin ? rkmin : bkmin;
+            if (ACC) bkmax = rkmax > bkmax ? rkmax : bkmax;
+        } else if (cur > 0) {
+            int h = slot_of(s_key, cur);
+            if (h >= 0) {
+                atomicMin(s_min + h, rmin); atomicMax(s_max + h, rmax);
+                atomicAdd(s_sum + h, rsum); atomicAdd(s_cnt + h, rcnt);
+                atomicMin(s_kmin + h, rkmin);
+                if (ACC) atomicMax(s_kmax + h, rkmax);
+            } else {            // table full: straight to the global tables
+                atomicMin(tmin + cur, rmin); atomicMax(tmax + cur, rmax);
+                atomicAdd(tsum + cur, rsum); atomicAdd(tcnt + cur, (unsigned long long)rcnt);
+                atomicMin(kmin + cur, rkmin);
+                if (ACC) atomicMax(kmax + cur, rkmax);
+            }
+        }
+        rmin = 0xffffffffu; rmax = 0; rcnt = 0; rsum = 0.0; rkmin = ~0ull; rkmax = 0ull;
+    };
+    auto flush_w = [&]() {
+        if (wcur == 0) bwz += wn;
+        else if (wcur > 0) {
+            int h = slot_of(s_wkey, wcur);
+            if (h >= 0) atomicAdd(s_wcnt + h, wn);
+            else atomicAdd(wcnt + wcur, (unsigned long long)wn);
+        }
+        wn = 0;
+    };
+    if (r < rows) {
+        const size_t base = (size_t)r * cols + c0;
+        const bool vec = ((cols & 3) == 0) && (c0 + 16 <= cols);
+#pragma unroll 1
+        for (int sub = 0; sub < 4; sub++) {
+            int lv[4], wv[4];
+            float dv[4];
+            double fv[4], av[4];
+            const size_t i0 = base + sub * 4;
+            if (vec) {
+                const int4 l4 = __ldg(reinterpret_cast<const int4 *>(lab + i0)), w4 = __ldg(reinterpret_cast<const int4 *>(ws + i0));
+                const float4 d4 = __ldg(reinterpret_cast<const float4 *>(depths + i0));
+                const double2 f0 = __ldg(reinterpret_cast<const double2 *>(fnf + i0)), f1 = __ldg(reinterpret_cast<const double2 *>(fnf + i0 + 2));
+                lv[0] = l4.x; lv[1] = l4.y; lv[2] = l4.z; lv[3] = l4.w;
+                wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+                dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
+                fv[0] = f0.x; fv[1] = f0.y; fv[2] = f1.x; fv[3] = f1.y;
+                if (ACC) {
+                    const double2 a0 = __ldg(reinterpret_cast<const double2 *>(accum + i0)), a1 = __ldg(reinterpret_cast<const double2 *>(accum + i0 + 2));
+                    av[0] = a0.x; av[1] = a0.y; av[2] = a1.x; av[3] = a1.y;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool in = c0 + sub * 4 + j < cols;
+                    lv[j] = in ? lab[i0 + j] : -2;
+                    wv[j] = in ? ws[i0 + j] : -2;
+                    dv[j] = in ? depths[i0 + j] : 0.f;
+                    fv[j] = in ? fnf[i0 + j] : 0.0;
+                    av[j] = (ACC && in) ? accum[i0 + j] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int lbl = lv[j], w = wv[j];
+                if (lbl == -2) continue;                       // beyond the raster
+                if (lbl < 0 || lbl > nlabels) { *err = 1; lbl = -1; }
+                if (w < 0 || w > nlabels) { *err = 1; w = -1; }
+                if (lbl != cur) { flush_run(); cur = lbl; }
+                if (w != wcur) { flush_w(); wcur = w; }
+                wn++;
+                const float v = dv[j];
+                const double f = fv[j], a = ACC ? av[j] : 0.0;
+                const bool vok = (v == v);
+                const uint32_t k = okey32(vok ? v : 0.f);
+                if (vok) { rmin = k < rmin ? k : rmin; rmax = k > rmax ? k : rmax; }
+                rsum += (double)v;
+                rcnt++;
+                const unsigned long long fk = (f == f) ? okey64(f) : ~0ull;
+                rkmin = fk < rkmin ? fk : rkmin;
+                if (ACC) {
+                    const unsigned long long ak = (a == a) ? okey64(a) : 0ull;
+                    rkmax = ak > rkmax ? ak : rkmax;
+                }
+            }
+        }
+        flush_run();
+        flush_w();
+    }
+    __syncthreads();
+    // the tile's tables -> the global tables
+    {
+        const int lbl = s_key[tid];
+        if (lbl > 0) {
+            if (s_min[tid] < tmin[lbl]) atomicMin(tmin + lbl, s_min[tid]);
+            if (s_max[tid] > tmax[lbl]) atomicMax(tmax + lbl, s_max[tid]);
+            atomicAdd(tsum + lbl, s_sum[tid]);
+            atomicAdd(tcnt + lbl, (unsigned long long)s_cnt[tid]);
+            if (s_kmin[tid] < kmin[lbl]) atomicMin(kmin + lbl, s_kmin[tid]);
+            if (ACC && s_kmax[tid] > kmax[lbl]) atomicMax(kmax + lbl, s_kmax[tid]);
+        }
+        const int w = s_wkey[tid];
+        if (w > 0) atomicAdd(wcnt + w, (unsigned long long)s_wcnt[tid]);
+    }
+    // CTA reduction of the label-0 accumulators
+    uint32_t wmin = grp_min(full, bmin), wmax = grp_max(full, bmax);
+    unsigned long long wkmin = grp_min(full, bkmin), wkmax = grp_max(full, bkmax);
+    double wsum = bsum;
+    unsigned long long wc = bcnt, wz = bwz;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        wsum += __shfl_xor_sync(full, wsum, o);
+        wc += __shfl_xor_sync(full, wc, o);
+        wz += __shfl_xor_sync(full, wz, o);
+    }
+    __shared__ uint32_t smin[8], smax[8];
+    __shared__ double ssum[8];
+    __shared__ unsigned long long scnt[8], swz[8], skmin[8], skmax[8];
+    int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    if (lane == 0) { smin[wp] = wmin; smax[wp] = wmax; ssum[wp] = wsum; scnt[wp] = wc; swz[wp] = wz; skmin[wp] = wkmin; skmax[wp] = wkmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; k++) {
+            wmin = smin[k] < wmin ? smin[k] : wmin;
+            wmax = smax[k] > wmax ? smax[k] : wmax;
+            wsum += ssum[k];
+            wc += scnt[k];
+            wz += swz[k];
+            wkmin = skmin[k] < wkmin ? skmin[k] : wkmin;
+            wkmax = skmax[k] > wkmax ? skmax[k] : wkmax;
+        }
+        if (wc) {
+            atomicMin(tmin, wmin);
+            atomicMax(tmax, wmax);
+            atomicAdd(tsum, wsum);
+            atomicAdd(tcnt, wc);
+            atomicMin(kmin, wkmin);
+            if (ACC) atomicMax(kmax, wkmax);
+        }
+        if (wz) atomicAdd(wcnt, wz);
+    }
+}
+
 template <bool ACC>
 __global__ void __launch_bounds__(256) k_tables_b(const int32_t *__restrict__ lab, const double *__restrict__ fnf,
                                                   const double *__restrict__ accum, int64_t n, int64_t nlabels,
@@ -809,10 +998,11 @@ int pipeline_tables_dev_impl(const float *depths, const int32_t *lab, const doub
     int64_t want = (n + 255) / 256;
     int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
     prof_units(n);
-    if (acc) MS_LAUNCH(k_tables_a<true>, blocks, 256, 0, s, depths, lab, fnf, accum, ws, n, nlabels, tmin.p, tmax.p, st_sum,
-                       tcnt.p, kmin.p, kmax.p, (unsigned long long *)ws_count, err_dev);
-    else MS_LAUNCH(k_tables_a<false>, blocks, 256, 0, s, depths, lab, fnf, accum, ws, n, nlabels, tmin.p, tmax.p, st_sum,
-                   tcnt.p, kmin.p, kmax.p, (unsigned long long *)ws_count, err_dev);
+    const int tiles_x = (int)cdiv(cols, 64), ntiles = tiles_x * (int)cdiv(rows, 64);
+    if (acc) MS_LAUNCH(k_tables_a2<true>, ntiles, 256, 0, s, depths, lab, fnf, accum, ws, (int)rows, (int)cols, tiles_x, nlabels,
+                       tmin.p, tmax.p, st_sum, tcnt.p, kmin.p, kmax.p, (unsigned long long *)ws_count, err_dev);
+    else MS_LAUNCH(k_tables_a2<false>, ntiles, 256, 0, s, depths, lab, fnf, accum, ws, (int)rows, (int)cols, tiles_x, nlabels,
+                   tmin.p, tmax.p, st_sum, tcnt.p, kmin.p, kmax.p, (unsigned long long *)ws_count, err_dev);
     MS_LAUNCH(k_stats_finish<float>, gm, 256, 0, s, tmin.p, tmax.p, tcnt.p, st_min, st_max, st_count, m);
     prof_units(n);
     if (acc) MS_LAUNCH(k_tables_b<true>, blocks, 256, 0, s, lab, fnf, accum, n, nlabels, kmin.p, kmax.p, imin.p, imax.p);
@@ -858,13 +1048,13 @@ extern "C" {
  * label) — combine across bands with min / max / sum all-reduces.  Phase B: with the GLOBAL extremes, the smallest
  * global flat index holding each (INT64_MAX: not in this band) — combine with a min all-reduce. */
 int ms_band_tables_a_dev(const float *depths, const int32_t *labels, const double *fnf, const double *accum,
-                         const int32_t *wsheds, int64_t n, int64_t nlabels, double *st_min, double *st_max,
+                         const int32_t *wsheds, int64_t n, int64_t cols, int64_t nlabels, double *st_min, double *st_max,
                          double *st_sum, int64_t *st_count, int64_t *ws_count, double *vmin, double *vmax,
                          void *stream) {
     using namespace ms;
     MS_TRY(ensure_init());
     if (!depths || !labels || !fnf || !accum || !wsheds || !st_min || !st_max || !st_sum || !st_count || !ws_count ||
-        !vmin || !vmax || n < 1 || nlabels < 0) {
+        !vmin || !vmax || n < 1 || cols < 1 || n % cols || nlabels < 0) {
         set_error("band tables: bad argument");
         return MS_ERR_ARG;
     }
@@ -889,8 +1079,11 @@ int ms_band_tables_a_dev(const float *depths, const int32_t *labels, const doubl
     int64_t want = (n + 255) / 256;
     int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
     prof_units(n);
-    MS_LAUNCH(k_tables_a<true>, blocks, 256, 0, s, depths, labels, fnf, accum, wsheds, n, nlabels, tmin.p, tmax.p, st_sum,
-              tcnt.p, kmin.p, kmax.p, (unsigned long long *)ws_count, err.p);
+    (void)blocks;
+    const int64_t rows = n / cols;
+    const int tiles_x = (int)cdiv(cols, 64), ntiles = tiles_x * (int)cdiv(rows, 64);
+    MS_LAUNCH(k_tables_a2<true>, ntiles, 256, 0, s, depths, labels, fnf, accum, wsheds, (int)rows, (int)cols, tiles_x, nlabels,
+              tmin.p, tmax.p, st_sum, tcnt.p, kmin.p, kmax.p, (unsigned long long *)ws_count, err.p);
     MS_LAUNCH(k_stats_finish<float>, gm, 256, 0, s, tmin.p, tmax.p, tcnt.p, st_min, st_max, st_count, m);
     MS_LAUNCH(k_key_to_val, gm, 256, 0, s, kmin.p, vmin, m, 0);
     MS_LAUNCH(k_key_to_val, gm, 256, 0, s, kmax.p, vmax, m, 1);
