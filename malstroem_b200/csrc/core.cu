@@ -1,5 +1,7 @@
 // core.cu — library state: device selection, stream-ordered memory pool, error string, pinned flags.
 #include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <chrono>
@@ -9,6 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ms {
 
@@ -169,6 +172,46 @@ void *band_buf(ms_band *b, int slot, size_t bytes) {
     b->buf[slot] = p;
     b->cap[slot] = want;
     return p;
+}
+
+// ---- TMA tensor maps (tma.cuh) ---------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_encode_tried = 0;
+
+bool tma_map_2d(CUtensorMap *out, const void *base, int64_t rows, int64_t cols, int box_rows, int box_cols, bool is_float,
+                bool nan_fill) {
+    if (!g_encode_tried) {
+        g_encode_tried = 1;
+        const char *e = getenv("MS_TMA");
+        if (!(e && e[0] == '0')) {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+                q == cudaDriverEntryPointSuccess)
+                g_encode = (EncodeTiledFn)fn;
+            else
+                cudaGetLastError();
+        }
+    }
+    if (getenv("MS_TMA_DEBUG") && !g_encode) fprintf(stderr, "tma_map_2d: no cuTensorMapEncodeTiled entry point\n");
+    if (!g_encode || ((uintptr_t)base & 15) || (cols & 3) || ((box_cols * 4) & 15) || box_rows > 256 || box_cols > 256 ||
+        rows < 1 || cols < 1)
+        return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(out, is_float ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_INT32, 2, (void *)base,
+                          dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (getenv("MS_TMA_DEBUG"))
+        fprintf(stderr, "tma_map_2d(base %p, %lld x %lld, box %d x %d) -> CUresult %d\n", base, (long long)rows,
+                (long long)cols, box_rows, box_cols, (int)r);
+    return r == CUDA_SUCCESS;
 }
 
 int ensure_init() {

@@ -19,7 +19,10 @@
 //                     Claim: when the component reaches "outside", E is the catchment's
 //                     spill elevation.
 //   5. k_fill_final   filled = max(z, E[catchment]), depths = filled - z
+#include <string.h>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ms {
 
@@ -88,19 +91,39 @@ int minmax_dev(const float *z, int64_t n, float *out2, cudaStream_t s) {
 // GLOBAL index its tile-local root stands for: itself (a local minimum), 0 (raster border = "outside"), or - when
 // the root's lowest neighbour lies in another tile - that neighbour.  Only cells of the last kind still need global
 // pointer jumping; they are appended to `list` (catchments are ~50 cells, so that is a small fraction).
+// TMA = true: the tile + apron comes in with ONE cp.async.bulk.tensor.2d issued by thread 0 - a 66 x 72 box starting at
+// column c0 - 4 (the innermost box coordinate and width must be multiples of 16 bytes: measured with tools/tma_probe.cu,
+// a start at c0 - 1 raises an illegal-instruction fault); cells outside the raster arrive as NaN, which no comparison
+// below selects - the same effect as the +inf the LDG -> STS form stores for them.
+constexpr int DT_LD_TMA = FT + 8, DT_X0_TMA = 4;
+template <bool TMA>
 __global__ void __launch_bounds__(256) k_descent_tile(const float *__restrict__ z, int *__restrict__ ptr, int rows,
-                                                      int cols, int tiles_x, int open, int *list, int *n_list) {
-    __shared__ float sz[(FT + 2) * (FT + 2)];
+                                                      int cols, int tiles_x, int open, int *list, int *n_list,
+                                                      const __grid_constant__ CUtensorMap zmap) {
+    constexpr int LD = TMA ? DT_LD_TMA : FT + 2;
+    constexpr int X0 = TMA ? DT_X0_TMA : 1;          // shared column of the tile's first cell
+    __shared__ __align__(128) float sz[(FT + 2) * LD];
     __shared__ unsigned short sp[FT * FT];
     __shared__ int tgt[FT * FT];          // per tile-local root: >= 0 final global index, < 0: -(1 + cell in another tile)
+    __shared__ uint64_t bar;
     int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     int r0 = ty * FT, c0 = tx * FT, tid = threadIdx.x;
-    for (int k = tid; k < (FT + 2) * (FT + 2); k += 256) {
-        int lr = k / (FT + 2), lc = k - lr * (FT + 2);
-        int r = r0 + lr - 1, c = c0 + lc - 1;
-        sz[k] = (r >= 0 && r < rows && c >= 0 && c < cols) ? z[(size_t)r * cols + c] : INFINITY;
+    if (TMA) {
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, (unsigned)sizeof(sz));
+            tma_load_2d(sz, &zmap, &bar, c0 - DT_X0_TMA, r0 - 1);
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        for (int k = tid; k < (FT + 2) * (FT + 2); k += 256) {
+            int lr = k / (FT + 2), lc = k - lr * (FT + 2);
+            int r = r0 + lr - 1, c = c0 + lc - 1;
+            sz[k] = (r >= 0 && r < rows && c >= 0 && c < cols) ? z[(size_t)r * cols + c] : INFINITY;
+        }
+        __syncthreads();
     }
-    __syncthreads();
 #pragma unroll 4
     for (int u = 0; u < 16; u++) {
         int k = tid + 256 * u;
@@ -113,7 +136,7 @@ __global__ void __launch_bounds__(256) k_descent_tile(const float *__restrict__ 
             if ((r == 0 && !(open & 1)) || c == 0 || (r == rows - 1 && !(open & 2)) || c == cols - 1) {
                 t = 0;                                   // raster border: points at "outside" (cell 0)
             } else {
-                float bz = sz[(lr + 1) * (FT + 2) + lc + 1];
+                float bz = sz[(lr + 1) * LD + lc + X0];
                 int bi = i, bdr = 0, bdc = 0;
 #pragma unroll
                 for (int dr = -1; dr <= 1; dr++)
@@ -122,7 +145,7 @@ __global__ void __launch_bounds__(256) k_descent_tile(const float *__restrict__ 
                         if (dr == 0 && dc == 0) continue;
                         if (r + dr < 0 || r + dr >= rows) continue;
                         int j = i + dr * cols + dc;
-                        float zj = sz[(lr + 1 + dr) * (FT + 2) + lc + 1 + dc];
+                        float zj = sz[(lr + 1 + dr) * LD + lc + X0 + dc];
                         if (zj < bz || (zj == bz && j < bi)) { bz = zj; bi = j; bdr = dr; bdc = dc; }
                     }
                 int tr = lr + bdr, tc = lc + bdc;
@@ -352,7 +375,13 @@ static int descent_resolve(const float *dem, int *lab, int *scratch, int64_t row
     MS_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int), s));
     int tiles_x = (int)cdiv(cols, FT), tiles_y = (int)cdiv(rows, FT);
     prof_units(rows * cols);
-    MS_LAUNCH(k_descent_tile, tiles_x * tiles_y, 256, 0, s, dem, lab, (int)rows, (int)cols, tiles_x, open, scratch, cnt.p);
+    CUtensorMap zmap;
+    memset(&zmap, 0, sizeof(zmap));
+    // (a band's rows sit inside a raster with halo rows: it keeps the LDG -> STS form)
+    if (!open && tma_map_2d(&zmap, dem, rows, cols, FT + 2, DT_LD_TMA, true, true))
+        MS_LAUNCH(k_descent_tile<true>, tiles_x * tiles_y, 256, 0, s, dem, lab, (int)rows, (int)cols, tiles_x, open, scratch, cnt.p, zmap);
+    else
+        MS_LAUNCH(k_descent_tile<false>, tiles_x * tiles_y, 256, 0, s, dem, lab, (int)rows, (int)cols, tiles_x, open, scratch, cnt.p, zmap);
     int64_t *h = host_flags().h;
     MS_CUDA(cudaMemcpyAsync(h, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));

@@ -39,6 +39,7 @@
 #include <unistd.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -873,30 +874,51 @@ constexpr int NI_A = NF_T + 4;          // tile + 2-cell apron
 // Dg — lake / flat cell: its distance above F in ulps (D_INF: not reached yet), anything else: D_WALL — and
 // tmeta[tile] = the binade range of the lake cells of the tile and its apron; *irbad is raised when a cell or tile
 // does not qualify for the integer form.
+// TMA = true (single GPU, raster describable by a tensor map): z and F of the tile + 2-cell apron arrive as two
+// 68 x 72 boxes (cp.async.bulk.tensor.2d from column c0 - 4, see tma.cuh; NaN outside the raster - fminf ignores it
+// like the +inf of the LDG -> STS form, and no cell outside the raster is ever read as a source).
+constexpr int NI_LD_TMA = NF_T + 8;
+template <bool TMA>
 __global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ z, const float *__restrict__ F,
                                                       double *__restrict__ W, int *tileflag, int *tilesides, NfCtl *ctl,
                                                       int rows, int cols, int tiles_x, double sh, double dg, double capB,
                                                       int *__restrict__ Dg, int P, int *tmeta, int *irbad, int open,
                                                       const uint8_t *__restrict__ fix_top,
-                                                      const uint8_t *__restrict__ fix_bot) {
+                                                      const uint8_t *__restrict__ fix_bot,
+                                                      const __grid_constant__ CUtensorMap zmap,
+                                                      const __grid_constant__ CUtensorMap fmap) {
+    constexpr int LDZ = TMA ? NI_LD_TMA : NI_A;       // shared row stride of z / F
+    constexpr int XO = TMA ? 2 : 0;                   // shared column of raster column c0 - 2
     // Row band (open != 0): z and F have a halo row above / below the band where it is open; whether a cell of a
     // halo row is fixed would need a second halo row, so the neighbour says (fix_top / fix_bot, k_band_edgefix).
     const int rlo = (open & 1) ? -1 : 0, rhi = rows + ((open & 2) ? 1 : 0);
-    __shared__ float sz[NI_A * NI_A], sf[NI_A * NI_A];
+    __shared__ __align__(128) float sz[NI_A * LDZ], sf[NI_A * LDZ];
+    __shared__ uint64_t bar;
     __shared__ unsigned char fixedc[(NF_T + 2) * (NF_T + 2)];      // 1: W = z there for good (seed or raster border)
     __shared__ int s_sides, s_elo, s_ehi, s_bad;
     int tile = blockIdx.x;
     int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     int r0 = ty * NF_T, c0 = tx * NF_T, tid = threadIdx.x;
     if (tid == 0) { s_sides = 0; s_elo = INT_MAX; s_ehi = INT_MIN; s_bad = 0; }
-    for (int k = tid; k < NI_A * NI_A; k += 256) {
-        int lr = k / NI_A, lc = k - lr * NI_A;
-        int r = r0 + lr - 2, c = c0 + lc - 2;
-        bool in = r >= rlo && r < rhi && c >= 0 && c < cols;
-        sz[k] = in ? z[(long long)r * cols + c] : INFINITY;
-        sf[k] = in ? F[(long long)r * cols + c] : INFINITY;
+    if (TMA) {
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, (unsigned)(2 * sizeof(sz)));
+            tma_load_2d(sz, &zmap, &bar, c0 - 4, r0 - 2);
+            tma_load_2d(sf, &fmap, &bar, c0 - 4, r0 - 2);
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        for (int k = tid; k < NI_A * NI_A; k += 256) {
+            int lr = k / NI_A, lc = k - lr * NI_A;
+            int r = r0 + lr - 2, c = c0 + lc - 2;
+            bool in = r >= rlo && r < rhi && c >= 0 && c < cols;
+            sz[k] = in ? z[(long long)r * cols + c] : INFINITY;
+            sf[k] = in ? F[(long long)r * cols + c] : INFINITY;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     for (int k = tid; k < (NF_T + 2) * (NF_T + 2); k += 256) {
         int lr = k / (NF_T + 2), lc = k - lr * (NF_T + 2);          // ring coordinates: cell (r0 + lr - 1, c0 + lc - 1)
         int r = r0 + lr - 1, c = c0 + lc - 1;
@@ -906,17 +928,17 @@ __global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ 
             else if (r >= rows) fx = fix_bot[c];
             else if ((r == 0 && !(open & 1)) || c == 0 || (r == rows - 1 && !(open & 2)) || c == cols - 1) fx = 1;
             else {
-                const float *pf = sf + (lr + 1) * NI_A + (lc + 1);
+                const float *pf = sf + (lr + 1) * LDZ + (lc + 1) + XO;
                 float f = *pf;
-                float m = fminf(fminf(fminf(pf[-NI_A - 1], pf[-NI_A]), fminf(pf[-NI_A + 1], pf[-1])),
-                                fminf(fminf(pf[1], pf[NI_A - 1]), fminf(pf[NI_A], pf[NI_A + 1])));
-                fx = (f == sz[(lr + 1) * NI_A + (lc + 1)]) && (m < f);
+                float m = fminf(fminf(fminf(pf[-LDZ - 1], pf[-LDZ]), fminf(pf[-LDZ + 1], pf[-1])),
+                                fminf(fminf(pf[1], pf[LDZ - 1]), fminf(pf[LDZ], pf[LDZ + 1])));
+                fx = (f == sz[(lr + 1) * LDZ + (lc + 1) + XO]) && (m < f);
             }
         }
         fixedc[k] = fx;
         if (Dg && !fx && r >= rlo && r < rhi && c >= 0 && c < cols) {
             // a lake cell of the tile or its apron: its binade counts for the tile's weight table
-            float f = sf[(lr + 1) * NI_A + (lc + 1)];
+            float f = sf[(lr + 1) * LDZ + (lc + 1) + XO];
             if (f == 0.f) atomicOr(&s_bad, 1);
             else {
                 int e = nf_binade((double)f);
@@ -936,7 +958,7 @@ __global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ 
             continue;
         }
         const unsigned char *fx = fixedc + (lr + 1) * (NF_T + 2) + (lc + 1);
-        const float *pz = sz + (lr + 2) * NI_A + (lc + 2);
+        const float *pz = sz + (lr + 2) * LDZ + (lc + 2) + XO;
         double w;
         if (*fx) {
             w = (double)*pz;
@@ -948,10 +970,10 @@ __global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ 
                 for (int dc = -1; dc <= 1; dc++) {
                     if (dr == 0 && dc == 0) continue;
                     if (!fx[dr * (NF_T + 2) + dc]) continue;
-                    double cand = __dadd_rn((double)pz[dr * NI_A + dc], (dr != 0 && dc != 0) ? dg : sh);
+                    double cand = __dadd_rn((double)pz[dr * LDZ + dc], (dr != 0 && dc != 0) ? dg : sh);
                     best = dmin2(best, cand);
                 }
-            w = (best <= (double)sf[(lr + 2) * NI_A + (lc + 2)] + capB) ? best : (double)INFINITY;
+            w = (best <= (double)sf[(lr + 2) * LDZ + (lc + 2) + XO] + capB) ? best : (double)INFINITY;
             nonseed++;
             sides |= (lr == 0 ? 1 : 0) | (lr == NF_T - 1 || r == rows - 2 ? 2 : 0) | (lc == 0 ? 4 : 0) |
                      (lc == NF_T - 1 || c == cols - 2 ? 8 : 0);
@@ -960,7 +982,7 @@ __global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ 
         if (Dg) {
             int bad = 0, elo = 0, ehi = 0, dmax = 0;
             unsigned char e8;
-            Dg[(size_t)(r + 1) * P + (c + 4)] = nf_to_int(w, sf[(lr + 2) * NI_A + (lc + 2)], bad, elo, ehi, dmax, &e8);
+            Dg[(size_t)(r + 1) * P + (c + 4)] = nf_to_int(w, sf[(lr + 2) * LDZ + (lc + 2) + XO], bad, elo, ehi, dmax, &e8);
             if (bad) atomicOr(&s_bad, 1);
         }
     }
@@ -1782,10 +1804,20 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
             MS_LAUNCH(k_ir_frame, cdiv(2 * (int64_t)P + 8 * (int64_t)inner_rows, 256), 256, 0, s, Dg.p, P, inner_rows);
             MS_CUDA(cudaMemsetAsync(irbad.p, 0, sizeof(int), s));
         }
-        if (cap)
-            MS_LAUNCH(k_nf_init_tile, ntiles, 256, 0, s, dtm, filled, out, tileflag.p, tilesides.p, ctl.p, (int)rows,
-                      (int)cols, tiles_x, sh, dg, cap_bound, ir ? Dg.p : (int *)nullptr, P, tmeta.p, irbad.p, 0,
-                      (const uint8_t *)nullptr, (const uint8_t *)nullptr);
+        if (cap) {
+            CUtensorMap zmap, fmap;
+            memset(&zmap, 0, sizeof(zmap));
+            memset(&fmap, 0, sizeof(fmap));
+            if (tma_map_2d(&zmap, dtm, rows, cols, NI_A, NI_LD_TMA, true, true) &&
+                tma_map_2d(&fmap, filled, rows, cols, NI_A, NI_LD_TMA, true, true))
+                MS_LAUNCH(k_nf_init_tile<true>, ntiles, 256, 0, s, dtm, filled, out, tileflag.p, tilesides.p, ctl.p, (int)rows,
+                          (int)cols, tiles_x, sh, dg, cap_bound, ir ? Dg.p : (int *)nullptr, P, tmeta.p, irbad.p, 0,
+                          (const uint8_t *)nullptr, (const uint8_t *)nullptr, zmap, fmap);
+            else
+                MS_LAUNCH(k_nf_init_tile<false>, ntiles, 256, 0, s, dtm, filled, out, tileflag.p, tilesides.p, ctl.p, (int)rows,
+                          (int)cols, tiles_x, sh, dg, cap_bound, ir ? Dg.p : (int *)nullptr, P, tmeta.p, irbad.p, 0,
+                          (const uint8_t *)nullptr, (const uint8_t *)nullptr, zmap, fmap);
+        }
         else
             MS_LAUNCH(k_nf_init, g2, 256, 0, s, dtm, filled, out, banned.p, tileflag.p, tilesides.p, ctl.p, (int)rows,
                       (int)cols, tiles_x, 0);
@@ -2194,9 +2226,11 @@ int ms_band_nf_ir_prepare_dev(ms_band *B, const float *dem, const float *filled,
     if (B->nf_rank == 0) MS_CUDA(cudaMemsetAsync(base + L.off_gactive, 0, sizeof(int), s));
     MS_LAUNCH(k_ir_frame, cdiv(2 * (int64_t)P + 8 * (int64_t)inner_rows, 256), 256, 0, s, Dg, P, inner_rows);
     prof_units(B->rows * B->cols);
-    MS_LAUNCH(k_nf_init_tile, nb.ntiles, 256, 0, s, dem, filled, (double *)nullptr, nb.tileflag, nb.tilesides, nb.ctl,
+    CUtensorMap nomap;
+    memset(&nomap, 0, sizeof(nomap));
+    MS_LAUNCH(k_nf_init_tile<false>, nb.ntiles, 256, 0, s, dem, filled, (double *)nullptr, nb.tileflag, nb.tilesides, nb.ctl,
               (int)B->rows, (int)B->cols, nb.tiles_x, short_eps, diag_eps, cap_bound, Dg, P, tmeta, irbad, B->open, fix_top,
-              fix_bot);
+              fix_bot, nomap, nomap);
     MS_LAUNCH(k_band_ir_publish, dim3(cdiv(P, 256), 2), 256, 0, s, Dg, P, (int)B->rows, (const NfP2P *)B->nf_pp_dev);
     MS_LAUNCH(k_nf_compact, cdiv(nb.ntiles, 256), 256, 0, s, nb.tileflag, nb.ring, nb.ctl, nb.ntiles);
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
