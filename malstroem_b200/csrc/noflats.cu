@@ -1190,6 +1190,9 @@ __device__ __forceinline__ void ir_sweep(int *sd, const unsigned char *se, IrSha
         // region, which costs more than the reduction (measured at 8192^2 / 32768^2: 4.03 / 41.5 ms against 4.46 / 43.8;
         // plain predicated stores with the sweeps restarted on the first changed line: 4.07 / 42.0 and more rounds)
 #if IR_UNCOND
+        // (tried and dropped: skipping the two reductions on lines no lane improves - a vote and a uniform branch per
+        // step - and plain stores when only one direction sweeps: 3.37 -> 4.00 ms at 8192^2, 38.6 -> 45.1 ms at 32768^2;
+        // the branch costs the step more scheduling freedom than the reductions cost LSU time)
         atomicMin(pa, chA ? candA : 0x7fffffff);
         atomicMin(pb, chB ? candB : 0x7fffffff);
 #elif IR_PLAIN
@@ -1442,8 +1445,15 @@ __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__r
                         // the tile lies in the neighbouring band: its flag word and FIFO are on another GPU
                         const NfPeer &q = y < 0 ? pp->up : pp->down;
                         if (q.tileflag) {
+#ifdef NF_STATS
+                            unsigned long long tq0 = gtimer();
+#endif
                             int nbq = (y < 0 ? q.tiles_y - 1 : 0) * tiles_x + x;
                             if (atomicOr_system(q.tileflag + nbq, bits) == 0) nf_push(q.ring, q.cap, q.ctl, nbq, true, pp->gactive);
+#ifdef NF_STATS
+                            atomicAdd(&g_nf_dbg[0], 1ull);
+                            atomicAdd(&g_nf_dbg[1], gtimer() - tq0);
+#endif
                         }
                     }
                 }

@@ -8,23 +8,27 @@ from malstroem_b200.pipeline import synth_fractal
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 binms = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
+C = int(sys.argv[3]) if len(sys.argv) > 3 else S          # columns (rows = S): a band-shaped raster
+R0 = int(sys.argv[4]) if len(sys.argv) > 4 else 0         # first row of the window in the synthetic terrain
 L = _lib.lib(); L.ms_init(0)
 raw = ctypes.CDLL(_lib.LIB_PATH)
 dev = torch.device("cuda", 0)
-dem = synth_fractal(S, S, seed=1)
+dem = synth_fractal(S, C, seed=1, row0=R0)
 filled = torch.empty_like(dem); depths = torch.empty_like(dem)
-fnf = torch.empty((S, S), dtype=torch.float64, device=dev)
+fnf = torch.empty((S, C), dtype=torch.float64, device=dev)
 sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-assert L.ms_fill_terrain_dev(dem.data_ptr(), filled.data_ptr(), depths.data_ptr(), S, S, sp) == 0
+assert L.ms_fill_terrain_dev(dem.data_ptr(), filled.data_ptr(), depths.data_ptr(), S, C, sp) == 0
 mv = np.float64(float(dem.abs().max())); sh = float((np.nextafter(mv, np.inf) - mv) * 1024); dg = sh * 2 ** 0.5
 nflog = raw.ms_nf_log
 nflog.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 for rep in range(3):
     nflog(None, None, 1)
     st = (ctypes.c_int64 * 8)()
-    rc = L.ms_fill_terrain_no_flats_dev(dem.data_ptr(), filled.data_ptr(), sh, dg, fnf.data_ptr(), S, S, st, sp)
+    import time as _t
+    torch.cuda.synchronize(); _t0 = _t.perf_counter()
+    rc = L.ms_fill_terrain_no_flats_dev(dem.data_ptr(), filled.data_ptr(), sh, dg, fnf.data_ptr(), S, C, st, sp)
     assert rc == 0, L.ms_last_error()
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(); print('no-flats stage wall %.2f ms, visits %d' % ((_t.perf_counter() - _t0) * 1e3, st[1]))
 log = np.zeros(4 * 262144, dtype=np.uint64)
 nl = ctypes.c_uint(0)
 nflog(log.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nl), 0)
