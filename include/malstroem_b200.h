@@ -404,6 +404,22 @@ int ms_tiff_decode_dev(const void *in, const uint64_t *in_off, const uint32_t *i
                        int64_t rows, int64_t cols, int subst_mode, double nodata, double subst, int compressed,
                        void *stream);
 
+/* ---- label polygonisation.  Replaces vector.py:42-87 (vectorize_labels_file), i.e.
+ * gdal.Polygonize(band, band.GetMaskBand(), layer, 0, ['8CONNECTED=8']): one polygon per 8-connected (connect8 = 0:
+ * 4-connected) region of equal cell value, cells equal to `nodata` (has_nodata != 0) in none.  The rings stay on the
+ * device; counts3[0..2] = rings, vertices, boundary edges.  ms_polygonize_fetch copies them to caller-allocated host
+ * arrays and releases them: ring k owns vertices [off[k], off[k+1]) (lattice corners: row 0..rows, col 0..cols; only
+ * the corners of the outline, without a repeated closing vertex; the region lies on the right-hand side walking the
+ * ring on the screen), ring_value = the cells' value, ring_cell = a cell of the ring's region touching it,
+ * ring_region = the first cell of the region in raster order (the same for an exterior ring and its holes),
+ * ring_hole = 1 for a hole.  Rings come ordered by their first boundary cell in raster order. */
+int ms_polygonize_dev(const int32_t *labels, int64_t rows, int64_t cols, int connect8, int has_nodata, int32_t nodata,
+                      int64_t *counts3, void *stream);
+int ms_polygonize(const int32_t *labels, int64_t rows, int64_t cols, int connect8, int has_nodata, int32_t nodata,
+                  int64_t *counts3);
+int ms_polygonize_fetch(int64_t *ring_vertex_offset, int32_t *ring_value, int64_t *ring_cell, int64_t *ring_region,
+                        uint8_t *ring_hole, int32_t *vertex_row, int32_t *vertex_col);
+
 #ifdef __cplusplus
 }
 #endif

@@ -283,6 +283,9 @@ struct HostCall {
     }
 };
 
+// polygon.cu: frees the rings held for ms_polygonize_fetch
+void poly_release();
+
 // internal device-pointer stage entry points used by the pipeline (pipeline.cu)
 int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_t rows, int64_t cols,
                           int64_t *stats, cudaStream_t s);

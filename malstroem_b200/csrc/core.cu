@@ -334,6 +334,7 @@ int ms_shutdown(void) {
     if (ms::g_device < 0) return MS_OK;
     cudaDeviceSynchronize();
     ms::cache_clear_all();
+    ms::poly_release();
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, ms::g_device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     if (ms::g_blocks.empty() && ms::g_arena) {

@@ -5,6 +5,7 @@ enable() rebinds the twelve whole-function names the tool layer resolves at call
 (malstroem/dem.py:67-89, malstroem/bluespots.py:159-205, malstroem/scripts/dem.py, scripts/bluespot.py) on the
 reference's own `malstroem.algorithms.{fill,flow,label}` modules to the B200 implementations, and leaves
 `malstroem.algorithms.speedups.enabled` truthy so the tools do not warn (dem.py:62, bluespots.py:154).
+Beyond the twelve: the §8(f) rows that are built (pour-point network, Network.rain_event, vectorize_labels_file).
 Nothing else of the reference is touched; disable() restores the saved originals.
 """
 import os
@@ -14,6 +15,7 @@ from . import _lib
 import importlib
 
 from . import network as _network
+from . import vector as _vector
 from .algorithms import fill as _fill, flow as _flow, label as _label, net as _net
 
 available = os.path.exists(_lib.LIB_PATH)
@@ -67,6 +69,15 @@ def enable(target=None):
         cls.rain_event = _rain_event_on_reference_instance
     except (ImportError, AttributeError, KeyError):
         pass
+    # BluespotTool binds vectorize_labels_file by name at import (bluespots.py:17, used at
+    # bluespots.py:179,192), so it is replaced on both modules
+    for refmod in ("vector", "bluespots"):
+        try:
+            mod = importlib.import_module(target.__name__.split(".")[0] + "." + refmod)
+            _orig[(refmod, "vectorize_labels_file")] = (mod, mod.__dict__["vectorize_labels_file"])
+            mod.vectorize_labels_file = _vector.vectorize_labels_file
+        except (ImportError, KeyError):
+            pass
     ref_speedups = getattr(target, "speedups", None)
     if ref_speedups is not None:
         _orig[("speedups", "enabled")] = (ref_speedups, ref_speedups.enabled)

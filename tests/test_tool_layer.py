@@ -80,3 +80,33 @@ def test_complete_on_b200_path_equals_reference(dtm188, filt, accum, nlabels, ne
                 assert (a is None) == (b is None), (nid, key)
                 if b is not None:
                     assert abs(a - b) <= 1e-6 * abs(b) + 1e-9, (nid, key, a, b)
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_bluespot_tool_vector_outputs(dtm188, tmp_path):
+    """§8(f4): the unchanged BluespotTool with its vector outputs on (bluespots.py:177-193): the polygons come from
+    the device path, one per 8-connected region of the rasters it wrote, and rasterise back to exactly those rasters"""
+    from malstroem_b200 import speedups
+    from oracle import polygonize as P
+    toolchain.import_reference()
+    speedups.enable()
+    try:
+        out = toolchain.run_bluespots_with_vectors(dtm188["depths"], dtm188["flowdir_noflats"], dtm188["dtm"], str(tmp_path))
+    finally:
+        speedups.disable()
+    gt = toolchain.DTM188_TRANSFORM
+    for raster, feats, key in ((out["bluespots"], out["bluespots_vector"], "bspot_id"),
+                               (out["watersheds"], out["watersheds_vector"], "bspot_id")):
+        ref = P.polygonize(raster, nodata=0)          # the label writers carry nodata 0: no polygon for the background
+        assert len(feats) == len(ref) and len(feats) >= int(raster.max())
+        polys = []
+        for f in feats:
+            rings = []
+            for ring in f["geometry"]["coordinates"]:
+                assert ring[0] == ring[-1]
+                rings.append([(int(round((y - gt[3]) / gt[5])), int(round((x - gt[0]) / gt[1]))) for x, y in ring[:-1]])
+            polys.append({"value": f["properties"][key], "region": 0, "rings": rings})
+        back, twice, _ = P.rasterize(polys, raster.shape, 0)
+        assert twice == 0 and np.array_equal(back, raster)
+    assert int(out["bluespots"].max()) == 523         # no filter: tests/test_commandline.py:43

@@ -88,6 +88,35 @@ def parse_filter(text):
     return eval('lambda stats: {}'.format(expr))
 
 
+class FileRaster(MemRaster):
+    """A writer that also leaves a GeoTIFF behind (BluespotTool vectorises from `filepath`, bluespots.py:179,192)."""
+
+    def __init__(self, filepath, transform=DTM188_TRANSFORM):
+        MemRaster.__init__(self, None, transform)
+        self.filepath = filepath
+
+    def write(self, data):
+        from malstroem_b200 import io as mio
+        self.data = data
+        # nodata 0 as scripts/complete.py:83-85 and scripts/bluespot.py:44,79 create the label writers
+        mio.RasterWriter(self.filepath, tuple(self.transform), "EPSG:25832", 0).write(data)
+
+
+def run_bluespots_with_vectors(depths, flowdir, dem_array, tmpdir, filter_text=None, transform=DTM188_TRANSFORM):
+    """BluespotTool with the `-vector` outputs of `malstroem bluespots` (scripts/bluespot.py) switched on."""
+    _, _, bluespots, _, _ = import_reference()
+    labeled = FileRaster(os.path.join(tmpdir, "bluespots.tif"), transform)
+    wsheds = FileRaster(os.path.join(tmpdir, "wsheds.tif"), transform)
+    labeled_vec, wsheds_vec, pourpoints = MemVector(), MemVector(), MemVector()
+    bluespots.BluespotTool(input_depths=MemRaster(depths, transform), input_flowdir=MemRaster(flowdir, transform),
+                           input_bluespot_filter_function=parse_filter(filter_text), input_accum=None,
+                           input_dem=MemRaster(dem_array, transform), output_labeled_raster=labeled,
+                           output_labeled_vector=labeled_vec, output_pourpoints=pourpoints,
+                           output_watersheds_raster=wsheds, output_watersheds_vector=wsheds_vec).process()
+    return dict(bluespots=labeled.data, watersheds=wsheds.data, bluespots_vector=labeled_vec.features,
+                watersheds_vector=wsheds_vec.features)
+
+
 def run_complete(dem_array, rain_mm, filter_text=None, accum=False, transform=DTM188_TRANSFORM, streams_geometry=True):
     """The tool sequence of `malstroem complete` (scripts/complete.py:57-127) on in-memory rasters.  Returns dict of
     every raster and feature list the command would write."""
