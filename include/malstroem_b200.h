@@ -187,6 +187,11 @@ int ms_band_nf_solve_dev(ms_band *band, const float *dem, const float *filled, d
                          void *stream);
 int ms_band_nf_verify_dev(ms_band *band, const float *dem, const double *fnf, double short_eps, double diag_eps,
                           int64_t *nviol, void *stream);
+/* seed repair (the retry loop of fill.fill_terrain_no_flats' device form, here per band): reset != 0 forgets the
+ * band's ban map; otherwise the stencil runs on fnf, every failing cell is added to the ban map (ms_band_nf_init_dev
+ * then treats it as a lake cell, not as a seed) and their count is returned. */
+int ms_band_nf_ban_dev(ms_band *band, const float *dem, const double *fnf, double short_eps, double diag_eps, int reset,
+                       int64_t *nviol, void *stream);
 /* The same solve fused over NVLink peer memory: every band's solver kernel runs at the same time and the bands feed
  * each other's tile queues and halo rows directly (system-scope atomics and stores into blocks mapped through CUDA
  * IPC), instead of one host-driven halo exchange per crossing of a band edge.  create: allocates the band's shared

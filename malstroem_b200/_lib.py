@@ -74,6 +74,7 @@ SIGNATURES = {
     "ms_band_nf_init_dev": (c_int, [c_p, c_p, c_p, c_p, c_p, c_p]),
     "ms_band_nf_solve_dev": (c_int, [c_p, c_p, c_p, c_p, c_dbl, c_dbl, c_dbl, c_int, c_int, c_int, c_p, c_p]),
     "ms_band_nf_verify_dev": (c_int, [c_p, c_p, c_p, c_dbl, c_dbl, c_p, c_p]),
+    "ms_band_nf_ban_dev": (c_int, [c_p, c_p, c_p, c_dbl, c_dbl, c_int, c_p, c_p]),
     "ms_band_nf_shared_create": (c_int, [c_p, c_p]),
     "ms_band_nf_shared_open": (c_int, [c_p, c_int, c_int, c_p, c_p]),
     "ms_band_nf_seedcand_dev": (c_int, [c_p, c_p, c_p, c_dbl, c_dbl, c_dbl, c_p]),

@@ -203,10 +203,13 @@ class BandPipeline(object):
                ("flowdir", torch.uint8, True), ("accum", torch.float64, False), ("labels", torch.int32, False),
                ("wsheds", torch.int32, False))
 
-    def __init__(self, rows, cols, comm, device=0):
+    def __init__(self, rows, cols, comm, device=0, eps=None):
+        """eps: optional (short, diag) for the no-flats fill instead of fill.minimum_safe_short_and_diag's values
+        (fill_terrain_no_flats takes them as arguments, fill.py:174)."""
         if not torch.cuda.is_available():
             raise RuntimeError("malstroem_b200.bands needs a CUDA device (there is no CPU fallback)")
         self.R, self.cols, self.comm = int(rows), int(cols), comm
+        self.eps = eps
         self.device = torch.device("cuda", device) if not isinstance(device, torch.device) else device
         self.r0, self.r1 = band_rows(self.R, comm.size)[comm.rank]
         self.rows = self.r1 - self.r0
@@ -337,6 +340,8 @@ class BandPipeline(object):
         maxval = np.float64(max(abs(np.float32(hi.item())), abs(np.float32(lo.item()))))
         self.short = float((np.nextafter(maxval, np.inf) - maxval) * 1024.0)
         self.diag = float(self.short * 2 ** 0.5)
+        if self.eps is not None:
+            self.short, self.diag = float(self.eps[0]), float(self.eps[1])
         self._tick("minmax")
         # K5/K6 phase 1 (needs the depths only): its host-side merge then overlaps the no-flats solver kernel
         self._cc_allr = None
@@ -389,7 +394,9 @@ class BandPipeline(object):
             return
         if self.p2p and self._noflats_p2p(st):
             return
-        for cap in (1, 0):
+        self._call("ms_band_nf_ban_dev", self.h, None, None, 0.0, 0.0, 1, None, st)      # no bans from an earlier run
+
+        def attempt(cap):
             ns = i64(0)
             self._call("ms_band_nf_init_dev", self.h, _p(self.dem), _p(self.out["filled"]), _p(self.out["fnf"]),
                        ctypes.byref(ns), st)
@@ -425,10 +432,22 @@ class BandPipeline(object):
             bad = comm.all_reduce(torch.tensor([nv.value], dtype=torch.int64, device=dev), "sum")
             self._tick("nf_verify")
             self.stats.update(noflat_exchanges=sweeps, noflat_tile_visits=total_visits, noflat_capped=cap)
-            if int(bad.item()) == 0:
+            return int(bad.item())
+
+        for cap in (1, 0):
+            if attempt(cap) == 0:
                 return
-        raise RuntimeError("band no-flats fill: the fixed-point verification failed (seed repair is not available in "
-                           "band mode)")
+        # Seed repair, as on one GPU (fill_no_flats_dev_impl): a "seed" the stencil rejects (the lake next to it has
+        # risen above it) is banned - relaxed like a lake cell from then on - and the uncapped solve is repeated.
+        # Every band bans its own cells; the decision to go on is taken on the all-reduced count.
+        for repairs in range(1, 1001):
+            nv = i64(0)
+            self._call("ms_band_nf_ban_dev", self.h, _p(self.dem), _p(self.out["fnf"]), self.short, self.diag, 0,
+                       ctypes.byref(nv), st)
+            self.stats["noflat_repairs"] = repairs
+            if attempt(0) == 0:
+                return
+        raise RuntimeError("band no-flats fill: seed verification did not settle")
 
     def _noflats_ir(self, st):
         """The capped solve on the integer raster (the single-GPU solver k_nf_solve_ir), every band's kernel running
@@ -784,7 +803,7 @@ class BandPipeline(object):
         return self.rows * self.cols * per_cell + (self.nlabels + 1) * per_label
 
 
-def run_threaded(dem, nbands, device=0, after=None):
+def run_threaded(dem, nbands, device=0, after=None, eps=None):
     """One process, one GPU, `nbands` bands as threads (the decomposition without NCCL): returns the BandPipelines
     after the run.  `dem`: cuda float32 tensor [rows, cols].  `after(pipeline)`, if given, runs in every band's
     thread after the run (for calls that communicate, like `network`); its result is kept in `p.after_result`."""
@@ -795,7 +814,7 @@ def run_threaded(dem, nbands, device=0, after=None):
     def work(rank):
         try:
             torch.cuda.set_device(device)
-            p = BandPipeline(rows, cols, ThreadComm(grp, rank), device=device)
+            p = BandPipeline(rows, cols, ThreadComm(grp, rank), device=device, eps=eps)
             pipes[rank] = p
             p.dem.copy_(dem[p.r0:p.r1])
             p.run()

@@ -1935,12 +1935,43 @@ int ms_band_nf_init_dev(ms_band *B, const float *dem, const float *filled, doubl
     MS_CUDA(cudaMemsetAsync(nb.tilesides, 0, (size_t)nb.ntiles * sizeof(int), s));
     MS_CUDA(cudaMemsetAsync(nb.ctl, 0, sizeof(NfCtl), s));
     dim3 g2(cdiv(B->cols, 64), cdiv(B->rows, 4));
-    MS_LAUNCH(k_nf_init, g2, 256, 0, s, dem, filled, fnf, (const uint8_t *)nullptr, nb.tileflag, nb.tilesides, nb.ctl,
-              (int)B->rows, (int)B->cols, nb.tiles_x, B->open);
+    MS_LAUNCH(k_nf_init, g2, 256, 0, s, dem, filled, fnf, B->nf_ban ? (const uint8_t *)B->buf[BB_NF_BANNED] : (const uint8_t *)nullptr,
+              nb.tileflag, nb.tilesides, nb.ctl, (int)B->rows, (int)B->cols, nb.tiles_x, B->open);
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
     MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
     MS_TRY(ms::stream_sync(s));
     if (nonseed) *nonseed = h->nonseed;
+    return MS_OK;
+}
+
+/* Seed repair in band mode (the single-GPU loop of fill_no_flats_dev_impl): a seed is a dry cell with a strictly lower
+ * filled neighbour, taken as W = z; next to a lake whose surface has risen above it by the time the wave arrives that
+ * is wrong, the stencil fails there, and the cell has to be relaxed like a lake cell.  reset != 0: forget the band's
+ * ban map (start of a stage).  Otherwise: run the verification stencil (incl. halo rows) on fnf, mark every failing
+ * cell in the ban map (kept across calls, so bans accumulate) and return the count; ms_band_nf_init_dev then treats
+ * the marked cells as non-seeds. */
+int ms_band_nf_ban_dev(ms_band *B, const float *dem, const double *fnf, double short_eps, double diag_eps, int reset,
+                       int64_t *nviol, void *stream) {
+    using namespace ms;
+    MS_TRY(ensure_init());
+    if (!B) { set_error("band no-flats: null pointer"); return MS_ERR_ARG; }
+    if (reset) { B->nf_ban = 0; return MS_OK; }
+    if (!dem || !fnf || !nviol) { set_error("band no-flats: null pointer"); return MS_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NfBandBufs nb;
+    MS_TRY(nf_band_bufs(B, &nb));
+    const size_t n = (size_t)B->rows * (size_t)B->cols;
+    uint8_t *banned = (uint8_t *)band_buf(B, BB_NF_BANNED, n);
+    if (!banned) return MS_ERR_CUDA;
+    if (!B->nf_ban) MS_CUDA(cudaMemsetAsync(banned, 0, n, s));
+    B->nf_ban = 1;
+    MS_CUDA(cudaMemsetAsync(nb.ctl, 0, sizeof(NfCtl), s));
+    dim3 g2(cdiv(B->cols, 64), cdiv(B->rows, 4));
+    MS_LAUNCH(k_nf_verify, g2, 256, 0, s, dem, fnf, banned, nb.ctl, (int)B->rows, (int)B->cols, short_eps, diag_eps, B->open);
+    NfCtl *h = (NfCtl *)(host_flags().h + 32);
+    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::stream_sync(s));
+    *nviol = h->nviol;
     return MS_OK;
 }
 

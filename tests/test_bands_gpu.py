@@ -167,3 +167,26 @@ def test_band_network_and_rain_equal_oracle(shape, nbands, seed):
     finally:
         for p in pipes:
             p.close()
+
+
+@pytest.mark.parametrize("eps", [(1e-3, 1.5e-3), (0.01, 0.015)])
+def test_band_seed_repair(eps):
+    """fill_terrain_no_flats takes short / diag as arguments (fill.py:174); with steps of the size of the DEM's own
+    height differences a lake rises above "seed" cells next to it (236 / 2604 of them here) and the seed assumption has
+    to be repaired: the stencil rejects, the cells are banned, the solve is repeated.  One GPU does that in
+    fill_no_flats_dev_impl, the bands in BandPipeline._noflats: both must give the reference's bits."""
+    from malstroem_b200.algorithms import fill
+    dem = synth.fractal_dem(320, 256, seed=5)
+    want = port.fill_terrain_no_flats(dem, eps[0], eps[1])
+    assert np.array_equal(fill.fill_terrain_no_flats(dem, eps[0], eps[1]), want)
+    for nb in (2, 5):
+        pipes = bands.run_threaded(torch.from_numpy(dem).cuda(), nb, eps=eps)
+        try:
+            got = torch.cat([p.out["fnf"] for p in pipes]).cpu().numpy()
+            assert np.array_equal(got, want)
+            assert max(p.stats.get("noflat_repairs", 0) for p in pipes) >= 1, pipes[0].stats
+            fd = torch.cat([p.out["flowdir"] for p in pipes]).cpu().numpy()
+            assert np.array_equal(fd, port.terrain_flowdirection(want))
+        finally:
+            for p in pipes:
+                p.close()
