@@ -771,7 +771,12 @@ class BandPipeline(object):
             with torch.cuda.stream(side):
                 for name in names:
                     if name in h:
-                        h[name].copy_(self.out[name], non_blocking=True)
+                        # in pieces of ~32 MB: the stages that follow read counters back every round, and such a
+                        # read-back queues behind whatever the copy engine is busy with (csrc/pipeline.cu ship())
+                        dst, src = h[name], self.out[name]
+                        step = max(1, (32 << 20) // max(1, src[0].numel() * src.element_size()))
+                        for a in range(0, src.shape[0], step):
+                            dst[a:a + step].copy_(src[a:a + step], non_blocking=True)
 
         self.run(ship=ship)
         tabs = {}

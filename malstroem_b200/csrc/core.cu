@@ -124,11 +124,27 @@ void prof_end(cudaStream_t s) { cudaEventRecord(g_recs.back().b, s); }
 
 int HostFlags::init() {
     if (h) return MS_OK;
-    MS_CUDA(cudaHostAlloc((void **)&h, 64 * sizeof(int64_t), cudaHostAllocDefault));
+    MS_CUDA(cudaHostAlloc((void **)&h, 64 * sizeof(int64_t), cudaHostAllocMapped | cudaHostAllocPortable));
     memset(h, 0, 64 * sizeof(int64_t));
     return MS_OK;
 }
 HostFlags &host_flags() { return g_flags; }
+
+__global__ void k_readback(const uint32_t *__restrict__ src, uint32_t *dst_host, int words) {
+    for (int k = threadIdx.x; k < words; k += blockDim.x) dst_host[k] = src[k];
+    __threadfence_system();
+}
+
+int readback(void *host_pinned, const void *dev, size_t bytes, cudaStream_t s) {
+    static int mode = -1;       // MS_READBACK=copy: the copy engine, as before
+    if (mode < 0) { const char *e = getenv("MS_READBACK"); mode = (e && e[0] == 'c') ? 0 : 1; }
+    if (!mode || (bytes & 3) || bytes > 4096 || ((uintptr_t)dev & 3) || ((uintptr_t)host_pinned & 3)) {
+        MS_CUDA(cudaMemcpyAsync(host_pinned, dev, bytes, cudaMemcpyDeviceToHost, s));
+        return MS_OK;
+    }
+    MS_LAUNCH(k_readback, 1, 32, 0, s, (const uint32_t *)dev, (uint32_t *)host_pinned, (int)(bytes >> 2));
+    return MS_OK;
+}
 
 static int init_device(int device) {
     int n = 0;

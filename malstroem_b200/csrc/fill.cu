@@ -383,7 +383,7 @@ static int descent_resolve(const float *dem, int *lab, int *scratch, int64_t row
     else
         MS_LAUNCH(k_descent_tile<false>, tiles_x * tiles_y, 256, 0, s, dem, lab, (int)rows, (int)cols, tiles_x, open, scratch, cnt.p, zmap);
     int64_t *h = host_flags().h;
-    MS_CUDA(cudaMemcpyAsync(h, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, cnt.p, sizeof(int), s));
     MS_TRY(ms::stream_sync(s));
     return forest_resolve_list(lab, scratch, *(int *)h, rounds_out, s);
 }
@@ -424,7 +424,7 @@ static int boruvka_rounds(const float *dem, const int *lab, int *comp, uint32_t 
         MS_LAUNCH(k_hook, gc, 256, 0, s, best.p, comp, lab, parent.p, wk.p, frozen, nC, (int)cols);
         MS_LAUNCH(k_boruvka_update, gc, 256, 0, s, comp, E, parent.p, wk.p, (const uint8_t *)frozen, nC, best.p,
                   counters.p);
-        MS_CUDA(cudaMemcpyAsync(h, counters.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        MS_TRY(ms::readback(h, counters.p, 2 * sizeof(int), s));
         MS_TRY(ms::stream_sync(s));
         int64_t now = ((int *)h)[0];
         n_list = ((int *)h)[1];
@@ -469,7 +469,7 @@ int fill_terrain_dev_impl(const float *dtm, float *filled, float *depths, int64_
     MS_TRY(descent_resolve(dtm, lab.p, tmp.p, rows, cols, 0, &jump_rounds, s));
     MS_TRY(exclusive_scan_selfptr(lab.p, tmp.p, n, total.p, s));
     MS_LAUNCH(k_catchment_ids, g1, 256, 0, s, lab.p, tmp.p, n);
-    MS_CUDA(cudaMemcpyAsync(h, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, total.p, sizeof(int64_t), s));
     MS_TRY(ms::stream_sync(s));
     int nC = (int)h[0];
     tmp.release();
@@ -642,7 +642,7 @@ int fill_band_local(ms_band *B, const float *dem, int64_t *n_frozen, cudaStream_
     MS_TRY(descent_resolve(dem, lab, tmp.p, rows, cols, B->open, nullptr, s));
     MS_TRY(exclusive_scan_selfptr(lab, tmp.p, n, total.p, s));
     MS_LAUNCH(k_catchment_ids, g1, 256, 0, s, lab, tmp.p, n);
-    MS_CUDA(cudaMemcpyAsync(h, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, total.p, sizeof(int64_t), s));
     MS_TRY(ms::stream_sync(s));
     int nC = (int)h[0];
     tmp.release();
@@ -659,7 +659,7 @@ int fill_band_local(ms_band *B, const float *dem, int64_t *n_frozen, cudaStream_
     // dense ranks of the frozen component roots
     MS_LAUNCH(k_frozen_flags, gc, 256, 0, s, comp, frozen, frank, nC);
     MS_TRY(exclusive_scan_i32(frank, frank, nC, total.p, s));
-    MS_CUDA(cudaMemcpyAsync(h, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, total.p, sizeof(int64_t), s));
     MS_TRY(ms::stream_sync(s));
     B->nF = (int)h[0];
     if (n_frozen) *n_frozen = B->nF;
@@ -714,7 +714,7 @@ int ms_band_fill_edges_dev(ms_band *B, const float *dem, const int32_t *halo_gid
                   (const int *)B->buf[BB_FRANK], B->gid_base, halo_gid_top, halo_gid_bot, (int)B->rows, (int)B->cols, hk,
                   hv, H, cnt + 1);
         MS_LAUNCH(k_band_edges_compact, cdiv(H, 256), 256, 0, s, hk, hv, H, edge_a, edge_b, edge_w, capacity, cnt);
-        MS_CUDA(cudaMemcpyAsync(h, cnt, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        MS_TRY(ms::readback(h, cnt, 2 * sizeof(int), s));
         MS_TRY(ms::stream_sync(s));
         int ne = ((int *)h)[0], overflow = ((int *)h)[1];
         if (overflow) continue;      // table too small: double it

@@ -147,8 +147,8 @@ static int ws_resolve(const uint8_t *fd, const L *lab, int *ptr, int *nodir_flag
     MS_LAUNCH(k_ws_tile<L>, tiles_x * tiles_y, 256, 0, s, fd, lab, ptr, nodir_flag, unassigned, (int)rows, (int)cols,
               tiles_x, list.p, cnt.p);
     int64_t *h = host_flags().h;
-    MS_CUDA(cudaMemcpyAsync(h, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (nodir_flag) MS_CUDA(cudaMemcpyAsync(h + 8, nodir_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, cnt.p, sizeof(int), s));
+    if (nodir_flag) MS_TRY(ms::readback(h + 8, nodir_flag, sizeof(int), s));
     MS_TRY(ms::stream_sync(s));
     return forest_resolve_list(ptr, list.p, *(int *)h, rounds_out, s);
 }
@@ -481,7 +481,7 @@ static int pp_network_t(const uint8_t *fd, const L *lab, int64_t rows, int64_t c
         }
     }
     int64_t *h = host_flags().h;
-    MS_CUDA(cudaMemcpyAsync(h, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, err.p, sizeof(int), s));
     MS_TRY(ms::stream_sync(s));
     if (*(int *)h) { set_error("pourpoint_network: cyclic flow directions"); return MS_ERR_NOCONV; }
     return MS_OK;

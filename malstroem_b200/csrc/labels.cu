@@ -312,7 +312,7 @@ int ms_band_cc_count_dev(ms_band *B, const int32_t *rerooted, int64_t n_rerooted
     MS_TRY(tot.alloc(1, s));
     MS_TRY(exclusive_scan_i32(rank, rank, n, tot.p, s));
     int64_t *h = host_flags().h;
-    MS_CUDA(cudaMemcpyAsync(h, tot.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, tot.p, sizeof(int64_t), s));
     MS_TRY(ms::stream_sync(s));
     *count = h[0];
     return MS_OK;
@@ -1249,7 +1249,7 @@ struct ErrFlag {
     // synchronises the stream
     int check(const char *what) {
         int64_t *h = ms::host_flags().h;
-        MS_CUDA(cudaMemcpyAsync(h + 16, d.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MS_TRY(ms::readback(h + 16, d.p, sizeof(int), s));
         MS_TRY(ms::stream_sync(s));
         if (*(int *)(h + 16)) {
             ms::set_error("%s: a label lies outside the table", what);
@@ -1280,7 +1280,7 @@ int ms_connected_components_dev(const void *data, int dtype, int32_t *labels, in
     MS_TRY(tot.alloc(1, s));
     MS_TRY(ms::cc_dev_impl(data, dtype, labels, rows, cols, tot.p, s));
     int64_t *h = ms::host_flags().h;
-    MS_CUDA(cudaMemcpyAsync(h, tot.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, tot.p, sizeof(int64_t), s));
     MS_TRY(ms::stream_sync(s));
     if (nlabels) *nlabels = h[0];
     return MS_OK;

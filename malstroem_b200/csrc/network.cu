@@ -167,7 +167,7 @@ int rain_events_dev_impl(int64_t n64, const int32_t *parent, const double *area,
     }
     MS_LAUNCH(k_net_fill_nan, cdiv((int64_t)n * ne, 256), 256, 0, s, rainv, spillv, v, pctv, (int64_t)n * ne);
     int64_t *h = host_flags().h;
-    MS_CUDA(cudaMemcpyAsync(h, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, bad.p, sizeof(int), s));
     MS_TRY(ms::stream_sync(s));
     if (*(int *)h) { set_error("rain_events: parent index outside [-2, n) or a node that is its own parent"); return MS_ERR_ARG; }
     RainEvents ev;
@@ -332,7 +332,7 @@ int ms_band_pp_parent_dev(const uint8_t *flowdir, const int32_t *wsheds, const i
         MS_LAUNCH(ms::k_band_pp_parent, ms::cdiv(n, 256), 256, 0, s, flowdir, wsheds, ws_above, ws_below, (int)band_rows,
                   (int)cols, first_row, total_rows, n, pp_row, pp_col, out_parent, err.p);
     int64_t *h = ms::host_flags().h;
-    MS_CUDA(cudaMemcpyAsync(h, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, err.p, sizeof(int), s));
     MS_TRY(ms::stream_sync(s));
     if (*(int *)h) {
         ms::set_error("band pour-point network: a pour point flows back into its own bluespot (not a no-flats D8 surface)");

@@ -1846,10 +1846,10 @@ int fill_no_flats_dev_impl(const float *dtm, const float *filled, double sh, dou
                                           tiles_y, ntiles, sh, dg, 0, -1.0, 0, n, s));
         }
         if (!ir) MS_LAUNCH(k_nf_verify, g2, 256, 0, s, dtm, out, banned.p, ctl.p, (int)rows, (int)cols, sh, dg, 0);
-        MS_CUDA(cudaMemcpyAsync(h, ctl.p, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+        MS_TRY(ms::readback(h, ctl.p, sizeof(NfCtl), s));
         int *h_irbad = (int *)(h + 1);
         *h_irbad = 0;
-        if (ir) MS_CUDA(cudaMemcpyAsync(h_irbad, irbad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (ir) MS_TRY(ms::readback(h_irbad, irbad.p, sizeof(int), s));
         MS_TRY(ms::stream_sync(s));
         visits += h->visits;
         rounds += h->reserved;
@@ -1938,7 +1938,7 @@ int ms_band_nf_init_dev(ms_band *B, const float *dem, const float *filled, doubl
     MS_LAUNCH(k_nf_init, g2, 256, 0, s, dem, filled, fnf, B->nf_ban ? (const uint8_t *)B->buf[BB_NF_BANNED] : (const uint8_t *)nullptr,
               nb.tileflag, nb.tilesides, nb.ctl, (int)B->rows, (int)B->cols, nb.tiles_x, B->open);
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
-    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, nb.ctl, sizeof(NfCtl), s));
     MS_TRY(ms::stream_sync(s));
     if (nonseed) *nonseed = h->nonseed;
     return MS_OK;
@@ -1969,7 +1969,7 @@ int ms_band_nf_ban_dev(ms_band *B, const float *dem, const double *fnf, double s
     dim3 g2(cdiv(B->cols, 64), cdiv(B->rows, 4));
     MS_LAUNCH(k_nf_verify, g2, 256, 0, s, dem, fnf, banned, nb.ctl, (int)B->rows, (int)B->cols, short_eps, diag_eps, B->open);
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
-    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, nb.ctl, sizeof(NfCtl), s));
     MS_TRY(ms::stream_sync(s));
     *nviol = h->nviol;
     return MS_OK;
@@ -2007,7 +2007,7 @@ int ms_band_nf_solve_dev(ms_band *B, const float *dem, const float *filled, doub
                                       nb.tiles_x, nb.tiles_y, nb.ntiles, short_eps, diag_eps, 0, -1.0, B->open,
                                       B->rows * B->cols, s));
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
-    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, nb.ctl, sizeof(NfCtl), s));
     MS_TRY(ms::stream_sync(s));
     if (h->done != 1 && h->tail != 0) {
         set_error("band no-flats: tile solver stopped early (done=%d, pending=%d)", h->done, h->pending);
@@ -2175,7 +2175,7 @@ int ms_band_nf_p2p_prepare_dev(ms_band *B, const double *fnf, int64_t *queued, v
     if (B->nf_rank == 0) MS_CUDA(cudaMemsetAsync(base + L.off_gactive, 0, sizeof(int), s));
     MS_LAUNCH(k_nf_compact, cdiv(nb.ntiles, 256), 256, 0, s, nb.tileflag, nb.ring, nb.ctl, nb.ntiles);
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
-    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, nb.ctl, sizeof(NfCtl), s));
     MS_TRY(ms::stream_sync(s));
     *queued = h->pending;
     return MS_OK;
@@ -2207,7 +2207,7 @@ int ms_band_nf_p2p_solve_dev(ms_band *B, const float *filled, double *fnf, doubl
                                  (int)B->cols, nb.tiles_x, nb.tiles_y, nb.ntiles, short_eps, diag_eps, g_nf_use_int,
                                  cap_bound, B->open, B->rows * B->cols, s, (const NfP2P *)B->nf_pp_dev));
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
-    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, nb.ctl, sizeof(NfCtl), s));
     MS_TRY(ms::stream_sync(s));
     if (h->done != 1) {
         set_error("band no-flats P2P: solver stopped early (done=%d, pending=%d)", h->done, h->pending);
@@ -2276,8 +2276,8 @@ int ms_band_nf_ir_prepare_dev(ms_band *B, const float *dem, const float *filled,
     MS_LAUNCH(k_nf_compact, cdiv(nb.ntiles, 256), 256, 0, s, nb.tileflag, nb.ring, nb.ctl, nb.ntiles);
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
     int *h_irbad = (int *)(h + 1);
-    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaMemcpyAsync(h_irbad, irbad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, nb.ctl, sizeof(NfCtl), s));
+    MS_TRY(ms::readback(h_irbad, irbad, sizeof(int), s));
     MS_TRY(ms::stream_sync(s));
     *queued = h->pending;
     *irbad_out = *h_irbad;
@@ -2301,8 +2301,8 @@ int ms_band_nf_ir_solve_launch_dev(ms_band *B, const float *filled, double short
                               B->rows * B->cols, s, (const NfP2P *)B->nf_pp_dev));
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
     int *h_irbad = (int *)(h + 1);
-    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
-    MS_CUDA(cudaMemcpyAsync(h_irbad, irbad, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, nb.ctl, sizeof(NfCtl), s));
+    MS_TRY(ms::readback(h_irbad, irbad, sizeof(int), s));
     return MS_OK;
 }
 
@@ -2347,7 +2347,7 @@ int ms_band_nf_ir_finish_dev(ms_band *B, const float *dem, const float *filled, 
               short_eps, diag_eps, flowdir, 1.0 / pow(2.0, 0.5), B->open, (const int *)(base + L.off_mtop),
               (const int *)(base + L.off_mbot));
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
-    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, nb.ctl, sizeof(NfCtl), s));
     MS_TRY(ms::stream_sync(s));
     *nviol = h->nviol;
     return MS_OK;
@@ -2366,7 +2366,7 @@ int ms_band_nf_verify_dev(ms_band *B, const float *dem, const double *fnf, doubl
     MS_LAUNCH(k_nf_verify, g2, 256, 0, s, dem, fnf, (uint8_t *)nullptr, nb.ctl, (int)B->rows, (int)B->cols, short_eps,
               diag_eps, B->open);
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
-    MS_CUDA(cudaMemcpyAsync(h, nb.ctl, sizeof(NfCtl), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, nb.ctl, sizeof(NfCtl), s));
     MS_TRY(ms::stream_sync(s));
     *nviol = h->nviol;
     return MS_OK;

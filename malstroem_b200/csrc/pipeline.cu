@@ -5,6 +5,9 @@
 // bluespot filter (bench: no filter; the tool layer applies its filter on the host between the stages).
 #include <math.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ms {
@@ -35,22 +38,58 @@ cudaStream_t g_copy_stream = nullptr;
 cudaEvent_t g_copy_ev[8];
 int g_copy_n = 0;
 
+// MS_SHIP_TRACE=1: time every shipped raster on the copy stream (printed by ms_copies_wait) - where the PCIe time of
+// the host-buffer path goes
+struct ShipTrace { cudaEvent_t ready, t0, t1; size_t bytes; };
+ShipTrace g_trace[16];
+int g_trace_n = 0, g_trace_on = -1;
+cudaEvent_t g_trace_origin = nullptr;
+
 int ship(void *dst, const void *src, size_t bytes, cudaStream_t s) {
     if (!dst) return MS_OK;
     if (!g_copy_stream) {
         MS_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
         for (int k = 0; k < 8; k++) MS_CUDA(cudaEventCreateWithFlags(&g_copy_ev[k], cudaEventDisableTiming));
     }
+    if (g_trace_on < 0) { const char *e = getenv("MS_SHIP_TRACE"); g_trace_on = e && e[0] == '1'; }
     cudaEvent_t ev = g_copy_ev[g_copy_n++ & 7];
+    ShipTrace *t = nullptr;
+    if (g_trace_on && g_trace_n < 16) {
+        t = &g_trace[g_trace_n++];
+        if (!t->ready) { cudaEventCreate(&t->ready); cudaEventCreate(&t->t0); cudaEventCreate(&t->t1); }
+        t->bytes = bytes;
+        ev = t->ready;
+    }
     MS_CUDA(cudaEventRecord(ev, s));
     MS_CUDA(cudaStreamWaitEvent(g_copy_stream, ev, 0));
-    MS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_copy_stream));
+    if (t) MS_CUDA(cudaEventRecord(t->t0, g_copy_stream));
+    // In pieces: the stages that follow read small counters back every round (Boruvka, pointer jumping, label
+    // counts), and a device-to-host read-back queues behind whatever the copy engine is busy with - behind one
+    // 8.6 GB copy the compute stream stood still for 170 ms (MS_SHIP_TRACE: 32768^2 host-buffer step 739 ms).
+    // Between pieces of 32 MB (0.6 ms) the engine takes the read-back.
+    const size_t piece = (size_t)32 << 20;
+    for (size_t off = 0; off < bytes; off += piece) {
+        const size_t nb = bytes - off < piece ? bytes - off : piece;
+        MS_CUDA(cudaMemcpyAsync((char *)dst + off, (const char *)src + off, nb, cudaMemcpyDeviceToHost, g_copy_stream));
+    }
+    if (t) MS_CUDA(cudaEventRecord(t->t1, g_copy_stream));
     return MS_OK;
 }
 }  // namespace
 
 extern "C" int ms_copies_wait(void) {
     if (g_copy_stream) MS_CUDA(cudaStreamSynchronize(g_copy_stream));
+    if (g_trace_on > 0 && g_trace_n) {
+        for (int k = 0; k < g_trace_n; k++) {
+            float ready = 0, a = 0, b = 0;
+            cudaEventElapsedTime(&ready, g_trace_origin ? g_trace_origin : g_trace[0].ready, g_trace[k].ready);
+            cudaEventElapsedTime(&a, g_trace_origin ? g_trace_origin : g_trace[0].ready, g_trace[k].t0);
+            cudaEventElapsedTime(&b, g_trace[k].t0, g_trace[k].t1);
+            fprintf(stderr, "[ship] raster %d: ready at %.1f ms, copy starts at %.1f ms, %.2f GB in %.1f ms = %.1f GB/s\n", k,
+                    ready, a, g_trace[k].bytes / 1e9, b, g_trace[k].bytes / 1e6 / b);
+        }
+        g_trace_n = 0;
+    }
     return MS_OK;
 }
 
@@ -58,6 +97,10 @@ extern "C" int ms_pipeline_dev(ms_rasters *io, void *stream) { return ms_pipelin
 
 extern "C" int ms_pipeline_host_dev(ms_rasters *io, const ms_host_out *host, void *stream) {
     using namespace ms;
+    if (host && g_trace_on > 0) {
+        if (!g_trace_origin) cudaEventCreate(&g_trace_origin);
+        cudaEventRecord(g_trace_origin, (cudaStream_t)stream);
+    }
     MS_TRY(ensure_init());
     cudaStream_t s = (cudaStream_t)stream;
     static const ms_host_out no_host = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -78,7 +121,7 @@ extern "C" int ms_pipeline_host_dev(ms_rasters *io, const ms_host_out *host, voi
     DevBuf<float> mm;
     MS_TRY(mm.alloc(2, s));
     MS_TRY(minmax_dev(io->dem, n, mm.p, s));
-    MS_CUDA(cudaMemcpyAsync(h + 24, mm.p, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h + 24, mm.p, 2 * sizeof(float), s));
     MS_TRY(ms::stream_sync(s));
     float lo = ((float *)(h + 24))[0], hi = ((float *)(h + 24))[1];
     double maxval = (double)fmaxf(fabsf(hi), fabsf(lo));
@@ -105,7 +148,7 @@ extern "C" int ms_pipeline_host_dev(ms_rasters *io, const ms_host_out *host, voi
     MS_TRY(err.alloc(1, s));
     MS_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), s));
     MS_TRY(cc_dev_impl(io->depths, MS_F32, io->labels, rows, cols, tot.p, s));
-    MS_CUDA(cudaMemcpyAsync(h, tot.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, tot.p, sizeof(int64_t), s));
     MS_TRY(ms::stream_sync(s));
     io->nlabels = h[0];
     MS_TRY(ship(host->labels, io->labels, (size_t)n * sizeof(int32_t), s));

@@ -261,7 +261,7 @@ static int jump_rounds(bool rank, unsigned long long **a, unsigned long long **b
         MS_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
         if (rank) MS_LAUNCH(k_poly_rankjump, cdiv(n, 256), 256, 0, s, (const unsigned long long *)*a, *b, n, flag.p);
         else MS_LAUNCH(k_poly_minjump, cdiv(n, 256), 256, 0, s, (const unsigned long long *)*a, *b, n, flag.p);
-        MS_CUDA(cudaMemcpyAsync(h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MS_TRY(ms::readback(h, flag.p, sizeof(int), s));
         MS_TRY(stream_sync(s));
         unsigned long long *t = *a; *a = *b; *b = t;
         if (*(int *)h == 0) return MS_OK;
@@ -296,7 +296,7 @@ int polygonize_dev_impl(const int32_t *labels, int64_t rows, int64_t cols, int c
     {
         // the scan's block sums are int32: the edge count has to fit
         MS_TRY(exclusive_scan_i32(eoff.p, eoff.p, n, total.p, s));
-        MS_CUDA(cudaMemcpyAsync(h, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        MS_TRY(ms::readback(h, total.p, sizeof(int64_t), s));
         MS_TRY(stream_sync(s));
     }
     const int64_t E = h[0];
@@ -339,7 +339,7 @@ int polygonize_dev_impl(const int32_t *labels, int64_t rows, int64_t cols, int c
     MS_TRY(ridx.alloc((size_t)ne, s));
     MS_TRY(rstart.alloc((size_t)ne, s));
     MS_TRY(exclusive_scan_i32(isleader.p, ridx.p, ne, total.p, s));
-    MS_CUDA(cudaMemcpyAsync(h, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, total.p, sizeof(int64_t), s));
     MS_TRY(stream_sync(s));
     const int64_t nrings = h[0];
     MS_TRY(exclusive_scan_i32(ringlen.p, rstart.p, ne, total.p, s));
@@ -349,7 +349,7 @@ int polygonize_dev_impl(const int32_t *labels, int64_t rows, int64_t cols, int c
     MS_LAUNCH(k_poly_place, cdiv(ne, 256), 256, 0, s, (const unsigned long long *)lead_state, (const unsigned long long *)rank,
               (const int *)succ.p, (const uint32_t *)ecell.p, (const int *)rstart.p, (const int *)ringlen.p, placed.p, corner.p, ne);
     MS_TRY(exclusive_scan_i32(corner.p, vidx.p, ne, total.p, s));
-    MS_CUDA(cudaMemcpyAsync(h, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    MS_TRY(ms::readback(h, total.p, sizeof(int64_t), s));
     MS_TRY(stream_sync(s));
     const int64_t nverts = h[0];
     MS_TRY(hold_alloc(&g_poly.voff, (size_t)nrings + 1));

@@ -217,7 +217,7 @@ int forest_resolve_list(int *ptr, const int *list, int n_list, int64_t *rounds_o
             MS_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
             prof_units(n_list);
             MS_LAUNCH(k_forest_jump_list, cdiv(n_list, 256), 256, 0, s, ptr, list, n_list, flag.p);
-            MS_CUDA(cudaMemcpyAsync(h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+            MS_TRY(ms::readback(h, flag.p, sizeof(int), s));
             MS_TRY(ms::stream_sync(s));
             rounds++;
             if (*(int *)h == 0) break;
@@ -239,7 +239,7 @@ int forest_resolve(int *ptr, int64_t n, int64_t *rounds_out, cudaStream_t s) {
     for (;;) {
         MS_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
         MS_LAUNCH(k_forest_jump, cdiv(n, 256), 256, 0, s, ptr, n, flag.p);
-        MS_CUDA(cudaMemcpyAsync(h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MS_TRY(ms::readback(h, flag.p, sizeof(int), s));
         MS_TRY(ms::stream_sync(s));
         rounds++;
         if (*(int *)h == 0) break;

@@ -574,7 +574,7 @@ int ms_tiff_decode_dev(const void *in, const uint64_t *in_off, const uint32_t *i
         MS_LAUNCH(k_tiff_inflate, cdiv(nblocks, 4), 128, 0, s, (const unsigned char *)in, (const unsigned long long *)in_off,
                   in_len, (int)nblocks, (unsigned char *)scratch, block_bytes, (unsigned)block_bytes, (unsigned)last_bytes, err.p);
         int *h = (int *)host_flags().h;
-        MS_CUDA(cudaMemcpyAsync(h, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        MS_TRY(ms::readback(h, err.p, sizeof(int), s));
         MS_TRY(ms::stream_sync(s));
         if (*h) { set_error("tiff decode: stream %d is not a valid zlib stream of %zu bytes", *h - 1, block_bytes); return MS_ERR_ARG; }
     }
