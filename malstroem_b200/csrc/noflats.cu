@@ -436,6 +436,9 @@ __device__ inline void nf_push(int *ring, int cap, NfCtl *ctl, int tile, bool sy
         unsigned idx = atomicAdd_system(&ctl->tail, 1u);
         volatile int *slot = ring + (idx % (unsigned)cap);
         for (unsigned spins = 0; *slot != -1 && spins < (1u << 23); spins++) __nanosleep(100);
+        // never overwrite a slot that is still taken (a queued tile would be lost silently): stop the solve instead,
+        // the host sees done == 2 and falls back
+        if (*slot != -1) { atomicExch_system(&ctl->done, 2); return; }
         *slot = tile;
         if (remote) __threadfence_system();
         return;
@@ -445,6 +448,7 @@ __device__ inline void nf_push(int *ring, int cap, NfCtl *ctl, int tile, bool sy
     volatile int *slot = ring + (idx % (unsigned)cap);
     // the ring holds every tile at most once, so the slot is free; wait if it is not (yet)
     for (unsigned spins = 0; *slot != -1 && spins < (1u << 23); spins++) __nanosleep(100);
+    if (*slot != -1) { atomicExch(&ctl->done, 2); return; }
     *slot = tile;
 }
 
