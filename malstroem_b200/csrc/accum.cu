@@ -4,14 +4,10 @@
 // cells flowing into c = size of c's upstream tree, exact float64 integers.
 //
 //   pass A  k_acc_tile_a   one CTA per 64x64 tile: D8 codes + 1-cell apron in shared memory, in-tile downstream index
-//           and in-degree per cell, then every in-tile leaf walks downstream — the reference's tracer rule ("stop at a
-//           cell that still waits for another input") run from all leaves at once.  A cell's state is ONE 32-bit word,
-//           count in the low 24 bits (<= 4096 inside a tile) and the number of inputs still missing above them, so a
-//           step is a single native shared-memory atomic: add (carried count - one missing input); whoever takes the
-//           last missing input away reads the complete count from the value the atomic returns and carries it on.
-//           (64-bit shared atomics are CAS loops on sm_100a; the packed word is 3x faster per step.)  Result: the
-//           count each cell collects from inside its own tile (kept as uint16 per cell), and per perimeter cell where
-//           its in-tile path ends; cells that leave the tile ("exits") publish their local count.
+//           per cell, then the size of every cell's in-tile upstream tree by pointer doubling (round 2; round 1 ran
+//           the reference's tracer rule from all leaves at once - correct, but a warp sat behind its longest walk).
+//           Result: the count each cell collects from inside its own tile (kept as uint16 per cell), and per
+//           perimeter cell where its in-tile path ends; cells that leave the tile ("exits") publish their local count.
 //   links   k_acc_links / k_acc_node_trace: exits form a forest (exit -> entry cell in the next tile -> the exit
 //           that entry's in-tile path ends at).  Same tracer on that forest (~1.5 % of the cells) in global memory
 //           gives every exit its full count.
@@ -28,8 +24,6 @@ constexpr int AT = 64;                    // tile edge
 constexpr int AH = AT + 2;                // apron row length
 constexpr unsigned short A_OUT = 0xffffu; // "leaves the tile or ends"
 constexpr int A_SLOTS = 256;              // perimeter slots per tile (252 used)
-constexpr unsigned A_CNT = 0x00ffffffu;   // packed word: count
-constexpr int A_SHIFT = 24;               // packed word: missing inputs
 
 __device__ inline int perim_slot(int lr, int lc) {
     if (lr == 0) return lc;
@@ -73,53 +67,62 @@ __global__ void __launch_bounds__(256) k_acc_tile_a(const uint8_t *__restrict__ 
                                                     double *__restrict__ nodeX, int *__restrict__ entry_next,
                                                     uint8_t *__restrict__ is_exit, unsigned short *__restrict__ loc16,
                                                     int open) {
-    __shared__ unsigned int word[AT * AT];
-    __shared__ unsigned short sdn[AT * AT];
+    // Round 2: subtree sizes by POINTER DOUBLING instead of walkers from the leaves (whose warps sat behind their
+    // longest walk: 18 of 202 ms at 32768^2).  Invariant at the start of round k: S[v] = number of in-tile cells whose
+    // path reaches v in fewer than 2^k steps (S = 1: the cell itself), J[v] = the cell exactly 2^k steps downstream
+    // (A_OUT when the path has left the tile or ended before).  A round adds S[w] to S[J[w]] for every w - those are
+    // the cells reaching J[w] in 2^k .. 2^(k+1) - 1 steps, counted nowhere else - and doubles the jumps; ~log2 of
+    // the longest in-tile path rounds, every cell busy in every one.  The additions of a round collect in the high half
+    // of the 32-bit word (a count never exceeds 4096), so the low half every other cell reads stays what it was at
+    // the start of the round; the new jumps wait in registers until the barrier.  E jumps to the last in-tile cell
+    // of the path (for the perimeter cells below).
+    __shared__ unsigned int S[AT * AT];
+    __shared__ unsigned short J[AT * AT];
+    __shared__ unsigned short E[AT * AT];
     __shared__ unsigned char sdir[AH * AH];
     int tile = blockIdx.x;
     int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     int r0 = ty * AT, c0 = tx * AT, tid = threadIdx.x;
     const int rlo = (open & 1) ? -1 : 0, rhi = rows + ((open & 2) ? 1 : 0);
-    acc_load_tile(fd, rows, cols, r0, c0, rlo, rhi, sdir, sdn);
-    unsigned leaves = 0;                                            // bit u: cell tid + 256 u has no in-tile input
-#pragma unroll 4
-    for (int u = 0; u < 16; u++) {
-        int k = tid + 256 * u;
-        int lr = k >> 6, lc = k & 63;
-        const unsigned char *ctr = sdir + (lr + 1) * AH + (lc + 1);
-        unsigned n = 15;                                            // outside the raster: never a leaf, never reached
-        if (r0 + lr < rows && c0 + lc < cols) {
-            n = 0;
+    acc_load_tile(fd, rows, cols, r0, c0, rlo, rhi, sdir, J);
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                int nr = lr + kDR[q], nc = lc + kDC[q];
-                if (ctr[kDR[q] * AH + kDC[q]] != ((q + 4) & 7)) continue;      // apron value 255 never matches
-                if (nr >= 0 && nr < AT && nc >= 0 && nc < AT) n++;
-            }
-            if (n == 0) leaves |= 1u << u;
-        }
-        word[k] = 1u | (n << A_SHIFT);
-    }
-    __syncthreads();
     for (int u = 0; u < 16; u++) {
-        if (!(leaves & (1u << u))) continue;
-        int k = tid + 256 * u;
-        unsigned carried = 1;
-        int cur = k;
-        for (;;) {
-            unsigned short d = sdn[cur];
-            if (d == A_OUT) break;
-            unsigned old = atomicAdd(&word[d], carried - (1u << A_SHIFT));
-            if ((old >> A_SHIFT) != 1u) break;                      // somebody else will bring the last input
-            carried += old & A_CNT;
-            cur = d;
-        }
+        int k = tid + 256 * u;                      // the cells this thread wrote in acc_load_tile
+        unsigned short d = J[k];
+        S[k] = 1u;
+        E[k] = d == A_OUT ? (unsigned short)k : d;
     }
     __syncthreads();
+    for (;;) {
+        unsigned short nj[16];
+        int any = 0;
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            int k = tid + 256 * u;
+            unsigned short j = J[k], jj = A_OUT;
+            if (j != A_OUT) {
+                atomicAdd(&S[j], (S[k] & 0xffffu) << 16);
+                jj = J[j];
+                any = 1;
+            }
+            nj[u] = jj;
+            E[k] = E[E[k]];
+        }
+        if (!__syncthreads_or(any)) break;
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            int k = tid + 256 * u;
+            unsigned w = S[k];
+            S[k] = (w & 0xffffu) + (w >> 16);
+            J[k] = nj[u];
+        }
+        __syncthreads();
+    }
+    // (J is A_OUT everywhere now; the in-tile step of a cell is recomputed from its code where needed)
     for (int k = tid; k < AT * AT; k += 256) {
         int lr = k >> 6, lc = k & 63;
         int r = r0 + lr, c = c0 + lc;
-        if (r < rows && c < cols) loc16[(size_t)r * cols + c] = (unsigned short)(word[k] & A_CNT);
+        if (r < rows && c < cols) loc16[(size_t)r * cols + c] = (unsigned short)(S[k] & 0xffffu);
     }
     // per perimeter cell, where its in-tile path ends and (for exits) the local count
     if (tid >= 4 * AT - 4) {          // the four unused slots of the tile
@@ -133,22 +136,21 @@ __global__ void __launch_bounds__(256) k_acc_tile_a(const uint8_t *__restrict__ 
         int nxt = -1;
         uint8_t ex = 0;
         if (r < rows && c < cols) {
-            int cur = lr * AT + lc;
-            for (int guard = 0; guard < AT * AT && sdn[cur] != A_OUT; guard++) cur = sdn[cur];
+            const int cur = E[lr * AT + lc];       // the last in-tile cell of the path from here
             // does the end cell step into another tile of the domain?
             int er = cur >> 6, ec = cur & 63;
             int d = sdir[(er + 1) * AH + (ec + 1)];
-            if (d <= 7 && sdn[cur] == A_OUT) {
+            if (d <= 7) {
                 int gr = r0 + er + kDR[d], gc = c0 + ec + kDC[d];
                 if (gr >= rlo && gr < rhi && gc >= 0 && gc < cols) nxt = tile * A_SLOTS + perim_slot(er, ec);
             }
-            // is this perimeter cell itself an exit?
+            // is this perimeter cell itself an exit (its own step leaves the tile)?
             int d0 = sdir[(lr + 1) * AH + (lc + 1)];
-            if (d0 <= 7 && sdn[lr * AT + lc] == A_OUT) {
+            if (d0 <= 7 && cur == lr * AT + lc) {
                 int gr = r + kDR[d0], gc = c + kDC[d0];
                 if (gr >= rlo && gr < rhi && gc >= 0 && gc < cols) {
                     ex = 1;
-                    nodeX[slot] = (double)(word[lr * AT + lc] & A_CNT);
+                    nodeX[slot] = (double)(S[lr * AT + lc] & 0xffffu);
                 }
             }
         }
