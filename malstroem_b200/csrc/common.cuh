@@ -194,7 +194,7 @@ enum BandBuf {
     BB_LAB, BB_COMP, BB_E, BB_FROZEN, BB_FRANK, BB_HASHK, BB_HASHV,
     BB_ACC_X, BB_ACC_X0, BB_ACC_ENTRY_NEXT, BB_ACC_NEXT, BB_ACC_INDEG, BB_ACC_INDEG0, BB_ACC_ISEXIT, BB_ACC_LOC16,
     BB_CC_PARENT, BB_CC_RANK, BB_WS_PTR, BB_NF_FLAG, BB_NF_SIDES, BB_NF_RING, BB_NF_CTL, BB_MISC, BB_NF_DG, BB_NF_TMETA,
-    BB_NF_IRBAD, BB_NF_BANNED, BB_COUNT
+    BB_NF_IRBAD, BB_NF_BANNED, BB_BLIST, BB_COUNT
 };
 }  // namespace ms
 struct ms_band {
@@ -212,6 +212,7 @@ struct ms_band {
     int nf_peer_ipc[16];   // 1: mapped with cudaIpcOpenMemHandle (must be closed)
     int nf_rank, nf_world;
     void *nf_pp_dev;
+    int n_blist;       // BB_BLIST: cells that still had a neighbour in another component when the local fill ended
     int nf_ban;        // BB_NF_BANNED holds seeds the verification stencil rejected (ms_band_nf_ban_dev)
 };
 namespace ms {

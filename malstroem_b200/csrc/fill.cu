@@ -208,7 +208,11 @@ __device__ inline bool minedge_cell(const float *__restrict__ z, const int *__re
                                     unsigned long long *best, int rows, int cols, int i, int r, int c) {
     int l = lab[i];
     int cc = FIRST ? l : (l ? comp[l] : 0);
-    if (cc == 0 || (!FIRST && frozen && frozen[cc])) return false;
+    if (cc == 0) return false;
+    // row bands: a cell of a FROZEN component no longer searches, but stays listed while a neighbour lies in another
+    // component - the boundary graph of the frozen components is built from the last list (k_band_edges)
+    const bool fz = !FIRST && frozen && frozen[cc];
+    bool other = false;
     float zc = z[i];
     unsigned long long bk = KEY_NONE;
     // interior cell (label != 0 implies not on the border): all 8 neighbours are in the raster, or in a halo row
@@ -219,6 +223,7 @@ __device__ inline bool minedge_cell(const float *__restrict__ z, const int *__re
             if (dr == 0 && dc == 0) continue;
             int j = i + dr * cols + dc;
             if (r + dr < 0 || r + dr >= rows) {
+                if (fz) { other = true; continue; }
                 float w = fmaxf(zc, __ldg(z + j));
                 unsigned long long key = ((unsigned long long)okey32(w) << 32) | FOREIGN_BIT | (unsigned)c;
                 bk = key < bk ? key : bk;
@@ -227,6 +232,7 @@ __device__ inline bool minedge_cell(const float *__restrict__ z, const int *__re
             int lj = __ldg(lab + j);
             if (lj == l) continue;
             if (!FIRST && __ldg(comp + lj) == cc) continue;
+            if (fz) { other = true; continue; }
             float w = fmaxf(zc, __ldg(z + j));
             // symmetric edge id: lower cell index and the direction to the higher one (E, SW, S, SE)
             int lo = j < i ? j : i;
@@ -234,6 +240,7 @@ __device__ inline bool minedge_cell(const float *__restrict__ z, const int *__re
             unsigned long long key = ((unsigned long long)okey32(w) << 32) | (unsigned)(((unsigned)lo << 2) | code);
             bk = key < bk ? key : bk;
         }
+    if (fz) return other;
     if (bk == KEY_NONE) return false;
     if (bk < best[cc]) atomicMin(&best[cc], bk);
     return true;
@@ -391,7 +398,8 @@ static int descent_resolve(const float *dem, int *lab, int *scratch, int64_t row
 // The Boruvka rounds shared by the single-GPU and the row-band fill.  comp / E initialised by k_boruvka_init;
 // `frozen` (row bands only, may be NULL) zeroed.  Returns the number of rounds.
 static int boruvka_rounds(const float *dem, const int *lab, int *comp, uint32_t *E, uint8_t *frozen, int nC,
-                          int64_t rows, int64_t cols, int *rounds_out, const char *what, cudaStream_t s) {
+                          int64_t rows, int64_t cols, int *rounds_out, const char *what, cudaStream_t s,
+                          ms_band *B = nullptr) {
     int64_t n = rows * cols;
     DevBuf<int> parent, counters, listA, listB;
     DevBuf<uint32_t> wk;
@@ -445,6 +453,18 @@ static int boruvka_rounds(const float *dem, const int *lab, int *comp, uint32_t 
         lout = (lout == listA.p) ? listB.p : listA.p;
     }
     if (rounds_out) *rounds_out = rounds;
+    if (B) {
+        // the last list: every cell that had a neighbour in another component in the last round (components only
+        // merge, so it is a superset of the cells on the borders between the frozen components)
+        B->n_blist = 0;
+        if (rounds > 0 && n_list > 0) {
+            int *dst = (int *)band_buf(B, BB_BLIST, (size_t)n_list * sizeof(int));
+            if (!dst) return MS_ERR_CUDA;
+            MS_CUDA(cudaMemcpyAsync(dst, lin, (size_t)n_list * sizeof(int), cudaMemcpyDeviceToDevice, s));
+            MS_TRY(ms::stream_sync(s));      // the list buffers go back to the arena when this function returns
+            B->n_blist = n_list;
+        }
+    }
     return MS_OK;
 }
 
@@ -542,11 +562,14 @@ __global__ void __launch_bounds__(256) k_band_edges(const float *__restrict__ z,
                                                     const int *__restrict__ comp, const int *__restrict__ frank,
                                                     int base, const int32_t *__restrict__ halo_top,
                                                     const int32_t *__restrict__ halo_bot, int rows, int cols,
-                                                    unsigned long long *hk, uint32_t *hv, unsigned H, int *overflow) {
-    int c = blockIdx.x * 64 + (threadIdx.x & 63);
-    int r = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (r >= rows || c >= cols) return;
-    int i = r * cols + c;
+                                                    unsigned long long *hk, uint32_t *hv, unsigned H, int *overflow,
+                                                    const int *__restrict__ list, int n_list) {
+    // over the last list of the Boruvka rounds (round 2; a pass over the whole band before: 4.7 of 37 ms of the fill
+    // of a 16384 x 32768 band, spent on a label read and a component gather per cell to find the few frozen ones)
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_list) return;
+    int i = list[k];
+    int r = i / cols, c = i - r * cols;
     int l = lab[i];
     if (l == 0) return;
     int K = comp[l];
@@ -655,7 +678,7 @@ int fill_band_local(ms_band *B, const float *dem, int64_t *n_frozen, cudaStream_
     unsigned gc = cdiv(nC, 256);
     MS_LAUNCH(k_boruvka_init, gc, 256, 0, s, comp, E, nC);
     MS_CUDA(cudaMemsetAsync(frozen, 0, (size_t)nC, s));
-    MS_TRY(boruvka_rounds(dem, lab, comp, E, frozen, nC, rows, cols, nullptr, "band fill", s));
+    MS_TRY(boruvka_rounds(dem, lab, comp, E, frozen, nC, rows, cols, nullptr, "band fill", s, B));
     // dense ranks of the frozen component roots
     MS_LAUNCH(k_frozen_flags, gc, 256, 0, s, comp, frozen, frank, nC);
     MS_TRY(exclusive_scan_i32(frank, frank, nC, total.p, s));
@@ -709,10 +732,10 @@ int ms_band_fill_edges_dev(ms_band *B, const float *dem, const int32_t *halo_gid
         MS_CUDA(cudaMemsetAsync(hk, 0xff, (size_t)H * 8, s));
         MS_CUDA(cudaMemsetAsync(hv, 0xff, (size_t)H * 4, s));
         MS_CUDA(cudaMemsetAsync(cnt, 0, 64, s));
-        dim3 g2(cdiv(B->cols, 64), cdiv(B->rows, 4));
-        MS_LAUNCH(k_band_edges, g2, 256, 0, s, dem, (const int *)B->buf[BB_LAB], (const int *)B->buf[BB_COMP],
-                  (const int *)B->buf[BB_FRANK], B->gid_base, halo_gid_top, halo_gid_bot, (int)B->rows, (int)B->cols, hk,
-                  hv, H, cnt + 1);
+        if (B->n_blist > 0)
+            MS_LAUNCH(k_band_edges, cdiv(B->n_blist, 256), 256, 0, s, dem, (const int *)B->buf[BB_LAB], (const int *)B->buf[BB_COMP],
+                      (const int *)B->buf[BB_FRANK], B->gid_base, halo_gid_top, halo_gid_bot, (int)B->rows, (int)B->cols, hk,
+                      hv, H, cnt + 1, (const int *)B->buf[BB_BLIST], B->n_blist);
         MS_LAUNCH(k_band_edges_compact, cdiv(H, 256), 256, 0, s, hk, hv, H, edge_a, edge_b, edge_w, capacity, cnt);
         MS_TRY(ms::readback(h, cnt, 2 * sizeof(int), s));
         MS_TRY(ms::stream_sync(s));

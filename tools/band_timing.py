@@ -16,13 +16,44 @@ for _ in range(2):
     p.run()
 p.timing = {}
 reps = 2
+# per stage: wall time (device synchronised at the stage boundary) and the time inside OUR kernels (library profiler);
+# the difference is collectives, torch glue kernels, host work and launch gaps
+import ctypes, time as _time
+from malstroem_b200 import _lib as _L
+kern, perk = {}, {}
+_orig_tick = p._tick
+
+
+def _tick(name):
+    _orig_tick(name)
+    buf = ctypes.create_string_buffer(1 << 16)
+    _L.lib().ms_profile_report(buf, len(buf))
+    ms = 0.0
+    for line in buf.value.decode().splitlines():
+        kname, cnt, kms, _units = line.rsplit(" ", 3)
+        ms += float(kms)
+        d = perk.setdefault(name, {})
+        d[kname] = d.get(kname, 0.0) + float(kms)
+    kern[name] = kern.get(name, 0.0) + ms
+    p._t_last = _time.perf_counter()
+
+
+p._tick = _tick
+_L.lib().ms_profile(20000)
 for _ in range(reps):
     p.run()
+_L.lib().ms_profile(0)
+p._tick = _orig_tick
 if rank == 0:
-    tot = 0
+    tot = ktot = 0
     for k, v in p.timing.items():
-        print("%-12s %7.2f ms" % (k, v / reps)); tot += v / reps
-    print("total        %7.2f ms" % tot, p.stats)
+        print("%-16s %7.2f ms   own kernels %7.2f ms   other %6.2f ms" % (k, v / reps, kern.get(k, 0) / reps, (v - kern.get(k, 0)) / reps))
+        tot += v / reps
+        ktot += kern.get(k, 0) / reps
+        top = sorted(perk.get(k, {}).items(), key=lambda kv: -kv[1])[:7]
+        if top:
+            print("      " + "  ".join("%s %.2f" % (a, b / reps) for a, b in top))
+    print("total            %7.2f ms   own kernels %7.2f ms   other %6.2f ms" % (tot, ktot, tot - ktot), p.stats)
 # the same run without the per-stage synchronisations: wall clock per step
 import time
 os.environ["MS_BAND_TIMING"] = "0"
