@@ -202,7 +202,10 @@ constexpr int ME_PER_THREAD = 4;      // cells per thread: one list append (atom
 
 // FIRST: round 1, where every catchment is its own component (comp[l] == l) and nothing is frozen yet — the component
 // lookups (a gather per neighbour across a catchment boundary) are skipped.
-template <bool FIRST>
+// BAND: row bands (frozen != nullptr).
+// r: the cell's row, or for a cell given by its index alone (the list rounds) 0 / 1 / rows - 1 for first / any other /
+// last row - only "does the neighbour row exist" is asked; c < 0: the column is worked out if a foreign edge needs it
+template <bool FIRST, bool BAND>
 __device__ inline bool minedge_cell(const float *__restrict__ z, const int *__restrict__ lab,
                                     const int *__restrict__ comp, const uint8_t *__restrict__ frozen,
                                     unsigned long long *best, int rows, int cols, int i, int r, int c) {
@@ -211,7 +214,7 @@ __device__ inline bool minedge_cell(const float *__restrict__ z, const int *__re
     if (cc == 0) return false;
     // row bands: a cell of a FROZEN component no longer searches, but stays listed while a neighbour lies in another
     // component - the boundary graph of the frozen components is built from the last list (k_band_edges)
-    const bool fz = !FIRST && frozen && frozen[cc];
+    const bool fz = BAND && !FIRST && frozen[cc];      // BAND: frozen != nullptr
     bool other = false;
     float zc = z[i];
     unsigned long long bk = KEY_NONE;
@@ -225,6 +228,7 @@ __device__ inline bool minedge_cell(const float *__restrict__ z, const int *__re
             if (r + dr < 0 || r + dr >= rows) {
                 if (fz) { other = true; continue; }
                 float w = fmaxf(zc, __ldg(z + j));
+                if (c < 0) c = i % cols;
                 unsigned long long key = ((unsigned long long)okey32(w) << 32) | FOREIGN_BIT | (unsigned)c;
                 bk = key < bk ? key : bk;
                 continue;
@@ -250,8 +254,8 @@ __device__ inline bool minedge_cell(const float *__restrict__ z, const int *__re
 // Either way the cells that still have a neighbour in another component are appended to list_out: a cell inside its
 // component never has an outgoing edge again, and components grow every round, so the later rounds touch ever
 // fewer cells.
-template <bool LIST>
-__global__ void __launch_bounds__(256) k_minedge(const float *__restrict__ z, const int *__restrict__ lab,
+template <bool LIST, bool BAND>
+__device__ __forceinline__ void minedge_body(const float *__restrict__ z, const int *__restrict__ lab,
                                                  const int *__restrict__ comp, const uint8_t *__restrict__ frozen,
                                                  unsigned long long *best, int rows, int cols,
                                                  const int *__restrict__ list_in, int n_in, int *list_out, int *n_out) {
@@ -264,8 +268,9 @@ __global__ void __launch_bounds__(256) k_minedge(const float *__restrict__ z, co
             int k = (blockIdx.x * ME_PER_THREAD + u) * 256 + threadIdx.x;
             if (k < n_in) {
                 i = list_in[k];
-                r = i / cols;
-                c = i - r * cols;
+                // no division per entry: only the first and the last row have a neighbour row missing
+                r = i < cols ? 0 : (i >= (rows - 1) * cols ? rows - 1 : 1);
+                c = -1;
             }
         } else {
             c = blockIdx.x * 64 + (threadIdx.x & 63);
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(256) k_minedge(const float *__restrict__ z, co
             if (r < rows && c < cols) i = r * cols + c;
         }
         cell[u] = i;
-        if (i >= 0 && minedge_cell<!LIST>(z, lab, comp, frozen, best, rows, cols, i, r, c)) keepbits |= 1u << u;
+        if (i >= 0 && minedge_cell<!LIST, BAND>(z, lab, comp, frozen, best, rows, cols, i, r, c)) keepbits |= 1u << u;
     }
     // append the survivors: block-wide exclusive scan of the per-thread counts, one atomic per CTA
     __shared__ int wsum[8];
@@ -297,6 +302,23 @@ __global__ void __launch_bounds__(256) k_minedge(const float *__restrict__ z, co
 #pragma unroll
     for (int u = 0; u < ME_PER_THREAD; u++)
         if (keepbits & (1u << u)) list_out[pos++] = cell[u];
+}
+
+// two kernels from one body: the single-GPU form carries none of the frozen-component logic (compiled into one kernel
+// behind a uniform branch it cost 2 ms of 12 in round 1: the body is instruction-cache-sized)
+template <bool LIST>
+__global__ void __launch_bounds__(256) k_minedge(const float *__restrict__ z, const int *__restrict__ lab,
+                                                 const int *__restrict__ comp, const uint8_t *__restrict__ frozen,
+                                                 unsigned long long *best, int rows, int cols,
+                                                 const int *__restrict__ list_in, int n_in, int *list_out, int *n_out) {
+    minedge_body<LIST, false>(z, lab, comp, frozen, best, rows, cols, list_in, n_in, list_out, n_out);
+}
+template <bool LIST>
+__global__ void __launch_bounds__(256) k_minedge_band(const float *__restrict__ z, const int *__restrict__ lab,
+                                                      const int *__restrict__ comp, const uint8_t *__restrict__ frozen,
+                                                      unsigned long long *best, int rows, int cols,
+                                                      const int *__restrict__ list_in, int n_in, int *list_out, int *n_out) {
+    minedge_body<LIST, true>(z, lab, comp, frozen, best, rows, cols, list_in, n_in, list_out, n_out);
 }
 
 __device__ inline int edge_other(int lo, int code, int cols) {
@@ -422,12 +444,20 @@ static int boruvka_rounds(const float *dem, const int *lab, int *comp, uint32_t 
         if (rounds == 0) {
             prof_units(n);
             dim3 g2m(cdiv(cols, 64), cdiv(rows, 4 * ME_PER_THREAD));
-            MS_LAUNCH(k_minedge<false>, g2m, 256, 0, s, dem, lab, (const int *)comp, (const uint8_t *)frozen, best.p,
-                      (int)rows, (int)cols, (const int *)nullptr, 0, lout, counters.p + 1);
+            if (frozen)
+                MS_LAUNCH(k_minedge_band<false>, g2m, 256, 0, s, dem, lab, (const int *)comp, (const uint8_t *)frozen, best.p,
+                          (int)rows, (int)cols, (const int *)nullptr, 0, lout, counters.p + 1);
+            else
+                MS_LAUNCH(k_minedge<false>, g2m, 256, 0, s, dem, lab, (const int *)comp, (const uint8_t *)frozen, best.p,
+                          (int)rows, (int)cols, (const int *)nullptr, 0, lout, counters.p + 1);
         } else {
             prof_units(n_list);
-            MS_LAUNCH(k_minedge<true>, cdiv(n_list, 256 * ME_PER_THREAD), 256, 0, s, dem, lab, (const int *)comp, (const uint8_t *)frozen,
-                      best.p, (int)rows, (int)cols, (const int *)lin, n_list, lout, counters.p + 1);
+            if (frozen)
+                MS_LAUNCH(k_minedge_band<true>, cdiv(n_list, 256 * ME_PER_THREAD), 256, 0, s, dem, lab, (const int *)comp,
+                          (const uint8_t *)frozen, best.p, (int)rows, (int)cols, (const int *)lin, n_list, lout, counters.p + 1);
+            else
+                MS_LAUNCH(k_minedge<true>, cdiv(n_list, 256 * ME_PER_THREAD), 256, 0, s, dem, lab, (const int *)comp,
+                          (const uint8_t *)frozen, best.p, (int)rows, (int)cols, (const int *)lin, n_list, lout, counters.p + 1);
         }
         MS_LAUNCH(k_hook, gc, 256, 0, s, best.p, comp, lab, parent.p, wk.p, frozen, nC, (int)cols);
         MS_LAUNCH(k_boruvka_update, gc, 256, 0, s, comp, E, parent.p, wk.p, (const uint8_t *)frozen, nC, best.p,
