@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(256) k_acc_tile_a(const uint8_t *__restrict__ 
     for (;;) {
         unsigned short nj[16];
         int any = 0;
+        // (batching the loads of 4 or 8 cells ahead of their atomics was tried: 13.6 / 14.0 ms against 12.9 for this
+        // plain loop at 32768^2 - the extra registers cost more than the overlapped latency gives)
 #pragma unroll
         for (int u = 0; u < 16; u++) {
             int k = tid + 256 * u;
@@ -177,20 +179,25 @@ __global__ void __launch_bounds__(256) k_acc_tile_a(const uint8_t *__restrict__ 
 
 // (FINAL) halo_top / halo_bot[column] = full count of the neighbouring band's edge-row cell, used where that cell
 // flows into this band.
+// WIDE = false: one 32-bit word per cell (a count cannot exceed the number of cells of the whole raster; one GPU holds
+// at most 2^30) - 16 KB less shared memory, 7 instead of 4 CTAs per SM for a kernel that waits on global loads (ncu:
+// long-scoreboard stalls 10.9 per issue, 48 % of the warp slots filled).  WIDE = true (row bands: the raster can have
+// 2^32 cells and more): the inflow in two 16-bit halves in separate words.
+template <bool WIDE>
 __global__ void __launch_bounds__(256) k_acc_tile_c(const uint8_t *__restrict__ fd, int rows, int cols, int tiles_x,
                                                     const double *__restrict__ nodeX,
                                                     const unsigned short *__restrict__ loc16,
                                                     double *__restrict__ accum, int open,
                                                     const double *__restrict__ halo_top,
                                                     const double *__restrict__ halo_bot) {
-    __shared__ unsigned int lo[AT * AT], hi[AT * AT];
+    __shared__ unsigned int lo[AT * AT], hi[WIDE ? AT * AT : 1];
     __shared__ unsigned short sdn[AT * AT];
     __shared__ __align__(16) unsigned char sdir[AH * AS];
     int tile = blockIdx.x;
     int ty = tile / tiles_x, tx = tile - ty * tiles_x;
     int r0 = ty * AT, c0 = tx * AT, tid = threadIdx.x;
     const int rlo = (open & 1) ? -1 : 0, rhi = rows + ((open & 2) ? 1 : 0);
-    for (int k = tid; k < AT * AT; k += 256) { lo[k] = 0; hi[k] = 0; }
+    for (int k = tid; k < AT * AT; k += 256) { lo[k] = 0; if (WIDE) hi[k] = 0; }
     acc_load_tile(fd, rows, cols, r0, c0, rlo, rhi, sdir, sdn);
     __syncthreads();
     if (tid < 4 * AT - 4) {
@@ -215,11 +222,11 @@ __global__ void __launch_bounds__(256) k_acc_tile_c(const uint8_t *__restrict__ 
                 }
             }
             if (inflow) {
-                unsigned a = (unsigned)(inflow & 0xffffu), b = (unsigned)(inflow >> 16);
+                unsigned a = WIDE ? (unsigned)(inflow & 0xffffu) : (unsigned)inflow, b = WIDE ? (unsigned)(inflow >> 16) : 0u;
                 int cur = lr * AT + lc;
                 for (int guard = 0; guard < AT * AT; guard++) {
                     atomicAdd(&lo[cur], a);
-                    if (b) atomicAdd(&hi[cur], b);
+                    if (WIDE && b) atomicAdd(&hi[cur], b);
                     unsigned short d = sdn[cur];
                     if (d == A_OUT) break;
                     cur = d;
@@ -233,7 +240,7 @@ __global__ void __launch_bounds__(256) k_acc_tile_c(const uint8_t *__restrict__ 
         int r = r0 + lr, c = c0 + lc;
         if (r < rows && c < cols) {
             size_t i = (size_t)r * cols + c;
-            unsigned long long v = (unsigned long long)loc16[i] + lo[k] + ((unsigned long long)hi[k] << 16);
+            unsigned long long v = (unsigned long long)loc16[i] + lo[k] + (WIDE ? ((unsigned long long)hi[k] << 16) : 0ull);
             accum[i] = (double)v;
         }
     }
@@ -313,7 +320,7 @@ int accum_dev_impl(const uint8_t *fd, double *acc, int64_t rows, int64_t cols, c
     MS_CUDA(cudaMemcpyAsync(indeg0.p, indeg.p, (size_t)nslots * sizeof(int), cudaMemcpyDeviceToDevice, s));
     MS_LAUNCH(k_acc_node_trace, cdiv(nslots, 256), 256, 0, s, is_exit.p, next.p, indeg0.p, indeg.p, X.p, nslots);
     prof_units(rows * cols);
-    MS_LAUNCH(k_acc_tile_c, ntiles, 256, 0, s, fd, (int)rows, (int)cols, tiles_x, (const double *)X.p,
+    MS_LAUNCH(k_acc_tile_c<false>, ntiles, 256, 0, s, fd, (int)rows, (int)cols, tiles_x, (const double *)X.p,
               (const unsigned short *)loc16.p, acc, 0, (const double *)nullptr, (const double *)nullptr);
     return MS_OK;
 }
@@ -495,7 +502,7 @@ int ms_band_accum_finish_dev(ms_band *B, const uint8_t *fd, const double *halo_t
                   halo_total_top, halo_total_bot);
     MS_LAUNCH(k_acc_node_trace, cdiv(nslots, 256), 256, 0, s, is_exit, next, indeg0, indeg, X, nslots);
     prof_units(B->rows * B->cols);
-    MS_LAUNCH(k_acc_tile_c, ntiles, 256, 0, s, fd, rows, cols, tiles_x, (const double *)X,
+    MS_LAUNCH(k_acc_tile_c<true>, ntiles, 256, 0, s, fd, rows, cols, tiles_x, (const double *)X,
               (const unsigned short *)B->buf[BB_ACC_LOC16], accum, B->open, halo_total_top, halo_total_bot);
     return MS_OK;
 }
