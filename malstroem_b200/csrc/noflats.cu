@@ -63,6 +63,8 @@ constexpr int NF_BLOCK_ITERS = 64;   // in-block iteration guard (a block that h
 #ifdef NF_STATS
 __device__ unsigned long long g_nf_dbg[16];
 __device__ unsigned long long g_nf_log[4 * 262144];     // per visit: t_pop, t_loaded, t_end, tile | iters << 32
+__device__ unsigned long long g_nf_hist[1024];          // per 65.5 us of the solve: visits started, ns spent in them
+__device__ unsigned long long g_nf_t0;                  // earliest visit start seen (reset to ~0)
 __device__ unsigned int g_nf_nlog;   // [0] tile iterations [1] block visits [2] block iterations [3] -, then per round (n, ns)
 __device__ inline unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #endif
@@ -1525,6 +1527,14 @@ __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__r
             if (S.bad && tid == 0) atomicExch(irbad, 1);
         }
 #ifdef NF_STATS
+        if (tid == 0) {                 // activity over time, all visits
+            atomicMin(&g_nf_t0, tg0);
+            long long rel = (long long)(tg0 - *(volatile unsigned long long *)&g_nf_t0);
+            unsigned b = rel < 0 ? 0u : (unsigned)(rel >> 16);
+            if (b > 511u) b = 511u;
+            atomicAdd(&g_nf_hist[2 * b], 1ull);
+            atomicAdd(&g_nf_hist[2 * b + 1], gtimer() - tg0);
+        }
 #ifdef NF_STATS_TAIL
         if (tid == 0 && S.mid) {        // only the visits of the tail (a raster with more visits than log entries)
 #else
@@ -2277,6 +2287,8 @@ int ms_band_nf_ir_prepare_dev(ms_band *B, const float *dem, const float *filled,
               (int)B->rows, (int)B->cols, nb.tiles_x, short_eps, diag_eps, cap_bound, Dg, P, tmeta, irbad, B->open, fix_top,
               fix_bot, nomap, nomap);
     MS_LAUNCH(k_band_ir_publish, dim3(cdiv(P, 256), 2), 256, 0, s, Dg, P, (int)B->rows, (const NfP2P *)B->nf_pp_dev);
+    // (queueing the tile rows next to an open band edge first - so that what crosses the edge reaches the neighbour
+    // early - was measured at N = 2: 30.4 vs 30.0 ms, no gain; both bands are saturated for 27 of the 30 ms)
     MS_LAUNCH(k_nf_compact, cdiv(nb.ntiles, 256), 256, 0, s, nb.tileflag, nb.ring, nb.ctl, nb.ntiles);
     NfCtl *h = (NfCtl *)(host_flags().h + 32);
     int *h_irbad = (int *)(h + 1);
@@ -2419,6 +2431,17 @@ int ms_nf_log(unsigned long long *out, unsigned *n, int reset) {
     if (n) cudaMemcpyFromSymbol(n, ms::g_nf_nlog, sizeof(unsigned));
     if (out) cudaMemcpyFromSymbol(out, ms::g_nf_log, sizeof(unsigned long long) * 4 * 262144);
     if (reset) { unsigned z = 0; cudaMemcpyToSymbol(ms::g_nf_nlog, &z, sizeof(z)); }
+    return 0;
+}
+
+int ms_nf_hist(unsigned long long *out1024, int reset) {
+    if (out1024) cudaMemcpyFromSymbol(out1024, ms::g_nf_hist, sizeof(unsigned long long) * 1024);
+    if (reset) {
+        static unsigned long long z[1024];
+        cudaMemcpyToSymbol(ms::g_nf_hist, z, sizeof(z));
+        unsigned long long big = ~0ull;
+        cudaMemcpyToSymbol(ms::g_nf_t0, &big, sizeof(big));
+    }
     return 0;
 }
 

@@ -18,8 +18,10 @@ for _ in range(2):
 p.timing = {}
 nflog = raw.ms_nf_log; nflog.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
 dbg = raw.ms_nf_debug; dbg.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
-nflog(None, None, 1); dbg(None, 0, 1)
+hist = raw.ms_nf_hist; hist.argtypes = [ctypes.c_void_p, ctypes.c_int]
+nflog(None, None, 1); dbg(None, 0, 1); hist(None, 1)
 p.run()
+hh = np.zeros(1024, dtype=np.uint64); hist(hh.ctypes.data_as(ctypes.c_void_p), 0)
 out = (ctypes.c_ulonglong * 16)(); dbg(out, 16, 0)
 log = np.zeros(4 * 262144, dtype=np.uint64); nl = ctypes.c_uint(0)
 nflog(log.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nl), 0)
@@ -36,6 +38,20 @@ if k:
     msg += "; per tail visit: load %.1f relax %.1f flush %.1f us, rounds %.2f" % (
         ((lg[:, 1] - lg[:, 0]) / 1e3).mean(), relax.mean(), ((lg[:, 2] - lg[:, 1]) / 1e3 - relax).mean(), rounds.mean())
 msg += "; remote pushes %d, mean %.1f us" % (out[0], out[1] / max(out[0], 1) / 1e3)
+if k:
+    # the tail log for tools/nf_chain.py --analyse (columns pop, loaded, end [ns], tile, rounds, relax [ns])
+    os.makedirs("gpurun_out", exist_ok=True)
+    np.save("gpurun_out/nf_tail_band_r%d_of%d.npy" % (rank, world),
+            np.stack([lg[:, 0], lg[:, 1], lg[:, 2], lg[:, 3] & 0xffffffff, (lg[:, 3] >> 32) & 0xff, (lg[:, 3] >> 40) & 0xffffff], axis=1))
+# activity per millisecond: visits started, mean number of tiles in flight (of %d CTAs)
+hv = hh.astype(np.float64).reshape(512, 2)
+per = 15        # 15 bins of 65.5 us ~ 1 ms
+lines = []
+for a in range(0, 512, per):
+    n, busy = hv[a:a + per, 0].sum(), hv[a:a + per, 1].sum()
+    if n:
+        lines.append("%5.1f ms: %6d visits, %5.0f in flight" % (a * 0.0655, n, busy / (per * 65536.0)))
+msg += "\n  " + "\n  ".join(lines)
 for r in range(world):
     dist.barrier()
     if r == rank:
