@@ -56,3 +56,26 @@ for a in edges:
           (end - loaded - relax)[m].mean(), r.mean(), relax[m].sum() / max(r.sum(), 1)))
 hist = np.bincount(rounds, minlength=12)
 print("rounds histogram:", hist[:16].tolist())
+# distribution of the visits by relax time and by rounds (share of visits / share of relax time)
+tot_relax = relax.sum()
+print("relax time [us]   visits   share   share of relax time")
+for a, b in ((0, 2), (2, 5), (5, 10), (10, 20), (20, 40), (40, 80), (80, 1e9)):
+    m = (relax >= a) & (relax < b)
+    print("  %4g-%-6g %8d  %5.1f%%  %5.1f%%" % (a, b if b < 1e9 else float('inf'), m.sum(), 100.0 * m.mean(), 100.0 * relax[m].sum() / max(tot_relax, 1e-9)))
+print("rounds   visits   mean relax us   share of relax time")
+for r in range(0, 12):
+    m = rounds == r
+    if m.any():
+        print("  %2d   %8d   %8.2f   %5.1f%%" % (r, m.sum(), relax[m].mean(), 100.0 * relax[m].sum() / max(tot_relax, 1e-9)))
+first = np.zeros(k, dtype=bool)
+seen = set()
+order = np.argsort(pop)
+tiles = (log[:, 3] & 0xffffffff)
+for i in order:
+    t = int(tiles[i])
+    if t not in seen:
+        seen.add(t)
+        first[i] = True
+print("first visits %d: mean relax %.2f us, rounds %.2f | re-visits %d: mean relax %.2f us, rounds %.2f, no-change (1 round) %.1f%%"
+      % (first.sum(), relax[first].mean(), rounds[first].mean(), (~first).sum(), relax[~first].mean(), rounds[~first].mean(),
+         100.0 * (rounds[~first] <= 1).mean()))
