@@ -1097,6 +1097,12 @@ constexpr int IR_SMEM = (NF_T + 2) * IR_LD * 4 + NF_T * NF_T;
 #ifndef IR_MIDFLUSH
 #define IR_MIDFLUSH 1
 #endif
+#ifndef IR_MID_SHIFT
+#define IR_MID_SHIFT 2        // tail mode (edges forwarded after the first round) below grid >> IR_MID_SHIFT queued or running tiles
+// (measured: shift 0 / 1 / 2 / 3 -> 3.15 / 3.21 / 3.42 / 3.47 ms at 8192^2, 38.8 / 38.8 / 38.6 / 38.8 ms at 32768^2; on two
+// bands of 4096 / 16384 rows shift 0 gives 6.6 / 29.5 ms against 7.0 / 29.0: it helps where the tail dominates and costs
+// where the bulk does - left at 2)
+#endif
 
 // the wall frame of the padded raster: row 0, the rows below the tiles, and 4 columns either side of every tile row
 // (k_nf_init_tile writes everything inside, including the cells of edge tiles that lie beyond the raster)
@@ -1294,7 +1300,7 @@ __global__ void __launch_bounds__(IR_NT, IR_CTAS) k_nf_solve_ir(const float *__r
                 S.elo = (int)(short)(meta & 0xffff);
                 S.e = S.elo + ((meta >> 16) & 15);
                 S.has = (meta >> 20) & 1;
-                S.mid = IR_MIDFLUSH && *(volatile int *)&ctl->pending < (int)(gridDim.x >> 2);
+                S.mid = IR_MIDFLUSH && *(volatile int *)&ctl->pending < (int)(gridDim.x >> IR_MID_SHIFT);
                 atomicAdd(&ctl->visits, 1);
             }
             S.k = t;
