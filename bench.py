@@ -36,7 +36,7 @@ UNIT = "Mcells/s"
 BYTES_PER_CELL = 79.0     # compulsory traffic of the eight stages
 # algorithmic bytes per cell of the stage each raster-wide kernel belongs to (SURVEY.md 8(d) / DESIGN.md 4)
 STAGE_BYTES = {
-    "k_descent_tile": 12, "k_forest_jump_list": 12, "k_ws_tile<L>": 9, "k_forest_jump": 12, "k_rootflag": 12, "k_catchment_ids": 12, "k_minedge<false>": 12, "k_minedge<true>": 12,
+    "k_descent_tile": 12, "k_forest_jump_list": 12, "k_ws_tile<L>": 9, "k_forest_jump": 12, "k_rootflag": 12, "k_catchment_ids": 12, "k_minedge<false>": 12, "k_minedge_first4": 12, "k_minedge<true>": 12,
     "k_fill_final": 12, "k_scan_reduce<SELF>": 8, "k_scan_final<SELF>": 8,
     "k_nf_init": 12, "k_nf_seedcand": 12, "k_nf_solve<true>": 12, "k_nf_solve<false>": 12, "k_nf_solve_ir": 12, "k_nf_finish_ir": 12, "k_nf_init_tile": 12, "k_nf_verify": 12,
     "k_flowdir": 9, "k_acc_tile_a": 9, "k_acc_tile_c": 9, "k_acc_tile_c<false>": 9, "k_acc_tile_c<true>": 9, "k_minedge_band<false>": 12, "k_minedge_band<true>": 12, "k_acc_links": 9, "k_acc_node_trace": 9,

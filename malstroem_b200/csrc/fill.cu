@@ -254,6 +254,31 @@ __device__ inline bool minedge_cell(const float *__restrict__ z, const int *__re
 // Either way the cells that still have a neighbour in another component are appended to list_out: a cell inside its
 // component never has an outgoing edge again, and components grow every round, so the later rounds touch ever
 // fewer cells.
+// append the survivors: block-wide exclusive scan of the per-thread counts, one atomic per CTA
+__device__ __forceinline__ void minedge_append(unsigned keepbits, const int (&cell)[ME_PER_THREAD], int *list_out, int *n_out) {
+    __shared__ int wsum[8];
+    __shared__ int base_s;
+    int cnt = __popc(keepbits), lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < 8; k++) { int t = wsum[k]; wsum[k] = tot; tot += t; }
+        base_s = tot ? atomicAdd(n_out, tot) : 0;
+    }
+    __syncthreads();
+    int pos = base_s + wsum[w] + inc - cnt;
+#pragma unroll
+    for (int u = 0; u < ME_PER_THREAD; u++)
+        if (keepbits & (1u << u)) list_out[pos++] = cell[u];
+}
+
 template <bool LIST, bool BAND>
 __device__ __forceinline__ void minedge_body(const float *__restrict__ z, const int *__restrict__ lab,
                                                  const int *__restrict__ comp, const uint8_t *__restrict__ frozen,
@@ -280,28 +305,61 @@ __device__ __forceinline__ void minedge_body(const float *__restrict__ z, const 
         cell[u] = i;
         if (i >= 0 && minedge_cell<!LIST, BAND>(z, lab, comp, frozen, best, rows, cols, i, r, c)) keepbits |= 1u << u;
     }
-    // append the survivors: block-wide exclusive scan of the per-thread counts, one atomic per CTA
-    __shared__ int wsum[8];
-    __shared__ int base_s;
-    int cnt = __popc(keepbits), lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int inc = cnt;
+    minedge_append(keepbits, cell, list_out, n_out);
+}
+
+// Round 1 on one GPU, cols % 4 == 0: a thread takes FOUR consecutive cells of a row and loads the three label rows and
+// the three elevation rows around them as 16-byte vectors plus the two columns either side (18 loads for 4 cells where
+// the generic form issues up to 18 per cell); every catchment is its own component and nothing is frozen.
+__global__ void __launch_bounds__(256) k_minedge_first4(const float *__restrict__ z, const int *__restrict__ lab,
+                                                        unsigned long long *best, int rows, int cols, int *list_out,
+                                                        int *n_out) {
+    const int c = (blockIdx.x * 16 + (threadIdx.x & 15)) * 4;
+    const int r = blockIdx.y * 16 + (threadIdx.x >> 4);
+    int cell[ME_PER_THREAD] = {-1, -1, -1, -1};
+    unsigned keepbits = 0;
+    if (r > 0 && r < rows - 1 && c < cols) {          // cells of the first / last row carry label 0
+        int L[3][6];
+        float Z[3][6];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += y;
-    }
-    if (lane == 31) wsum[w] = inc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int tot = 0;
-        for (int k = 0; k < 8; k++) { int t = wsum[k]; wsum[k] = tot; tot += t; }
-        base_s = tot ? atomicAdd(n_out, tot) : 0;
-    }
-    __syncthreads();
-    int pos = base_s + wsum[w] + inc - cnt;
+        for (int a = 0; a < 3; a++) {
+            const size_t row = (size_t)(r - 1 + a) * cols + c;
+            const int4 l4 = __ldg(reinterpret_cast<const int4 *>(lab + row));
+            const float4 z4 = __ldg(reinterpret_cast<const float4 *>(z + row));
+            L[a][1] = l4.x; L[a][2] = l4.y; L[a][3] = l4.z; L[a][4] = l4.w;
+            Z[a][1] = z4.x; Z[a][2] = z4.y; Z[a][3] = z4.z; Z[a][4] = z4.w;
+            L[a][0] = c > 0 ? __ldg(lab + row - 1) : 0;
+            Z[a][0] = c > 0 ? __ldg(z + row - 1) : 0.f;
+            L[a][5] = c + 4 < cols ? __ldg(lab + row + 4) : 0;
+            Z[a][5] = c + 4 < cols ? __ldg(z + row + 4) : 0.f;
+        }
 #pragma unroll
-    for (int u = 0; u < ME_PER_THREAD; u++)
-        if (keepbits & (1u << u)) list_out[pos++] = cell[u];
+        for (int j = 0; j < 4; j++) {
+            const int l = L[1][j + 1];
+            const int i = r * cols + c + j;
+            cell[j] = i;
+            if (l == 0) continue;                      // raster border (first / last column)
+            const float zc = Z[1][j + 1];
+            unsigned long long bk = KEY_NONE;
+#pragma unroll
+            for (int dr = -1; dr <= 1; dr++)
+#pragma unroll
+                for (int dc = -1; dc <= 1; dc++) {
+                    if (dr == 0 && dc == 0) continue;
+                    if (L[1 + dr][j + 1 + dc] == l) continue;
+                    const float w = fmaxf(zc, Z[1 + dr][j + 1 + dc]);
+                    const int jn = i + dr * cols + dc;
+                    const int lo = jn < i ? jn : i;
+                    const int code = (dr == 0) ? 0 : ((dr * dc == -1) ? 1 : (dc == 0 ? 2 : 3));
+                    const unsigned long long key = ((unsigned long long)okey32(w) << 32) | (unsigned)(((unsigned)lo << 2) | code);
+                    bk = key < bk ? key : bk;
+                }
+            if (bk == KEY_NONE) continue;
+            if (bk < best[l]) atomicMin(&best[l], bk);
+            keepbits |= 1u << j;
+        }
+    }
+    minedge_append(keepbits, cell, list_out, n_out);
 }
 
 // two kernels from one body: the single-GPU form carries none of the frozen-component logic (compiled into one kernel
@@ -447,6 +505,9 @@ static int boruvka_rounds(const float *dem, const int *lab, int *comp, uint32_t 
             if (frozen)
                 MS_LAUNCH(k_minedge_band<false>, g2m, 256, 0, s, dem, lab, (const int *)comp, (const uint8_t *)frozen, best.p,
                           (int)rows, (int)cols, (const int *)nullptr, 0, lout, counters.p + 1);
+            else if ((cols & 3) == 0 && ((uintptr_t)dem & 15) == 0 && ((uintptr_t)lab & 15) == 0)
+                MS_LAUNCH(k_minedge_first4, dim3(cdiv(cols, 64), cdiv(rows, 16)), 256, 0, s, dem, lab, best.p, (int)rows, (int)cols,
+                          lout, counters.p + 1);
             else
                 MS_LAUNCH(k_minedge<false>, g2m, 256, 0, s, dem, lab, (const int *)comp, (const uint8_t *)frozen, best.p,
                           (int)rows, (int)cols, (const int *)nullptr, 0, lout, counters.p + 1);
