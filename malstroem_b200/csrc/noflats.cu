@@ -949,8 +949,10 @@ __global__ void __launch_bounds__(256) k_nf_init_tile(const float *__restrict__ 
             else {
                 int e = nf_binade((double)f);
                 if (e < -900) atomicOr(&s_bad, 1);
-                atomicMin(&s_elo, e);
-                atomicMax(&s_ehi, e);
+                // nearly every lake cell of a tile lies in the same binade: look before reducing (a third of the
+                // tile's cells otherwise queue on these two words)
+                if (e < *(volatile int *)&s_elo) atomicMin(&s_elo, e);
+                if (e > *(volatile int *)&s_ehi) atomicMax(&s_ehi, e);
             }
         }
     }
