@@ -81,3 +81,24 @@ def test_rings_grouping_and_features():
     assert [f["properties"] for f in feats] == [{"wshed_id": 1}, {"wshed_id": 0}]
     assert feats[0]["geometry"]["coordinates"][0] == [[100.0, 50.0], [106.0, 50.0], [106.0, 44.0], [100.0, 44.0], [100.0, 50.0]]
     assert len(feats[0]["geometry"]["coordinates"]) == 2 and feats[0]["id"] == 0 and feats[1]["id"] == 1
+
+
+def test_oracle_round_trip_property():
+    """hypothesis: any small label raster, both connectivities, with and without a nodata value"""
+    from hypothesis import given, settings, strategies as st
+    from hypothesis.extra import numpy as hnp
+
+    @settings(max_examples=120, deadline=None)
+    @given(hnp.arrays(np.int32, st.tuples(st.integers(1, 9), st.integers(1, 9)), elements=st.integers(0, 3)),
+           st.booleans(), st.sampled_from([None, 0, 2]))
+    def check(a, connect8, nodata):
+        polys = P.polygonize(a, connect8=connect8, nodata=nodata)
+        assert len(polys) == _region_count(a, connect8, nodata)
+        fill = -7 if nodata is None else nodata
+        ras, twice, _ = P.rasterize(polys, a.shape, fill)
+        assert twice == 0 and np.array_equal(ras, a)
+        # one exterior ring per polygon, holes negative, and the areas add up to the cells outside the mask
+        cells = sum(sum(P.area2(g) for g in p["rings"]) // 2 for p in polys)
+        assert cells == int((a != nodata).sum()) if nodata is not None else cells == a.size
+
+    check()
